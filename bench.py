@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the SLR-SFS frame-synthesis hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one scene's clip per GPU: N_FRAMES (60) frames of
+Euler -> forward+backward splat -> normalise at 768x1024, 64 feature channels
+(BASELINE.json configs[1]).  With --gpus N there are N scenes per step and every
+scene's frames are sharded over the N ranks (weak scaling, configs[3]).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "synthesized frames/sec at 768x1024 (N=60)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", default=None, choices=[None, "scatter", "gather"],
+                    help="joint-block algorithm (default: the fastest available)")
+    ap.add_argument("--height", type=int, default=768)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--channels", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=60)
+    ap.add_argument("--motion", default="A", choices=["A", "B", "C"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the CPU baseline sample")
+    return ap.parse_args()
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------
+# clocks: sample nvidia-smi while the timed region runs
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# the reference arm / cpu baseline: the reference's own kernels on the host cores
+# --------------------------------------------------------------------------
+def cpu_frames_per_second(args, n_frames, threads=None):
+    """Times the CPU path on `n_frames` frames of the workload: Euler (oracle port) +
+    the reference's own splat kernels compiled for the CPU (oracle/_ref, all host
+    threads) + the reference's torch glue restated in numpy.  Returns (fps, info)."""
+    import numpy as np
+    import oracle
+    from slr_sfs_b200 import workloads
+    feat, Z, motion = workloads.scene(args.height, args.width, args.channels, args.motion, seed=0)
+    feat, Z, motion = feat.numpy(), Z.numpy(), motion.numpy()
+    use_ref = oracle.ref_available()
+    threads = threads or os.cpu_count() or 1
+    if use_ref:
+        splat = lambda x, f: oracle.ref_softsplat_sum(x, f, threads=threads)
+        kind = "reference"
+    else:
+        splat = oracle.softsplat_sum
+        kind, threads = "port", 1
+    N = args.frames
+    picks = [int(round(i * (N - 1) / max(1, n_frames - 1))) for i in range(n_frames)] if n_frames > 1 else [N // 2]
+    t0 = time.perf_counter()
+    for t in picks:
+        oracle.joint_splat_baseline(feat, Z, motion, (0, t, N - 1), splat=splat)
+    dt = time.perf_counter() - t0
+    info = {"kind": kind, "cores": threads,
+            "sample": "%d of %d frames (t=%s) of the %dx%dx%d workload; splat = %s, Euler = oracle C port (1 thread), "
+                      "glue = numpy" % (n_frames, N, picks, args.height, args.width, args.channels,
+                                        "reference kernel text compiled for CPU (oracle/_ref, OpenMP)" if use_ref
+                                        else "oracle C port")}
+    return n_frames / dt, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(1, args.cpu_frames)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_frames_per_second(args, 1)
+    t0 = time.perf_counter()
+    fps_list = []
+    for _ in range(args.steps):
+        fps, info = cpu_frames_per_second(args, n)
+        fps_list.append(fps)
+    dt = time.perf_counter() - t0
+    fps = args.steps * n / sum(n / f for f in fps_list)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "cpu"),
+        "cpu_baseline": dict(info, value=fps, unit=UNIT),
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, algo):
+    return {"workload": "configs[1]: %dx%d image, %d-ch encoder features, N=%d frames, forward+backward splat + blend"
+                        % (args.height, args.width, args.channels, args.frames),
+            "height": args.height, "width": args.width, "channels": args.channels, "frames_per_clip": args.frames,
+            "motion": args.motion, "algo": algo,
+            "l2": "no flush: one frame's working set (features 201 MB + output 201 MB) exceeds the 126 MB L2",
+            "parallelism": "frames of every scene sharded over ranks (one scene per rank per step)"}
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def frame_block(n_frames, rank, world):
+    """Contiguous frame block of `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n_frames, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    __graft_entry__.build()
+    import slr_sfs_b200 as pkg
+    from slr_sfs_b200 import workloads, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    H, W, C, N = args.height, args.width, args.channels, args.frames
+    P = H * W
+    algo = args.algo or ("gather" if hasattr(pkg.JointSplat, "frame") else "scatter")
+
+    # one scene per rank ("encoded" on that rank); every rank synthesises its frame
+    # block of every scene.  Host copies live in pinned memory for the e2e leg.
+    scenes_host = []
+    for s in range(world):
+        feat, Z, motion = workloads.scene(H, W, C, args.motion, seed=s)
+        scenes_host.append((feat, Z, motion))
+    own = tuple(t.pin_memory() for t in scenes_host[rank])
+    lo, hi = frame_block(N, rank, world)
+
+    def make_joint(feat, Z, motion):
+        return pkg.JointSplat(feat, Z, motion)
+
+    def synth(js, t, out=None):
+        fn = js.frame if algo == "gather" else js.frame_scatter
+        return fn((0, t, N - 1))
+
+    # resident inputs for the `value` leg
+    resident = [tuple(t.to(dev) for t in sc) for sc in scenes_host]
+    torch.cuda.synchronize()
+
+    def step_resident(record=None):
+        for sc in resident:
+            js = make_joint(*sc)
+            for t in range(lo, hi):
+                out = synth(js, t)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.kernel_timing(True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ktimes = _lib.kernel_timing(False)
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        tl = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(tl)
+        launches = int(tl.item())
+    frames_total = world * N * args.steps          # world scenes x N frames per step, over all ranks
+    value = frames_total / (ms / 1000.0)
+
+    # ---------------- e2e: host buffers in, host buffers out, every step -----------------
+    e2e = None
+    if not args.no_e2e:
+        n_slots = 3
+        ring = [torch.empty(1, C, H, W, dtype=torch.float32).pin_memory() for _ in range(n_slots)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        slot_free = [torch.cuda.Event() for _ in range(n_slots)]
+        in_bytes = sum(t.numel() * 4 for t in own)
+        out_bytes = (hi - lo) * world * C * P * 4
+
+        def step_e2e():
+            # H2D of this rank's scene, broadcast of every scene from its owner, synthesis of
+            # this rank's frame block of every scene, D2H of every synthesised frame.
+            mine = tuple(t.to(dev, non_blocking=True) for t in own)
+            k = 0
+            for s in range(world):
+                if world > 1:
+                    sc = mine if s == rank else tuple(torch.empty_like(t, device=dev) for t in own)
+                    for t in sc:
+                        dist.broadcast(t, src=s)
+                else:
+                    sc = mine
+                js = make_joint(*sc)
+                for t in range(lo, hi):
+                    out = synth(js, t)
+                    done = torch.cuda.Event()
+                    done.record()
+                    slot = k % n_slots
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(done)
+                        out.record_stream(copy_stream)
+                        ring[slot].copy_(out, non_blocking=True)
+                    k += 1
+            copy_stream.synchronize()
+
+        for _ in range(min(args.warmup, 1)):
+            step_e2e()
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        steps_e2e = max(1, min(args.steps, 2))
+        t0.record()
+        for _ in range(steps_e2e):
+            step_e2e()
+        t1.record()
+        barrier()
+        ms_e = t0.elapsed_time(t1)
+        if world > 1:
+            tms = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms_e = float(tms.item())
+        e2e = {"value": world * N * steps_e2e / (ms_e / 1000.0), "unit": UNIT,
+               "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
+               "steps": steps_e2e,
+               "note": "per step: pinned-host features+Z+motion -> device (+ NCCL broadcast when N>1), every "
+                       "synthesised [C,H,W] fp32 frame -> pinned host ring (3 slots) on a copy stream"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        # dominant kernel: the one with the largest total time in the timed region
+        roof = None
+        if ktimes:
+            name, (tot_ms, calls) = max(ktimes.items(), key=lambda kv: kv[1][0])
+            alg_bytes = _lib.algorithmic_bytes(name, C, P)
+            avg_s = tot_ms / 1000.0 / calls
+            achieved = alg_bytes / avg_s / 1e9
+            share = tot_ms / (ms if world == 1 else ms)
+            roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_s * 1e6,
+                    "share_of_step": share,
+                    "all_kernels_ms_per_frame": {k: v[0] / max(1, (hi - lo) * world * args.steps) for k, v in ktimes.items()}}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            fps, info = cpu_frames_per_second(args, max(1, args.cpu_frames))
+            cpu = dict(info, value=fps, unit=UNIT)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, algo), "clocks": clocks, "gpu_launches": launches,
+            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "whole_path_roofline_frac": value / world / (peak * 1e9 / (4.0 * P * (4 * C + 5))),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

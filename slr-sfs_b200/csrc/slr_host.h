@@ -1,0 +1,24 @@
+// Host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slr_splat.h"
+
+namespace slr_host {
+// Records `msg` as the calling thread's last error and returns `code`.
+int fail(int code, const char* msg);
+// SM count of the current device (cached per device).
+int sm_count();
+}  // namespace slr_host
+
+#define SLR_CHECK_ARGS(cond, msg) \
+    do { if (!(cond)) return slr_host::fail(-1, msg); } while (0)
+
+#define SLR_CUDA(expr) \
+    do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return slr_host::fail((int)e_, cudaGetErrorString(e_)); } while (0)
+
+// After a kernel launch: report launch-configuration errors without synchronising.
+#define SLR_LAUNCH_STATUS() \
+    ([]() -> int { cudaError_t e_ = cudaGetLastError(); \
+                   return e_ == cudaSuccess ? 0 : slr_host::fail((int)e_, cudaGetErrorString(e_)); })()

@@ -1,0 +1,106 @@
+"""The joint-splat block of the reference models as one fused operator.
+
+What ``forward_flow`` does between the encoder and the decoder
+(models/animating_softmax_splating.py:847-924; 2-layer variant
+models/animating_softmax_splating_2layers_alpha_seperate.py:921-1045):
+
+    D+ = euler_integration( flow, t - start)         D- = euler_integration(-flow, end - t + 1)
+    Zn = Z - Z.max()                                  alpha = 1 - (t - start) / (end - start + 1)
+    acc = splat([fs*e^Zn*alpha, e^Zn*alpha], D+) + splat([fs*e^Zn*(1-alpha), e^Zn*(1-alpha)], D-)
+    gen_fs = acc[:, :-1] / clamp(acc[:, -1:], 1e-8)
+
+The reference runs this as ~40 eager torch ops, two Euler integrations restarted
+from zero and two cupy launches per frame.  Here a frame is a handful of launches
+of the sm_100a library, nothing is synchronised with the host, and no
+intermediate ``tenInput`` tensor is materialised.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+EPS = 1e-8
+
+
+def blend_alpha(start, mid, end):
+    """alpha of animating_softmax_splating.py:860, computed in fp32 like the reference."""
+    a = np.float32(mid - start) / np.float32(end - start + 1)
+    return float(np.float32(1.0) - a)
+
+
+def _index_triplet(index):
+    if torch.is_tensor(index):
+        index = index.reshape(-1).tolist()
+    start, mid, end = [int(v) for v in index]
+    return start, mid, end
+
+
+def _req(t, name):
+    assert t.is_cuda, "%s must be a CUDA tensor (no CPU path)" % name
+    assert t.dtype == torch.float32 and t.is_contiguous(), "%s must be contiguous fp32" % name
+    return t
+
+
+class JointSplat:
+    """Frame synthesiser for one scene: features [1,C,H,W], importance Z [1,1,H,W]
+    and Eulerian motion [1,2,H,W] are fixed, frames t = start..end are produced on
+    demand.  ``z_mode``: 'max' (Z - Z.max(), :855), 'v1' (Z as is, :853).
+
+    ``tail`` ([1,n_tail,H,W], optional) carries the 2-layer model's extra
+    pre-weighted channels (a_f*e^A, e^A with use_alpha0_as_blending_weight,
+    2layers...py:967-972; a_f*e^Zn without, :974-976); they are blended with
+    alpha / 1-alpha and splatted like the features and come back un-normalised
+    positions C..C+n_tail-1 of the accumulator.
+    """
+
+    def __init__(self, features, Z, motion, z_mode="max", tail=None):
+        assert features.dim() == 4 and features.shape[0] == 1
+        self.feat = _req(features.detach(), "features")
+        self.C, self.H, self.W = features.shape[1:]
+        self.Z = _req(Z.detach().reshape(1, 1, self.H, self.W), "Z")
+        self.motion = _req(motion.detach().reshape(1, 2, self.H, self.W), "motion")
+        self.tail = None if tail is None else _req(tail.detach(), "tail")
+        self.n_tail = 0 if tail is None else tail.shape[1]
+        assert z_mode in ("max", "v1")
+        self.device = features.device
+        with torch.cuda.device(self.device):
+            self.stream = None
+            if z_mode == "max":
+                self.zsub = torch.empty(1, dtype=torch.float32, device=self.device)
+                _lib.call("slr_reduce_max", _lib.ptr(self.Z), self.Z.numel(), _lib.ptr(self.zsub),
+                          _lib.current_stream(self.device))
+            else:
+                self.zsub = None
+
+    # -- scatter variant: Euler x2 -> atomic scatter of both directions -> normalise
+    def accumulate_scatter(self, index, alpha=None):
+        start, mid, end = _index_triplet(index)
+        if alpha is None:
+            alpha = blend_alpha(start, mid, end)
+        H, W, C = self.H, self.W, self.C
+        dev = self.device
+        disp = torch.empty(2, 2, H, W, dtype=torch.float32, device=dev)
+        acc = torch.empty(1, C + self.n_tail + 1, H, W, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            s = _lib.current_stream(dev)
+            _lib.call("slr_euler", _lib.ptr(self.motion), 1.0, mid - start, _lib.ptr(disp[0]), None, H, W, s)
+            _lib.call("slr_euler", _lib.ptr(self.motion), -1.0, end - mid + 1, _lib.ptr(disp[1]), None, H, W, s)
+            _lib.call("slr_joint_scatter", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self.zsub),
+                      _lib.ptr(self.tail), self.n_tail, _lib.ptr(disp[0]), _lib.ptr(disp[1]), alpha,
+                      _lib.ptr(acc), C, H, W, s)
+        return acc
+
+    def normalize(self, acc, n_out=None, norm_ch=None, want_mask=False):
+        n_acc = acc.shape[1]
+        n_out = self.C if n_out is None else n_out
+        norm_ch = n_acc - 1 if norm_ch is None else norm_ch
+        out = torch.empty(1, n_out, self.H, self.W, dtype=torch.float32, device=self.device)
+        mask = torch.empty(1, 1, self.H, self.W, dtype=torch.float32, device=self.device) if want_mask else None
+        with torch.cuda.device(self.device):
+            _lib.call("slr_normalize", _lib.ptr(acc), _lib.ptr(out), _lib.ptr(mask), n_out, norm_ch, n_acc,
+                      EPS, self.H, self.W, _lib.current_stream(self.device))
+        return (out, mask) if want_mask else out
+
+    def frame_scatter(self, index, alpha=None):
+        """gen_fs [1,C,H,W] for index = (start, t, end)."""
+        return self.normalize(self.accumulate_scatter(index, alpha))

@@ -1,0 +1,117 @@
+"""GPU: the joint block (Euler -> forward+backward splat -> normalise) against the
+reference models' golden outputs and against the oracle, small and full size."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__
+    __graft_entry__.build()
+    import slr_sfs_b200
+    return slr_sfs_b200
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def paths(js):
+    out = [("scatter", js.frame_scatter)]
+    if hasattr(js, "frame"):
+        out.append(("gather", js.frame))
+    return out
+
+
+def test_baseline_joint_vs_reference_model_golden(pkg, golden_joint):
+    j = golden_joint
+    N = int(j["N"])
+    for z_mode in ("max", "v1"):
+        js = pkg.JointSplat(cu(j["feat"]), cu(j["Z"]), cu(j["motion"]), z_mode=z_mode)
+        for t in (0, 3, N - 1):
+            want = j[f"baseline/{z_mode}/t{t}/gen_fs"]
+            for name, fn in paths(js):
+                got = fn((0, t, N - 1)).cpu().numpy()
+                assert rel_err(got, want) <= TOL, (z_mode, t, name)
+                assert np.all(got[want == 0.0] == 0.0)       # holes stay exactly zero
+
+
+def test_two_layer_joint_vs_reference_model_golden(pkg, golden_joint):
+    j = golden_joint
+    N = int(j["N"])
+    ao = torch.from_numpy(j["alpha_encoder_out"]).cuda()
+    a_bg = torch.sigmoid(ao[:, 0:1])
+    a_f = ao[:, 1:2]
+    Z = cu(j["Z"])
+    for alpha0 in (True, False):
+        if alpha0:
+            A = torch.sigmoid(a_f) / torch.clamp(torch.sigmoid(a_f) + a_bg, min=1e-8)
+            tail = torch.cat([a_f * A.exp(), A.exp()], 1).contiguous()
+        else:
+            tail = (a_f * (Z - Z.max()).exp()).contiguous()
+        js = pkg.JointSplat(cu(j["feat"]), Z, cu(j["motion"]), tail=tail)
+        C = js.C
+        for t in (0, 3, N - 1):
+            tag = f"twolayer/{'alpha0' if alpha0 else 'plain'}/t{t}"
+            a = pkg.synthesis.blend_alpha(0, t, N - 1)
+            a = min(max(a, float(np.float32(1.0 / 600.0))), float(np.float32(599.0 / 600.0)))   # 2layers...py:952
+            acc = js.accumulate_scatter((0, t, N - 1), alpha=a)
+            gen = js.normalize(acc).cpu().numpy()
+            if alpha0:
+                alpha_fluid = (acc[:, C:C + 1] / torch.clamp(acc[:, C + 1:C + 2], min=1e-8)).cpu().numpy()
+            else:
+                alpha_fluid = (acc[:, C:C + 1] / torch.clamp(acc[:, C + 1:C + 2], min=1e-8)).cpu().numpy()
+            assert rel_err(gen, j[f"{tag}/gen_fs"]) <= TOL, tag
+            assert rel_err(alpha_fluid, j[f"{tag}/alpha_fluid"]) <= TOL, tag
+
+
+@pytest.mark.parametrize("motion", ["A", "B", "C"])
+def test_joint_vs_oracle_medium(pkg, motion):
+    from slr_sfs_b200 import workloads
+    H, W, C, N = 96, 128, 16, 20
+    feat, Z, m = workloads.scene(H, W, C, motion, seed=3)
+    js = pkg.JointSplat(feat.cuda(), Z.cuda(), m.cuda())
+    for t in (0, 7, N - 1):
+        want = oracle.joint_splat_baseline(feat.numpy(), Z.numpy(), m.numpy(), (0, t, N - 1))
+        for name, fn in paths(js):
+            got = fn((0, t, N - 1)).cpu().numpy()
+            assert rel_err(got, want) <= TOL, (motion, t, name)
+
+
+def test_joint_full_size_768x1024(pkg):
+    """BASELINE.json configs[1] shape: 768x1024, 64 channels, N=60; two frames against the oracle."""
+    from slr_sfs_b200 import workloads
+    H, W, C, N = 768, 1024, 64, 60
+    feat, Z, m = workloads.scene(H, W, C, "A", seed=0)
+    js = pkg.JointSplat(feat.cuda(), Z.cuda(), m.cuda())
+    for t in (1, 40):
+        want = oracle.joint_splat_baseline(feat.numpy(), Z.numpy(), m.numpy(), (0, t, N - 1))
+        for name, fn in paths(js):
+            got = fn((0, t, N - 1)).cpu().numpy()
+            assert rel_err(got, want) <= TOL, (t, name)
+            assert np.array_equal(got == 0.0, want == 0.0) or np.mean((got == 0.0) != (want == 0.0)) < 1e-6
+
+
+def test_blend_is_convex_combination_property(pkg):
+    """Size-independent property: with constant features the normalised output is that
+    constant wherever anything landed (softmax weights cancel), 0 in holes."""
+    H, W, C, N = 768, 1024, 8, 60
+    from slr_sfs_b200 import workloads
+    _, Z, m = workloads.scene(H, W, C, "A", seed=2)
+    feat = torch.full((1, C, H, W), 0.75)
+    js = pkg.JointSplat(feat.cuda(), Z.cuda(), m.cuda())
+    for name, fn in paths(js):
+        out = fn((0, 30, N - 1))
+        covered = out[:, 0] != 0
+        assert covered.float().mean() > 0.5
+        vals = out[:, :, covered[0]]
+        close = torch.isclose(vals, torch.tensor(0.75, device="cuda"), rtol=1e-5, atol=0)
+        # cells whose total weight is below the 1e-8 clamp legitimately come out smaller
+        assert close.float().mean() > 0.9999 and bool((vals <= 0.75 * (1 + 1e-5)).all()), name
