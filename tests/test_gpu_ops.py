@@ -54,8 +54,12 @@ def test_backward_vs_reference_golden(pkg, golden_softsplat, case):
 def test_backward_respects_needs_input_grad(pkg):
     x = torch.randn(1, 3, 8, 8, device="cuda", requires_grad=True)
     f = torch.rand(1, 2, 8, 8, device="cuda")          # GT motion: no grad wanted
-    pkg.softsplat._FunctionSoftsplat.apply(x, f).sum().backward()
+    out = pkg.softsplat._FunctionSoftsplat.apply(x, f)
+    out.backward(torch.ones_like(out))
     assert x.grad is not None and f.grad is None
+    # like the reference (softsplat.py:438) a non-contiguous gradOutput is an assertion error
+    with pytest.raises(AssertionError):
+        pkg.softsplat._FunctionSoftsplat.apply(x, f).sum().backward()
 
 
 @pytest.mark.parametrize("case", SPLAT_CASES)
