@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--channels", type=int, default=64)
     ap.add_argument("--frames", type=int, default=60)
     ap.add_argument("--motion", default="A", choices=["A", "B", "C"])
+    ap.add_argument("--batch", type=int, default=0, help="frames per gather launch (0 = library default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the CPU baseline sample")
@@ -225,11 +226,30 @@ def main():
     lo, hi = frame_block(N, rank, world)
 
     def make_joint(feat, Z, motion):
-        return pkg.JointSplat(feat, Z, motion)
+        js = pkg.JointSplat(feat, Z, motion)
+        if args.batch:
+            js.batch = args.batch
+        return js
 
-    def synth(js, t, out=None):
-        fn = js.frame if algo == "gather" else js.frame_scatter
-        return fn((0, t, N - 1))
+    n_mine = hi - lo
+    nbuf = min(n_mine, args.batch or pkg.JointSplat.batch)
+    frame_buf = torch.empty(nbuf, C, H, W, dtype=torch.float32, device=dev) if algo == "gather" else None
+
+    def synth_block(js, on_frames=None):
+        """Synthesise this rank's frame block of one scene; on_frames(tensor [k,C,H,W]) consumes
+        each finished group of frames (the decoder's place; the e2e leg copies them out)."""
+        if algo == "gather":
+            for b0 in range(lo, hi, nbuf):
+                nb = min(nbuf, hi - b0)
+                out = js.frames(0, N - 1, b0, nb, out=frame_buf[:nb])
+                if on_frames is not None:
+                    on_frames(out)
+        else:
+            for t in range(lo, hi):
+                out = js.frame_scatter((0, t, N - 1))
+                if on_frames is not None:
+                    on_frames(out)
+        return out
 
     # resident inputs for the `value` leg
     resident = [tuple(t.to(dev) for t in sc) for sc in scenes_host]
@@ -237,9 +257,7 @@ def main():
 
     def step_resident(record=None):
         for sc in resident:
-            js = make_joint(*sc)
-            for t in range(lo, hi):
-                out = synth(js, t)
+            out = synth_block(make_joint(*sc))
         return out
 
     def barrier():
@@ -282,7 +300,6 @@ def main():
         n_slots = 3
         ring = [torch.empty(1, C, H, W, dtype=torch.float32).pin_memory() for _ in range(n_slots)]
         copy_stream = torch.cuda.Stream(device=dev)
-        slot_free = [torch.cuda.Event() for _ in range(n_slots)]
         in_bytes = sum(t.numel() * 4 for t in own)
         out_bytes = (hi - lo) * world * C * P * 4
 
@@ -290,7 +307,21 @@ def main():
             # H2D of this rank's scene, broadcast of every scene from its owner, synthesis of
             # this rank's frame block of every scene, D2H of every synthesised frame.
             mine = tuple(t.to(dev, non_blocking=True) for t in own)
-            k = 0
+            state = {"k": 0}
+
+            def copy_out(frames):
+                done = torch.cuda.Event()
+                done.record()
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    for i in range(frames.shape[0]):
+                        ring[state["k"] % n_slots].copy_(frames[i:i + 1], non_blocking=True)
+                        state["k"] += 1
+                    copied = torch.cuda.Event()
+                    copied.record()
+                # the frame buffer is reused by the next batch: do not overwrite before it is copied out
+                torch.cuda.current_stream().wait_event(copied)
+
             for s in range(world):
                 if world > 1:
                     sc = mine if s == rank else tuple(torch.empty_like(t, device=dev) for t in own)
@@ -298,17 +329,7 @@ def main():
                         dist.broadcast(t, src=s)
                 else:
                     sc = mine
-                js = make_joint(*sc)
-                for t in range(lo, hi):
-                    out = synth(js, t)
-                    done = torch.cuda.Event()
-                    done.record()
-                    slot = k % n_slots
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(done)
-                        out.record_stream(copy_stream)
-                        ring[slot].copy_(out, non_blocking=True)
-                    k += 1
+                synth_block(make_joint(*sc), copy_out)
             copy_stream.synchronize()
 
         for _ in range(min(args.warmup, 1)):
@@ -339,7 +360,8 @@ def main():
         roof = None
         if ktimes:
             name, (tot_ms, calls) = max(ktimes.items(), key=lambda kv: kv[1][0])
-            alg_bytes = _lib.algorithmic_bytes(name, C, P)
+            frames_per_call = (hi - lo) * world * args.steps / calls if name.startswith("slr_clip") else 1
+            alg_bytes = _lib.algorithmic_bytes(name, C, P) * frames_per_call
             avg_s = tot_ms / 1000.0 / calls
             achieved = alg_bytes / avg_s / 1e9
             share = tot_ms / (ms if world == 1 else ms)

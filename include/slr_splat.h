@@ -87,20 +87,19 @@ int slr_euler(const float* motion, float sign, int T, float* disp, float* visibl
 /* max over a tensor into a device scalar (Z.max(), animating_softmax_splating.py:855). */
 int slr_reduce_max(const float* x, int64_t n, float* out_scalar, slr_stream_t stream);
 
-/* Scatter variant of the joint block ("algorithm A", kept as the measured
- * baseline for the gather pipeline below).  For every source pixel and both
- * directions d in {forward, backward}:
- *   acc[c]      += ((feat[c] * e^{Z - zsub}) * a_d) * w    c < C
- *   acc[C + j]  += ((extra_val[j] * e_j) * a_d) * w         j < n_extra   (2-layer alpha channels)
- *   acc[last]   += (e^{Z - zsub} * a_d) * w
- * with a_fwd = alpha, a_bwd = 1 - alpha, and displacement fields disp_f / disp_b
- * ([2,H,W] each, e.g. from slr_euler).  zsub points at a device scalar (Z.max())
- * or is NULL (no subtraction, use_softmax_splatter_v1).  `splat_in` optional
- * channels: `tail` is [n_tail,H,W] of already-weighted extra channels that are
- * multiplied by a_d and splatted as they are (the 2-layer model's
- * a_f*e^A, e^A planes, 2layers...py:967-972); they land in acc[C .. C+n_tail).
- * The e^Z weight plane lands in acc[C+n_tail].  acc is [C+n_tail+1,H,W] and is
- * cleared first. */
+/* Scatter variant of the joint block ("algorithm A": the design BASELINE.json's
+ * north_star sketches; kept as the measured baseline of the gather pipeline
+ * below).  acc is [C + n_tail + 1, H, W] and is cleared first; for every source
+ * pixel and both directions d in {forward, backward}, with a_fwd = alpha,
+ * a_bwd = 1 - alpha and displacement fields disp_f / disp_b ([2,H,W], e.g. from
+ * slr_euler):
+ *   acc[c]          += ((feat[c] * e^(Z - *zsub)) * a_d) * w     c < C
+ *   acc[C + j]      += (tail[j] * a_d) * w                        j < n_tail
+ *   acc[C + n_tail] += (e^(Z - *zsub) * a_d) * w                  (the normaliser)
+ * zsub points at a device scalar (Z.max(), animating_softmax_splating.py:855) or
+ * is NULL (use_softmax_splatter_v1, :853).  tail ([n_tail,H,W], may be NULL) holds
+ * the 2-layer model's extra, already weighted channels (a_f*e^A and e^A,
+ * 2layers...py:967-972, or a_f*e^Z, :974-976). */
 int slr_joint_scatter(const float* feat, const float* z, const float* zsub,
                       const float* tail, int n_tail,
                       const float* disp_f, const float* disp_b, float alpha,
@@ -111,6 +110,54 @@ int slr_joint_scatter(const float* feat, const float* z, const float* zsub,
  * acc[norm_ch] > eps (2layers...py:1039).  Exact-zero holes stay exactly 0. */
 int slr_normalize(const float* acc, float* out, float* mask, int64_t n_out, int64_t norm_ch,
                   int64_t n_acc, float eps, int64_t H, int64_t W, slr_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Clip level ("algorithm G", the fast path): bin source pixels by destination
+ * tile, then gather with register accumulators and write normalised frames
+ * directly.  Same results as slr_euler x2 + slr_joint_scatter + slr_normalize
+ * up to fp32 summation order.  The unit of work is the reference's frame loop
+ * (test_animating/test_v1_4eval_rawsize.py:233-239): for t in range(N):
+ * index = [start, t, end]; forward_flow(batch).
+ * ------------------------------------------------------------------------- */
+
+/* Bytes of the per-scene buffer slr_scene_prep fills. */
+size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W);
+
+/* Once per scene (features, Z and motion are constant over the clip): writes the
+ * pre-weighted, channel-interleaved features feat[c]*e^(Z - *zsub) and the scalar
+ * planes (tail..., e^(Z - *zsub)) into `scene` (16-byte aligned,
+ * slr_scene_bytes).  zsub / tail as in slr_joint_scatter; n_tail <= 2. */
+int slr_scene_prep(const float* feat, const float* z, const float* zsub,
+                   const float* tail, int n_tail, void* scene,
+                   int64_t C, int64_t H, int64_t W, slr_stream_t stream);
+
+/* Bytes of scratch slr_clip_frames needs for a batch of n_frames. */
+size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames);
+
+/* Synthesise frames t0 .. t0+n_frames-1 (n_frames <= 64) of the clip whose index
+ * triplets are [start, t, end]: forward displacement = t - start Euler steps of
+ * +motion, backward = end - t + 1 steps of -motion
+ * (animating_softmax_splating.py:847-848), alpha = 1 - (t-start)/(end-start+1)
+ * clamped to [alpha_lo, alpha_hi] (:860; 2layers...py:952 clamps to
+ * [1/600, 599/600], the baseline model does not clamp: pass 0 and 1).
+ *   out  [n_frames, C, H, W]  features / max(norm, 1e-8)           (:923-924)
+ *   aux  [n_frames, n_tail + 1, H, W] or NULL: raw sums of the tail channels and
+ *        the norm (the 2-layer model divides them itself, 2layers...py:1038-1045)
+ *   mask [n_frames, H, W] or NULL: norm > 1e-8                      (2layers...py:1039)
+ * workspace: slr_clip_workspace_bytes(H, W, n_frames) bytes, 16-byte aligned.
+ * slr_clip_frames = slr_clip_plan (Euler chains, landing table, destination-tile
+ * bins; depends on the motion only) followed by slr_clip_gather (the gather
+ * kernel) on the same workspace. */
+int slr_clip_plan(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
+                  int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream);
+int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t H, int64_t W,
+                    int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                    float* out, float* aux, float* mask,
+                    const void* workspace, size_t workspace_bytes, slr_stream_t stream);
+int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tail,
+                    int64_t H, int64_t W, int start, int end, int t0, int n_frames,
+                    float alpha_lo, float alpha_hi, float* out, float* aux, float* mask,
+                    void* workspace, size_t workspace_bytes, slr_stream_t stream);
 
 #ifdef __cplusplus
 }

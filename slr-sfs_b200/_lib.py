@@ -29,8 +29,17 @@ SIGNATURES = {
     "slr_reduce_max": [_f32p, _i64, _f32p, _strm],
     "slr_joint_scatter": [_f32p, _f32p, _f32p, _f32p, _int, _f32p, _f32p, _flt, _f32p, _i64, _i64, _i64, _strm],
     "slr_normalize": [_f32p, _f32p, _f32p, _i64, _i64, _i64, _flt, _i64, _i64, _strm],
+    "slr_scene_bytes": [_i64, _int, _i64, _i64],
+    "slr_scene_prep": [_f32p, _f32p, _f32p, _f32p, _int, _f32p, _i64, _i64, _i64, _strm],
+    "slr_clip_workspace_bytes": [_i64, _i64, _int],
+    "slr_clip_plan": [_f32p, _i64, _i64, _int, _int, _int, _int, _f32p, ctypes.c_size_t, _strm],
+    "slr_clip_gather": [_f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
+                        _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
+    "slr_clip_frames": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
+                        _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
 }
-_OTHER_RESTYPE = {"slr_last_error_string": ctypes.c_char_p}
+_OTHER_RESTYPE = {"slr_last_error_string": ctypes.c_char_p, "slr_scene_bytes": ctypes.c_size_t,
+                  "slr_clip_workspace_bytes": ctypes.c_size_t}
 
 _lib = None
 _lock = threading.Lock()
@@ -86,7 +95,8 @@ def current_stream(device):
 KERNELS_PER_CALL = {
     "slr_softsplat_sum_fwd": 1, "slr_softsplat_grad_input": 1, "slr_softsplat_grad_flow": 1,
     "slr_maxsplat_fwd": 2, "slr_maxwarpnorm": 3, "slr_euler": 1, "slr_reduce_max": 2,
-    "slr_joint_scatter": 1, "slr_normalize": 1,
+    "slr_joint_scatter": 1, "slr_normalize": 1, "slr_scene_prep": 1, "slr_clip_frames": 4,
+    "slr_clip_plan": 3, "slr_clip_gather": 1,
 }
 _launches = 0
 _timing = None          # None, or list of (name, start_event, end_event)
@@ -123,6 +133,8 @@ def algorithmic_bytes(name, C, P, n_tail=0):
         return plane * (2 * C + 1)
     if name == "slr_euler":
         return plane * 4
+    if name in ("slr_clip_frames", "slr_clip_gather"):        # per FRAME: same unit as slr_joint_scatter (section 8d, 2C+4 planes)
+        return plane * (2 * C + 4 + 2 * n_tail)
     return 0
 
 

@@ -1,0 +1,576 @@
+// Clip pipeline ("algorithm G"): the joint block of the reference models
+// (/root/reference/models/animating_softmax_splating.py:847-924) restructured
+// for sm_100a as  bin-by-destination-tile  +  gather with register accumulators.
+//
+// Why not scatter: a frame at 768x1024x65 is 2 directions x 4 corners x 51 M
+// elements = 409 M fp32 atomics.  The measured L2 reduction rate on B200
+// (profiles/r01: 0.65 ms per frame) is 10x the HBM time of the same bytes.  The
+// splat weights do not depend on the channel, so the scatter is a sparse
+// (destination x source) matrix applied to all channels: we build that sparse
+// structure once per frame from the displacement alone (2 planes, cheap) and then
+// every destination pixel PULLS its contributions, accumulates them in registers
+// and writes the normalised result once.  No feature atomics, no accumulator
+// round trip through HBM, no separate normalise pass.
+//
+//   scene_prep      once per scene: G4[g][p] = feat[4g..4g+3][p] * e^(Z[p]-zsub) as
+//                   float4 (one 16-byte load later fetches 4 channels of a source
+//                   pixel), S[j][p] = scalar planes (2-layer tail channels, e^Z).
+//   euler_table     once per batch of frames: both Euler chains in registers,
+//                   landing coordinates of every (frame, direction, pixel), and
+//                   per-(frame, destination tile) entry counts.
+//   bin_scan        exclusive scan of the counts -> bin offsets.
+//   bin_fill        every (pixel, direction) is appended to the bins of the
+//                   destination tiles its 2x2 footprint touches.
+//   gather          one CTA per (destination tile 32x8, frame): expands its bin
+//                   into per-destination-pixel (source, weight) lists in shared
+//                   memory, each thread loads its list into registers and loops
+//                   over the channel groups: LDG.128 + 4 FMA per (pair, group).
+#include "slr_common.cuh"
+#include "slr_host.h"
+#include <algorithm>
+
+namespace slr {
+
+constexpr int TW = 32;                 // destination tile width  (one warp per tile row)
+constexpr int TH = 8;                  // destination tile height
+constexpr int TILE = TW * TH;          // threads per gather CTA, one destination pixel each
+constexpr int kDepth = 16;             // (source, weight) pairs a thread holds in registers
+constexpr int kChunk = 1024;           // bin entries expanded per pass
+constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the parameters)
+constexpr unsigned kDirBit = 0x80000000u;
+
+struct FrameAlphas { float a[kMaxFrames]; };
+
+// Destination tiles touched by a footprint, in a fixed order shared by the count
+// and the fill pass.  East / south columns only count when their weight is
+// non-zero (landing exactly on a cell -- static pixels -- touches one cell).
+__device__ __forceinline__ void touched_tiles(const Footprint& f, float ox, float oy, int H, int W,
+                                              int tiles_x, int out[4])
+{
+    out[0] = out[1] = out[2] = out[3] = -1;
+    if (f.ok == 0u) return;
+    const bool c0 = f.x0 >= 0 && f.x0 < W;
+    const bool c1 = f.x0 + 1 >= 0 && f.x0 + 1 < W && ox > (float)f.x0;
+    const bool r0 = f.y0 >= 0 && f.y0 < H;
+    const bool r1 = f.y0 + 1 >= 0 && f.y0 + 1 < H && oy > (float)f.y0;
+    const int tc0 = c0 ? f.x0 / TW : -1;
+    int tc1 = c1 ? (f.x0 + 1) / TW : -1;
+    const int tr0 = r0 ? f.y0 / TH : -1;
+    int tr1 = r1 ? (f.y0 + 1) / TH : -1;
+    if (tc1 == tc0) tc1 = -1;
+    if (tr1 == tr0) tr1 = -1;
+    if (tr0 >= 0 && tc0 >= 0) out[0] = tr0 * tiles_x + tc0;
+    if (tr0 >= 0 && tc1 >= 0) out[1] = tr0 * tiles_x + tc1;
+    if (tr1 >= 0 && tc0 >= 0) out[2] = tr1 * tiles_x + tc0;
+    if (tr1 >= 0 && tc1 >= 0) out[3] = tr1 * tiles_x + tc1;
+}
+
+// Warp-aggregated "reserve one slot in counters[key]" for the lanes whose key >= 0.
+// All 32 lanes must call.  Returns the lane's slot (undefined for key < 0).
+__device__ __forceinline__ unsigned warp_reserve(unsigned* counters, int key)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (key >= 0 && (int)lane == leader) base = atomicAdd(counters + key, (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+}
+
+// ---------------------------------------------------------------------------
+// scene_prep: pre-weighted, channel-interleaved features
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, const float* __restrict__ zsub,
+                  const float* __restrict__ tail, int n_tail, float4* __restrict__ G4, float* __restrict__ S,
+                  int C, int64_t P)
+{
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= P) return;
+    const float ez = expf(z[p] - (zsub ? *zsub : 0.0f));
+    const int groups = (C + 3) >> 2;
+    const int g0 = blockIdx.y * ((groups + gridDim.y - 1) / gridDim.y);
+    const int g1 = min(groups, g0 + (groups + (int)gridDim.y - 1) / (int)gridDim.y);
+    for (int g = g0; g < g1; ++g) {
+        float v[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * g + j;
+            v[j] = c < C ? feat[(int64_t)c * P + p] * ez : 0.0f;
+        }
+        G4[(int64_t)g * P + p] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (blockIdx.y == 0) {
+        for (int j = 0; j < n_tail; ++j) S[(int64_t)j * P + p] = tail[(int64_t)j * P + p];
+        S[(int64_t)n_tail * P + p] = ez;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// euler_table: both chains for frames f = 0..n-1 of the batch.
+//   forward  steps of frame f: steps_f0 + f      (t - start)
+//   backward steps of frame f: steps_b0 - f      (end - t + 1)
+// Same arithmetic as euler_kernel (bit-identical displacements); the landing
+// coordinate stored is x + (dest - x), i.e. exactly what the reference splat
+// computes from the displacement (softsplat.py:169-170).
+// ---------------------------------------------------------------------------
+struct EulerState { float dx, dy; bool invalid; };
+
+__device__ __forceinline__ void euler_step(EulerState& s, const float* __restrict__ motion, float sign,
+                                           float cx, float cy, float xmax, float ymax, int W, int64_t P)
+{
+    const int64_t at = (int64_t)rintf(s.dy) * W + (int64_t)rintf(s.dx);
+    const float mx = __fmul_rn(sign, __ldg(motion + at));
+    const float my = __fmul_rn(sign, __ldg(motion + P + at));
+    s.dx = __fadd_rn(s.dx, mx);
+    s.dy = __fadd_rn(s.dy, my);
+    s.invalid = s.invalid || s.dx > xmax || s.dx < 0.0f || s.dy > ymax || s.dy < 0.0f;
+    if (s.invalid) { s.dx = cx; s.dy = cy; }
+}
+
+__global__ void __launch_bounds__(256)
+euler_table_kernel(const float* __restrict__ motion, int H, int W, int steps_f0, int steps_b0, int n,
+                   float* __restrict__ land, unsigned* __restrict__ counts, int tiles_x, int n_tiles)
+{
+    const int64_t P = (int64_t)H * W;
+    const int64_t p_raw = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : 0;
+    const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    const float cx = (float)x, cy = (float)y;
+    const float xmax = (float)(W - 1), ymax = (float)(H - 1);
+    const float sentinel = (float)(max(H, W) + 1);
+
+    auto emit = [&](const EulerState& s, int f, int dir) {
+        const float ddx = s.invalid ? sentinel : __fsub_rn(s.dx, cx);
+        const float ddy = s.invalid ? sentinel : __fsub_rn(s.dy, cy);
+        const float ox = __fadd_rn(cx, ddx), oy = __fadd_rn(cy, ddy);
+        int tiles[4];
+        if (active) {
+            float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
+            l[0] = ox;
+            l[P] = oy;
+            const Footprint fp = footprint_at(ox, oy, H, W);
+            touched_tiles(fp, ox, oy, H, W, tiles_x, tiles);
+        } else {
+            tiles[0] = tiles[1] = tiles[2] = tiles[3] = -1;
+        }
+        unsigned* cnt = counts + (int64_t)f * n_tiles;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (__any_sync(0xffffffffu, tiles[k] >= 0)) warp_reserve(cnt, tiles[k]);
+    };
+
+    // forward chain
+    EulerState s = {cx, cy, false};
+    if (steps_f0 == 0) emit(s, 0, 0);
+    const int last_f = steps_f0 + n - 1;
+    for (int k = 1; k <= last_f; ++k) {
+        euler_step(s, motion, 1.0f, cx, cy, xmax, ymax, W, P);
+        if (k >= steps_f0) emit(s, k - steps_f0, 0);
+    }
+    // backward chain (-motion); frame f needs steps_b0 - f steps
+    s = {cx, cy, false};
+    const int first_b = steps_b0 - (n - 1);          // >= 0, checked by the host
+    if (first_b == 0) emit(s, n - 1, 1);
+    for (int k = 1; k <= steps_b0; ++k) {
+        euler_step(s, motion, -1.0f, cx, cy, xmax, ymax, W, P);
+        if (k >= first_b) emit(s, steps_b0 - k, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bin_scan: per frame, exclusive scan of tile counts -> offsets; counts are zeroed
+// so that the fill pass can reuse them as cursors.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+bin_scan_kernel(unsigned* __restrict__ counts, unsigned* __restrict__ offsets, int n_tiles)
+{
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry_s;
+    unsigned* cnt = counts + (int64_t)blockIdx.x * n_tiles;
+    unsigned* off = offsets + (int64_t)blockIdx.x * (n_tiles + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < n_tiles ? cnt[i] : 0u;
+        unsigned incl = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sums[lane];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;        // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned carry = carry_s;
+        const unsigned before = carry + (warp ? warp_sums[warp - 1] : 0u) + incl - v;
+        if (i < n_tiles) { off[i] = before; cnt[i] = 0u; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n_tiles] = carry_s;
+}
+
+// ---------------------------------------------------------------------------
+// bin_fill: append (pixel | direction, landing x, landing y) to every touched tile.
+// grid: (ceil(P/256), frames)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ offsets,
+                unsigned* __restrict__ cursors, unsigned* __restrict__ ent_p, float* __restrict__ ent_x,
+                float* __restrict__ ent_y, int H, int W, int tiles_x, int n_tiles, int64_t cap)
+{
+    const int64_t P = (int64_t)H * W;
+    const int f = blockIdx.y;
+    const int64_t p_raw = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : 0;
+    const unsigned* off = offsets + (int64_t)f * (n_tiles + 1);
+    unsigned* cur = cursors + (int64_t)f * n_tiles;
+    unsigned* ep = ent_p + (int64_t)f * cap;
+    float* ex = ent_x + (int64_t)f * cap;
+    float* ey = ent_y + (int64_t)f * cap;
+    #pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
+        const float ox = __ldcs(l), oy = __ldcs(l + P);
+        int tiles[4];
+        if (active) {
+            const Footprint fp = footprint_at(ox, oy, H, W);
+            touched_tiles(fp, ox, oy, H, W, tiles_x, tiles);
+        } else {
+            tiles[0] = tiles[1] = tiles[2] = tiles[3] = -1;
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!__any_sync(0xffffffffu, tiles[k] >= 0)) continue;
+            const unsigned slot = warp_reserve(cur, tiles[k]);
+            if (tiles[k] >= 0) {
+                const int64_t at = (int64_t)off[tiles[k]] + slot;
+                ep[at] = (unsigned)p | (dir ? kDirBit : 0u);
+                ex[at] = ox;
+                ey[at] = oy;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// gather
+// ---------------------------------------------------------------------------
+struct GatherParams {
+    const float4* G4;          // [groups][P]
+    const float* S;            // [n_tail + 1][P]   (last plane = e^Z)
+    const unsigned* ent_p;     // [frames][cap]
+    const float* ent_x;
+    const float* ent_y;
+    const unsigned* offsets;   // [frames][n_tiles + 1]
+    float* out;                // [frames][C][P]
+    float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
+    float* mask;               // [frames][P] norm > eps, or NULL
+    int C, groups, H, W, tiles_x, n_tiles;
+    int64_t P, cap;
+    float eps;
+    FrameAlphas alphas;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(TILE, 3)
+gather_kernel(const GatherParams prm)
+{
+    __shared__ uint2 ell[kDepth * TILE];     // ell[k * TILE + d]: k-th (source, weight) pair of destination d
+    __shared__ int cnt[TILE];
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x, f = blockIdx.y;
+    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+    const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
+    const bool inframe = X < prm.W && Y < prm.H;
+    const int64_t P = prm.P;
+    const int64_t pix = (int64_t)Y * prm.W + X;
+    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+
+    const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+    const unsigned beg = off[tile], end = off[tile + 1];
+    const unsigned* ep = prm.ent_p + (int64_t)f * prm.cap;
+    const float* ex = prm.ent_x + (int64_t)f * prm.cap;
+    const float* ey = prm.ent_y + (int64_t)f * prm.cap;
+    float* out = prm.out + (int64_t)f * prm.C * P + pix;
+
+    float nrm = 0.0f;
+    float tl[NT > 0 ? NT : 1] = {0.0f};
+    bool wrote = false;          // this thread's output planes hold partial sums already
+    bool partial = false;        // outputs were written un-normalised (multi-pass bin)
+
+    // visits the pairs of entries [cb, ce) that land inside this tile
+    auto for_each_pair = [&](unsigned cb, unsigned ce, auto&& fn) {
+        for (unsigned e = cb + tid; e < ce; e += TILE) {
+            const unsigned pd = __ldg(ep + e);
+            const float ox = __ldg(ex + e), oy = __ldg(ey + e);
+            const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
+            const float a = (pd & kDirBit) ? a_b : a_f;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                const float wa = fp.w[k] * a;
+                if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                    fn(ly * TW + lx, pd & ~kDirBit, wa);
+            }
+        }
+    };
+
+    unsigned cb = beg;
+    while (cb < end) {
+        // pick the largest prefix of the remaining entries whose per-pixel lists fit kDepth
+        unsigned len = min((unsigned)kChunk, end - cb);
+        for (;;) {
+            cnt[tid] = 0;
+            __syncthreads();
+            for_each_pair(cb, cb + len, [&](int d, unsigned, float) { atomicAdd(&cnt[d], 1); });
+            __syncthreads();
+            const int over = __syncthreads_or(cnt[tid] > kDepth);
+            if (!over || len == 1) break;
+            len = (len + 1) >> 1;
+        }
+        const bool whole_bin = (cb == beg) && (cb + len == end);
+        const int my_cnt = min(cnt[tid], kDepth);
+        __syncthreads();
+        cnt[tid] = 0;
+        __syncthreads();
+        for_each_pair(cb, cb + len, [&](int d, unsigned p, float wa) {
+            const int k = atomicAdd(&cnt[d], 1);
+            if (k < kDepth) ell[k * TILE + d] = make_uint2(p, __float_as_uint(wa));
+        });
+        __syncthreads();
+
+        // my list -> registers
+        unsigned pk[kDepth];
+        float wk[kDepth];
+        const int kmax = __reduce_max_sync(0xffffffffu, my_cnt);
+        #pragma unroll
+        for (int k = 0; k < kDepth; ++k) {
+            if (k >= kmax) break;
+            const uint2 e = ell[k * TILE + tid];
+            pk[k] = k < my_cnt ? e.x : 0u;
+            wk[k] = k < my_cnt ? __uint_as_float(e.y) : 0.0f;
+        }
+
+        // scalar planes: tail channels and the e^Z weight (the normaliser)
+        #pragma unroll
+        for (int k = 0; k < kDepth; ++k) {
+            if (k >= kmax) break;
+            if (k < my_cnt) {
+                #pragma unroll
+                for (int j = 0; j < NT; ++j) tl[j] = fmaf(__ldg(prm.S + (int64_t)j * P + pk[k]), wk[k], tl[j]);
+                nrm = fmaf(__ldg(prm.S + (int64_t)NT * P + pk[k]), wk[k], nrm);
+            }
+        }
+        partial = partial || !whole_bin;
+        const float inv = whole_bin ? 1.0f / fmaxf(nrm, prm.eps) : 1.0f;
+
+        for (int g = 0; g < prm.groups; ++g) {
+            const float4* Gg = prm.G4 + (int64_t)g * P;
+            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            #pragma unroll
+            for (int k = 0; k < kDepth; ++k) {
+                if (k >= kmax) break;
+                if (k < my_cnt) {
+                    const float4 v = __ldg(Gg + pk[k]);
+                    acc.x = fmaf(v.x, wk[k], acc.x);
+                    acc.y = fmaf(v.y, wk[k], acc.y);
+                    acc.z = fmaf(v.z, wk[k], acc.z);
+                    acc.w = fmaf(v.w, wk[k], acc.w);
+                }
+            }
+            if (inframe) {
+                const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 4 * g + j;
+                    if (c < prm.C) {
+                        float* o = out + (int64_t)c * P;
+                        if (whole_bin) __stcs(o, r[j] * inv);
+                        else *o = wrote ? *o + r[j] : r[j];
+                    }
+                }
+            }
+        }
+        wrote = true;
+        cb += len;
+        __syncthreads();
+    }
+
+    if (!inframe) return;
+    const float den = fmaxf(nrm, prm.eps);
+    if (!wrote) {
+        // empty bin: the whole tile is a hole
+        for (int c = 0; c < prm.C; ++c) __stcs(out + (int64_t)c * P, 0.0f);
+    } else if (partial) {
+        const float inv = 1.0f / den;
+        for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] *= inv;
+    }
+    if (prm.aux) {
+        float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
+        #pragma unroll
+        for (int j = 0; j < NT; ++j) a[(int64_t)j * P] = tl[j];
+        a[(int64_t)NT * P] = nrm;
+    }
+    if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
+}
+
+}  // namespace slr
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace slr;
+
+namespace {
+
+struct Workspace {
+    float* land;          // [n][2 dirs][2][P]
+    unsigned* counts;     // [n][n_tiles]      (counts, then cursors)
+    unsigned* offsets;    // [n][n_tiles + 1]
+    unsigned* ent_p;      // [n][cap]
+    float* ent_x;
+    float* ent_y;
+    size_t bytes;
+};
+
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+Workspace carve(void* base, int64_t H, int64_t W, int n)
+{
+    const int64_t P = H * W;
+    const int64_t tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+    const int64_t cap = 8 * P;
+    char* p = (char*)base;
+    size_t o = 0;
+    Workspace w;
+    w.land = (float*)(p + o);        o += align_up(sizeof(float) * 4 * P * n);
+    w.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
+    w.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
+    w.ent_p = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * cap * n);
+    w.ent_x = (float*)(p + o);       o += align_up(sizeof(float) * cap * n);
+    w.ent_y = (float*)(p + o);       o += align_up(sizeof(float) * cap * n);
+    w.bytes = o;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames)
+{
+    if (H <= 0 || W <= 0 || n_frames <= 0) return 0;
+    return carve(nullptr, H, W, n_frames).bytes;
+}
+
+extern "C" size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W)
+{
+    if (C <= 0 || n_tail < 0 || H <= 0 || W <= 0) return 0;
+    return sizeof(float) * (size_t)(((C + 3) / 4) * 4 + n_tail + 1) * (size_t)(H * W);
+}
+
+extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zsub,
+                              const float* tail, int n_tail, void* scene,
+                              int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(feat && z && scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 15) == 0,
+                   "slr_scene_prep: bad arguments");
+    const int64_t P = H * W;
+    const int groups = (int)((C + 3) / 4);
+    float4* G4 = (float4*)scene;
+    float* S = (float*)scene + (int64_t)groups * 4 * P;
+    dim3 grid((unsigned)((P + 255) / 256), (unsigned)std::min(groups, 4), 1);
+    scene_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(feat, z, zsub, tail, n_tail, G4, S, (int)C, P);
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
+                             int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(motion && workspace && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   n_frames > 0 && n_frames <= kMaxFrames &&
+                   t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)workspace & 15) == 0,
+                   "slr_clip_plan: bad arguments");
+    const int64_t P = H * W;
+    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
+    const int n_tiles = tiles_x * tiles_y;
+    const Workspace ws = carve(workspace, H, W, n_frames);
+    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_plan: workspace too small (see slr_clip_workspace_bytes)");
+    cudaStream_t s = (cudaStream_t)stream_;
+
+    SLR_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
+    const unsigned pblocks = (unsigned)((P + 255) / 256);
+    euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
+                                               ws.land, ws.counts, tiles_x, n_tiles);
+    bin_scan_kernel<<<n_frames, 1024, 0, s>>>(ws.counts, ws.offsets, n_tiles);
+    bin_fill_kernel<<<dim3(pblocks, n_frames), 256, 0, s>>>(ws.land, ws.offsets, ws.counts, ws.ent_p, ws.ent_x,
+                                                            ws.ent_y, (int)H, (int)W, tiles_x, n_tiles, 8 * P);
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t H, int64_t W,
+                               int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                               float* out, float* aux, float* mask,
+                               const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(scene && out && workspace && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   n_tail >= 0 && n_tail <= 2 && n_frames > 0 && n_frames <= kMaxFrames &&
+                   t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)workspace & 15) == 0,
+                   "slr_clip_gather: bad arguments");
+    const int64_t P = H * W;
+    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
+    const int n_tiles = tiles_x * tiles_y;
+    const Workspace ws = carve(const_cast<void*>(workspace), H, W, n_frames);
+    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_gather: workspace too small (see slr_clip_workspace_bytes)");
+
+    GatherParams prm;
+    const int groups = (int)((C + 3) / 4);
+    prm.G4 = (const float4*)scene;
+    prm.S = (const float*)scene + (int64_t)groups * 4 * P;
+    prm.ent_p = ws.ent_p; prm.ent_x = ws.ent_x; prm.ent_y = ws.ent_y; prm.offsets = ws.offsets;
+    prm.out = out; prm.aux = aux; prm.mask = mask;
+    prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
+    prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
+    for (int f = 0; f < n_frames; ++f) {
+        // alpha = 1 - (t - start) / (end - start + 1) in fp32 (animating_softmax_splating.py:860),
+        // optionally clamped (2layers...py:952)
+        float a = 1.0f - (float)(t0 + f - start) / (float)(end - start + 1);
+        a = fminf(fmaxf(a, alpha_lo), alpha_hi);
+        prm.alphas.a[f] = a;
+    }
+    dim3 grid((unsigned)n_tiles, (unsigned)n_frames, 1);
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (n_tail == 0) gather_kernel<0><<<grid, TILE, 0, s>>>(prm);
+    else if (n_tail == 1) gather_kernel<1><<<grid, TILE, 0, s>>>(prm);
+    else gather_kernel<2><<<grid, TILE, 0, s>>>(prm);
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tail,
+                               int64_t H, int64_t W, int start, int end, int t0, int n_frames,
+                               float alpha_lo, float alpha_hi,
+                               float* out, float* aux, float* mask,
+                               void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    int rc = slr_clip_plan(motion, H, W, start, end, t0, n_frames, workspace, workspace_bytes, stream_);
+    if (rc) return rc;
+    return slr_clip_gather(scene, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                           out, aux, mask, workspace, workspace_bytes, stream_);
+}

@@ -16,10 +16,10 @@ struct Footprint {
     unsigned ok;       // bit k set when corner k lies inside the frame
 };
 
-__device__ __forceinline__ Footprint landing(int x, int y, float fx, float fy, int H, int W)
+// Footprint of a landing position (ox, oy) given directly.
+__device__ __forceinline__ Footprint footprint_at(float ox, float oy, int H, int W)
 {
     Footprint f;
-    const float ox = (float)x + fx, oy = (float)y + fy;
     const float flx = floorf(ox), fly = floorf(oy);
     // Anything this far out (or non-finite) misses the frame with all four
     // corners; testing in the float domain keeps the int conversion defined.
@@ -35,6 +35,11 @@ __device__ __forceinline__ Footprint landing(int x, int y, float fx, float fy, i
     const bool yt = iy >= 0 && iy < H, yb = iy + 1 >= 0 && iy + 1 < H;
     f.ok = far ? 0u : ((xl && yt) ? 1u : 0u) | ((xr && yt) ? 2u : 0u) | ((xl && yb) ? 4u : 0u) | ((xr && yb) ? 8u : 0u);
     return f;
+}
+
+__device__ __forceinline__ Footprint landing(int x, int y, float fx, float fy, int H, int W)
+{
+    return footprint_at((float)x + fx, (float)y + fy, H, W);
 }
 
 // fp32 add with no returned value: compiles to RED.E.ADD.F32 (fire-and-forget at L2).

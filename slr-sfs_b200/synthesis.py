@@ -13,6 +13,11 @@ The reference runs this as ~40 eager torch ops, two Euler integrations restarted
 from zero and two cupy launches per frame.  Here a frame is a handful of launches
 of the sm_100a library, nothing is synchronised with the host, and no
 intermediate ``tenInput`` tensor is materialised.
+
+Two algorithms, same results up to fp32 summation order:
+  * ``frames`` / ``frame``   -- gather pipeline (csrc/clip_pipeline.cu), the fast path;
+  * ``frame_scatter``        -- atomic scatter + normalise (csrc/splat_ops.cu), the
+                                design BASELINE.json sketches, kept as measured baseline.
 """
 import numpy as np
 import torch
@@ -53,6 +58,10 @@ class JointSplat:
     positions C..C+n_tail-1 of the accumulator.
     """
 
+    #: frames per slr_clip_frames launch (bigger batches amortise the Euler chains,
+    #: smaller ones keep the landing table and the bins inside the 126 MB L2)
+    batch = 6
+
     def __init__(self, features, Z, motion, z_mode="max", tail=None):
         assert features.dim() == 4 and features.shape[0] == 1
         self.feat = _req(features.detach(), "features")
@@ -71,6 +80,55 @@ class JointSplat:
                           _lib.current_stream(self.device))
             else:
                 self.zsub = None
+        self._scene = None
+        self._workspace = None
+
+    # -- gather pipeline: scene_prep once, then bin + gather per batch of frames
+    def _prepare(self):
+        if self._scene is None:
+            n = _lib.load().slr_scene_bytes(self.C, self.n_tail, self.H, self.W)
+            self._scene = torch.empty(n // 4, dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self.zsub),
+                          _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W,
+                          _lib.current_stream(self.device))
+        return self._scene
+
+    def _scratch(self, n):
+        need = _lib.load().slr_clip_workspace_bytes(self.H, self.W, n)
+        if self._workspace is None or self._workspace.numel() * 4 < need:
+            self._workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+        return self._workspace, self._workspace.numel() * 4
+
+    def frames(self, start, end, t0, n, out=None, want_aux=False, want_mask=False, alpha_clamp=(0.0, 1.0)):
+        """Frames t0..t0+n-1 of the clip [start, end]: gen_fs [n,C,H,W]
+        (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W])."""
+        scene = self._prepare()
+        H, W, C = self.H, self.W, self.C
+        if out is None:
+            out = torch.empty(n, C, H, W, dtype=torch.float32, device=self.device)
+        assert out.shape == (n, C, H, W) and out.is_contiguous() and out.device == self.device
+        aux = torch.empty(n, self.n_tail + 1, H, W, dtype=torch.float32, device=self.device) if want_aux else None
+        mask = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_mask else None
+        with torch.cuda.device(self.device):
+            s = _lib.current_stream(self.device)
+            for b0 in range(0, n, self.batch):
+                nb = min(self.batch, n - b0)
+                ws, ws_bytes = self._scratch(nb)
+                _lib.call("slr_clip_plan", _lib.ptr(self.motion), H, W, start, end, t0 + b0, nb,
+                          _lib.ptr(ws), ws_bytes, s)
+                _lib.call("slr_clip_gather", _lib.ptr(scene), C, self.n_tail, H, W,
+                          start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1], _lib.ptr(out[b0:]),
+                          None if aux is None else _lib.ptr(aux[b0:]),
+                          None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes, s)
+        res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
+        return res if len(res) > 1 else out
+
+    def frame(self, index, **kw):
+        """gen_fs [1,C,H,W] for index = (start, t, end) -- the per-frame call of the
+        reference's loop (test_v1_4eval_rawsize.py:233-239)."""
+        start, mid, end = _index_triplet(index)
+        return self.frames(start, end, mid, 1, **kw)
 
     # -- scatter variant: Euler x2 -> atomic scatter of both directions -> normalise
     def accumulate_scatter(self, index, alpha=None):
