@@ -182,13 +182,6 @@ def workload_config(args, algo):
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
-def frame_block(n_frames, rank, world):
-    """Contiguous frame block of `rank` (sizes differ by at most one)."""
-    base, rem = divmod(n_frames, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
-
-
 def main():
     args = parse()
     if args.impl == "reference":
@@ -201,6 +194,7 @@ def main():
     __graft_entry__.build()
     import slr_sfs_b200 as pkg
     from slr_sfs_b200 import workloads, _lib
+    from slr_sfs_b200.sharding import frame_block
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

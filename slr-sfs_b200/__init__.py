@@ -13,6 +13,7 @@ from . import _lib
 from . import softsplat
 from . import euler_integration_manipulator
 from . import synthesis
+from . import sharding
 from .softsplat import (FunctionSoftsplat, ModuleSoftsplat, ModuleMaximumsplat,
                         ModuleMaximumWarpNormsplat)
 from .euler_integration_manipulator import EulerIntegration, euler_integration

@@ -272,6 +272,98 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
 // ---------------------------------------------------------------------------
 // gather
 // ---------------------------------------------------------------------------
+// Predicated read-only loads (zero when the predicate is off).  Written as PTX so
+// that they stay branch-free: the gather issues a block of them back to back and
+// only then consumes them, which is what hides the L2 / HBM latency.
+__device__ __forceinline__ float4 ldg128_if(const char* ptr, bool pred)
+{
+    float4 v;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+        "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
+        : "l"(ptr), "r"((unsigned)pred));
+    return v;
+}
+
+__device__ __forceinline__ float ldg32_if(const float* ptr, bool pred)
+{
+    float v;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
+        : "=&f"(v) : "l"(ptr), "r"((unsigned)pred));
+    return v;
+}
+
+struct GatherCtx {
+    const char* G;       // channel-group planes, 16 bytes per pixel
+    const float* S;      // scalar planes
+    float* out;          // this thread's pixel in plane 0 of the frame
+    int64_t P;
+    int groups, C, my_cnt;
+    float eps;
+    bool inframe, whole_bin, wrote;
+};
+
+// One pass of a destination pixel over its (source, weight) list, K = compile-time
+// list capacity (the warp's longest list rounded up).  Loads are issued in blocks
+// of up to 8 independent LDG.128 before the FMAs that consume them.
+template <int NT, int K>
+__device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned (&pk)[kDepth],
+                                             const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
+{
+    constexpr int B = K < 8 ? K : 8;
+    constexpr int BS = K < 4 ? K : (NT > 0 ? 4 : B);
+    // scalar planes: tail channels, then the e^Z weight (the normaliser)
+    #pragma unroll
+    for (int kb = 0; kb < K; kb += BS) {
+        float sv[NT + 1][BS];
+        #pragma unroll
+        for (int j = 0; j < BS; ++j) {
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) sv[t][j] = ldg32_if(c.S + (int64_t)t * c.P + pk[kb + j], kb + j < c.my_cnt);
+        }
+        #pragma unroll
+        for (int j = 0; j < BS; ++j) {
+            #pragma unroll
+            for (int t = 0; t < NT; ++t) tl[t] = fmaf(sv[t][j], wk[kb + j], tl[t]);
+            nrm = fmaf(sv[NT][j], wk[kb + j], nrm);
+        }
+    }
+    const float inv = c.whole_bin ? 1.0f / fmaxf(nrm, c.eps) : 1.0f;
+
+    const char* Gg = c.G;
+    const size_t gstride = (size_t)c.P * 16;
+    float* o = c.out;
+    for (int g = 0; g < c.groups; ++g, Gg += gstride) {
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        #pragma unroll
+        for (int kb = 0; kb < K; kb += B) {
+            float4 v[B];
+            #pragma unroll
+            for (int j = 0; j < B; ++j) v[j] = ldg128_if(Gg + (size_t)pk[kb + j] * 16, kb + j < c.my_cnt);
+            #pragma unroll
+            for (int j = 0; j < B; ++j) {
+                acc.x = fmaf(v[j].x, wk[kb + j], acc.x);
+                acc.y = fmaf(v[j].y, wk[kb + j], acc.y);
+                acc.z = fmaf(v[j].z, wk[kb + j], acc.z);
+                acc.w = fmaf(v[j].w, wk[kb + j], acc.w);
+            }
+        }
+        if (c.inframe) {
+            const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+            #pragma unroll
+            for (int j = 0; j < 4; ++j, o += c.P) {
+                if (4 * g + j < c.C) {
+                    if (c.whole_bin) __stcs(o, r[j] * inv);
+                    else *o = c.wrote ? *o + r[j] : r[j];
+                }
+            }
+        }
+    }
+}
+
 struct GatherParams {
     const float4* G4;          // [groups][P]
     const float* S;            // [n_tail + 1][P]   (last plane = e^Z)
@@ -357,58 +449,27 @@ gather_kernel(const GatherParams prm)
         });
         __syncthreads();
 
-        // my list -> registers
+        // my list -> registers (conflict-free LDS: consecutive lanes read consecutive pairs)
         unsigned pk[kDepth];
         float wk[kDepth];
         const int kmax = __reduce_max_sync(0xffffffffu, my_cnt);
         #pragma unroll
         for (int k = 0; k < kDepth; ++k) {
-            if (k >= kmax) break;
             const uint2 e = ell[k * TILE + tid];
             pk[k] = k < my_cnt ? e.x : 0u;
             wk[k] = k < my_cnt ? __uint_as_float(e.y) : 0.0f;
         }
-
-        // scalar planes: tail channels and the e^Z weight (the normaliser)
-        #pragma unroll
-        for (int k = 0; k < kDepth; ++k) {
-            if (k >= kmax) break;
-            if (k < my_cnt) {
-                #pragma unroll
-                for (int j = 0; j < NT; ++j) tl[j] = fmaf(__ldg(prm.S + (int64_t)j * P + pk[k]), wk[k], tl[j]);
-                nrm = fmaf(__ldg(prm.S + (int64_t)NT * P + pk[k]), wk[k], nrm);
-            }
-        }
         partial = partial || !whole_bin;
-        const float inv = whole_bin ? 1.0f / fmaxf(nrm, prm.eps) : 1.0f;
 
-        for (int g = 0; g < prm.groups; ++g) {
-            const float4* Gg = prm.G4 + (int64_t)g * P;
-            float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            #pragma unroll
-            for (int k = 0; k < kDepth; ++k) {
-                if (k >= kmax) break;
-                if (k < my_cnt) {
-                    const float4 v = __ldg(Gg + pk[k]);
-                    acc.x = fmaf(v.x, wk[k], acc.x);
-                    acc.y = fmaf(v.y, wk[k], acc.y);
-                    acc.z = fmaf(v.z, wk[k], acc.z);
-                    acc.w = fmaf(v.w, wk[k], acc.w);
-                }
-            }
-            if (inframe) {
-                const float r[4] = {acc.x, acc.y, acc.z, acc.w};
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = 4 * g + j;
-                    if (c < prm.C) {
-                        float* o = out + (int64_t)c * P;
-                        if (whole_bin) __stcs(o, r[j] * inv);
-                        else *o = wrote ? *o + r[j] : r[j];
-                    }
-                }
-            }
-        }
+        GatherCtx ctx;
+        ctx.G = reinterpret_cast<const char*>(prm.G4);
+        ctx.S = prm.S; ctx.P = P; ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
+        ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote; ctx.my_cnt = my_cnt;
+        // the list length is warp-uniform after the max-reduce: pick the unroll that fits
+        if (kmax <= 2) gather_lists<NT, 2>(ctx, pk, wk, nrm, tl);
+        else if (kmax <= 4) gather_lists<NT, 4>(ctx, pk, wk, nrm, tl);
+        else if (kmax <= 8) gather_lists<NT, 8>(ctx, pk, wk, nrm, tl);
+        else gather_lists<NT, 16>(ctx, pk, wk, nrm, tl);
         wrote = true;
         cb += len;
         __syncthreads();

@@ -50,7 +50,9 @@ __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
 // like unsigned ints.
 __device__ __forceinline__ void red_max(float* p, float v)
 {
-    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(p), __float_as_int(v));
+    // keyed on the sign BIT: -0.0 (a zero-weight corner of a negative value) must
+    // still beat every negative number, as fmaxf does in the reference's CAS loop
+    if (!signbit(v)) atomicMax(reinterpret_cast<int*>(p), __float_as_int(v));
     else atomicMin(reinterpret_cast<unsigned*>(p), __float_as_uint(v));
 }
 
