@@ -35,7 +35,9 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    # tuning knobs of the gather kernel (see clip_pipeline.cu); e.g. SLR_DEFINES="-DSLR_GATHER_DEPTH=12"
+    extra = os.environ.get("SLR_DEFINES", "").split()
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout)

@@ -34,8 +34,16 @@ namespace slr {
 constexpr int TW = 32;                 // destination tile width  (one warp per tile row)
 constexpr int TH = 8;                  // destination tile height
 constexpr int TILE = TW * TH;          // threads per gather CTA, one destination pixel each
-constexpr int kDepth = 16;             // (source, weight) pairs a thread holds in registers
-constexpr int kChunk = 1024;           // bin entries expanded per pass
+#ifndef SLR_GATHER_DEPTH
+#define SLR_GATHER_DEPTH 16            // 12 or 16
+#endif
+#ifndef SLR_GATHER_MINBLOCKS
+#define SLR_GATHER_MINBLOCKS 2         // resident CTAs per SM the register budget is sized for
+#endif
+constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread holds in registers
+constexpr int kSmemDepth = 32;         // pairs per destination pixel the shared list table holds
+constexpr int kChunk = 8192;           // bin entries expanded per pass
+constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
 constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the parameters)
 constexpr unsigned kDirBit = 0x80000000u;
 
@@ -86,8 +94,17 @@ scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, c
                   const float* __restrict__ tail, int n_tail, float4* __restrict__ G4, float* __restrict__ S,
                   int C, int64_t P)
 {
+    // planes have stride P + 1: pixel P is the all-zero pixel unused gather slots read
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (p >= P) return;
+    if (p > P) return;
+    if (p == P) {
+        const int groups = (C + 3) >> 2;
+        if (blockIdx.y == 0) {
+            for (int g = 0; g < groups; ++g) G4[(int64_t)g * (P + 1) + P] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int j = 0; j <= n_tail; ++j) S[(int64_t)j * (P + 1) + P] = 0.0f;
+        }
+        return;
+    }
     const float ez = expf(z[p] - (zsub ? *zsub : 0.0f));
     const int groups = (C + 3) >> 2;
     const int g0 = blockIdx.y * ((groups + gridDim.y - 1) / gridDim.y);
@@ -99,11 +116,11 @@ scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, c
             const int c = 4 * g + j;
             v[j] = c < C ? feat[(int64_t)c * P + p] * ez : 0.0f;
         }
-        G4[(int64_t)g * P + p] = make_float4(v[0], v[1], v[2], v[3]);
+        G4[(int64_t)g * (P + 1) + p] = make_float4(v[0], v[1], v[2], v[3]);
     }
     if (blockIdx.y == 0) {
-        for (int j = 0; j < n_tail; ++j) S[(int64_t)j * P + p] = tail[(int64_t)j * P + p];
-        S[(int64_t)n_tail * P + p] = ez;
+        for (int j = 0; j < n_tail; ++j) S[(int64_t)j * (P + 1) + p] = tail[(int64_t)j * P + p];
+        S[(int64_t)n_tail * (P + 1) + p] = ez;
     }
 }
 
@@ -272,101 +289,12 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
 // ---------------------------------------------------------------------------
 // gather
 // ---------------------------------------------------------------------------
-// Predicated read-only loads (zero when the predicate is off).  Written as PTX so
-// that they stay branch-free: the gather issues a block of them back to back and
-// only then consumes them, which is what hides the L2 / HBM latency.
-__device__ __forceinline__ float4 ldg128_if(const char* ptr, bool pred)
-{
-    float4 v;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
-        "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
-        "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
-        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-        : "=&f"(v.x), "=&f"(v.y), "=&f"(v.z), "=&f"(v.w)
-        : "l"(ptr), "r"((unsigned)pred));
-    return v;
-}
-
-__device__ __forceinline__ float ldg32_if(const float* ptr, bool pred)
-{
-    float v;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t"
-        "mov.f32 %0, 0f00000000;\n\t@p ld.global.nc.f32 %0, [%1];\n\t}"
-        : "=&f"(v) : "l"(ptr), "r"((unsigned)pred));
-    return v;
-}
-
-struct GatherCtx {
-    const char* G;       // channel-group planes, 16 bytes per pixel
-    const float* S;      // scalar planes
-    float* out;          // this thread's pixel in plane 0 of the frame
-    int64_t P;
-    int groups, C, my_cnt;
-    float eps;
-    bool inframe, whole_bin, wrote;
-};
-
-// One pass of a destination pixel over its (source, weight) list, K = compile-time
-// list capacity (the warp's longest list rounded up).  Loads are issued in blocks
-// of up to 8 independent LDG.128 before the FMAs that consume them.
-template <int NT, int K>
-__device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned (&pk)[kDepth],
-                                             const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
-{
-    constexpr int B = K < 8 ? K : 8;
-    constexpr int BS = K < 4 ? K : (NT > 0 ? 4 : B);
-    // scalar planes: tail channels, then the e^Z weight (the normaliser)
-    #pragma unroll
-    for (int kb = 0; kb < K; kb += BS) {
-        float sv[NT + 1][BS];
-        #pragma unroll
-        for (int j = 0; j < BS; ++j) {
-            #pragma unroll
-            for (int t = 0; t <= NT; ++t) sv[t][j] = ldg32_if(c.S + (int64_t)t * c.P + pk[kb + j], kb + j < c.my_cnt);
-        }
-        #pragma unroll
-        for (int j = 0; j < BS; ++j) {
-            #pragma unroll
-            for (int t = 0; t < NT; ++t) tl[t] = fmaf(sv[t][j], wk[kb + j], tl[t]);
-            nrm = fmaf(sv[NT][j], wk[kb + j], nrm);
-        }
-    }
-    const float inv = c.whole_bin ? 1.0f / fmaxf(nrm, c.eps) : 1.0f;
-
-    const char* Gg = c.G;
-    const size_t gstride = (size_t)c.P * 16;
-    float* o = c.out;
-    for (int g = 0; g < c.groups; ++g, Gg += gstride) {
-        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        #pragma unroll
-        for (int kb = 0; kb < K; kb += B) {
-            float4 v[B];
-            #pragma unroll
-            for (int j = 0; j < B; ++j) v[j] = ldg128_if(Gg + (size_t)pk[kb + j] * 16, kb + j < c.my_cnt);
-            #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                acc.x = fmaf(v[j].x, wk[kb + j], acc.x);
-                acc.y = fmaf(v[j].y, wk[kb + j], acc.y);
-                acc.z = fmaf(v[j].z, wk[kb + j], acc.z);
-                acc.w = fmaf(v[j].w, wk[kb + j], acc.w);
-            }
-        }
-        if (c.inframe) {
-            const float r[4] = {acc.x, acc.y, acc.z, acc.w};
-            #pragma unroll
-            for (int j = 0; j < 4; ++j, o += c.P) {
-                if (4 * g + j < c.C) {
-                    if (c.whole_bin) __stcs(o, r[j] * inv);
-                    else *o = c.wrote ? *o + r[j] : r[j];
-                }
-            }
-        }
-    }
-}
-
+// Scene buffer layout: every plane carries one extra, all-zero pixel at index P
+// (plane stride P + 1).  Unused list slots point at it, so the hot loop needs no
+// predicates and no zero-initialisation: an unused slot loads zeros with weight 0.
 struct GatherParams {
-    const float4* G4;          // [groups][P]
-    const float* S;            // [n_tail + 1][P]   (last plane = e^Z)
+    const char* G;             // [groups] planes of (P + 1) float4
+    const float* S;            // [n_tail + 1] planes of (P + 1) float   (last plane = e^Z)
     const unsigned* ent_p;     // [frames][cap]
     const float* ent_x;
     const float* ent_y;
@@ -380,12 +308,132 @@ struct GatherParams {
     FrameAlphas alphas;
 };
 
+struct GatherCtx {
+    const char* G;       // group plane 0
+    const float* S;      // scalar plane 0
+    const uint2* ell;    // this thread's column of the shared list table (stride TILE)
+    float* out;          // this thread's pixel in plane 0 of the frame
+    int64_t P;
+    int groups, C, my_cnt, kmax;
+    float eps;
+    bool inframe, whole_bin, wrote;
+};
+
+// address of pixel `p` in a float4 plane: one IMAD.WIDE
+__device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
+{
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(p), "l"(plane));
+    return reinterpret_cast<const float4*>(a);
+}
+
+// One pass of a destination pixel over its (source, weight) list.  K = compile-time
+// number of register-resident list slots (the warp's longest list rounded up to
+// even, at most kDepth); longer lists continue from shared memory.  Loads are
+// issued in blocks of up to 8 independent LDG.128 before the FMAs that consume them.
+// FAST: the whole bin fits one pass and C % 4 == 0 -> plain normalised streaming stores.
+template <int NT, int K, bool FAST>
+__device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned (&pk)[kDepth],
+                                             const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
+{
+    constexpr int B = K <= 8 ? K : K / 2;
+    const int64_t sstride = c.P + 1;
+    // scalar planes: tail channels, then the e^Z weight (the normaliser)
+    #pragma unroll
+    for (int kb = 0; kb < K; kb += B) {
+        float sv[NT + 1][B];
+        #pragma unroll
+        for (int j = 0; j < B; ++j) {
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) sv[t][j] = __ldg(c.S + (int64_t)t * sstride + pk[kb + j]);
+        }
+        #pragma unroll
+        for (int j = 0; j < B; ++j) {
+            #pragma unroll
+            for (int t = 0; t < NT; ++t) tl[t] = fmaf(sv[t][j], wk[kb + j], tl[t]);
+            nrm = fmaf(sv[NT][j], wk[kb + j], nrm);
+        }
+    }
+    if (K == kDepth) {
+        for (int k = kDepth; k < c.kmax; ++k) {
+            const uint2 e = c.ell[k * TILE];
+            const bool on = k < c.my_cnt;
+            const unsigned p = on ? e.x : (unsigned)c.P;
+            const float w = on ? __uint_as_float(e.y) : 0.0f;
+            #pragma unroll
+            for (int t = 0; t < NT; ++t) tl[t] = fmaf(__ldg(c.S + (int64_t)t * sstride + p), w, tl[t]);
+            nrm = fmaf(__ldg(c.S + (int64_t)NT * sstride + p), w, nrm);
+        }
+    }
+    const float inv = c.whole_bin ? 1.0f / fmaxf(nrm, c.eps) : 1.0f;
+
+    const char* Gg = c.G;
+    const size_t gstride = (size_t)(c.P + 1) * 16;
+    const size_t ostride = (size_t)c.P;
+    float* o = c.out;
+    for (int g = 0; g < c.groups; ++g, Gg += gstride, o += 4 * ostride) {
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        #pragma unroll
+        for (int kb = 0; kb < K; kb += B) {
+            float4 v[B];
+            #pragma unroll
+            for (int j = 0; j < B; ++j) v[j] = __ldg(px16(Gg, pk[kb + j]));
+            #pragma unroll
+            for (int j = 0; j < B; ++j) {
+                acc.x = fmaf(v[j].x, wk[kb + j], acc.x);
+                acc.y = fmaf(v[j].y, wk[kb + j], acc.y);
+                acc.z = fmaf(v[j].z, wk[kb + j], acc.z);
+                acc.w = fmaf(v[j].w, wk[kb + j], acc.w);
+            }
+        }
+        if (K == kDepth) {
+            for (int k = kDepth; k < c.kmax; ++k) {       // rare: lists longer than the register file holds
+                const uint2 e = c.ell[k * TILE];
+                const bool on = k < c.my_cnt;
+                const float4 v = __ldg(px16(Gg, on ? e.x : (unsigned)c.P));
+                const float w = on ? __uint_as_float(e.y) : 0.0f;
+                acc.x = fmaf(v.x, w, acc.x);
+                acc.y = fmaf(v.y, w, acc.y);
+                acc.z = fmaf(v.z, w, acc.z);
+                acc.w = fmaf(v.w, w, acc.w);
+            }
+        }
+        if (c.inframe) {
+            if (FAST) {
+                __stcs(o, acc.x * inv);
+                __stcs(o + ostride, acc.y * inv);
+                __stcs(o + 2 * ostride, acc.z * inv);
+                __stcs(o + 3 * ostride, acc.w * inv);
+            } else {
+                const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (4 * g + j < c.C) {
+                        float* oj = o + j * ostride;
+                        if (c.whole_bin) __stcs(oj, r[j] * inv);
+                        else *oj = c.wrote ? *oj + r[j] : r[j];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int NT, int K>
+__device__ __forceinline__ void gather_dispatch(const GatherCtx& c, const unsigned (&pk)[kDepth],
+                                                const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
+{
+    if (c.whole_bin && (c.C & 3) == 0) gather_lists<NT, K, true>(c, pk, wk, nrm, tl);
+    else gather_lists<NT, K, false>(c, pk, wk, nrm, tl);
+}
+
 template <int NT>
-__global__ void __launch_bounds__(TILE, 3)
+__global__ void __launch_bounds__(TILE, SLR_GATHER_MINBLOCKS)
 gather_kernel(const GatherParams prm)
 {
-    __shared__ uint2 ell[kDepth * TILE];     // ell[k * TILE + d]: k-th (source, weight) pair of destination d
-    __shared__ int cnt[TILE];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* ell = reinterpret_cast<uint2*>(smem_raw);                 // ell[k * TILE + d], k < kSmemDepth
+    int* cnt = reinterpret_cast<int*>(ell + kSmemDepth * TILE);      // pairs per destination pixel
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x, f = blockIdx.y;
@@ -408,68 +456,72 @@ gather_kernel(const GatherParams prm)
     bool wrote = false;          // this thread's output planes hold partial sums already
     bool partial = false;        // outputs were written un-normalised (multi-pass bin)
 
-    // visits the pairs of entries [cb, ce) that land inside this tile
-    auto for_each_pair = [&](unsigned cb, unsigned ce, auto&& fn) {
-        for (unsigned e = cb + tid; e < ce; e += TILE) {
-            const unsigned pd = __ldg(ep + e);
-            const float ox = __ldg(ex + e), oy = __ldg(ey + e);
-            const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
-            const float a = (pd & kDirBit) ? a_b : a_f;
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-                const float wa = fp.w[k] * a;
-                if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
-                    fn(ly * TW + lx, pd & ~kDirBit, wa);
-            }
-        }
-    };
-
     unsigned cb = beg;
     while (cb < end) {
-        // pick the largest prefix of the remaining entries whose per-pixel lists fit kDepth
+        // Expand entries [cb, cb+len) into per-destination lists.  If a destination pixel
+        // overflows the table (> kSmemDepth pairs: sinks, strong compression) retry with half
+        // the entries; one entry adds at most one pair per pixel, so this terminates.
         unsigned len = min((unsigned)kChunk, end - cb);
         for (;;) {
             cnt[tid] = 0;
             __syncthreads();
-            for_each_pair(cb, cb + len, [&](int d, unsigned, float) { atomicAdd(&cnt[d], 1); });
+            for (unsigned e = cb + tid; e < cb + len; e += TILE) {
+                const unsigned pd = __ldcs(ep + e);
+                const float ox = __ldcs(ex + e), oy = __ldcs(ey + e);
+                const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
+                const float a = (pd & kDirBit) ? a_b : a_f;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                    const float wa = fp.w[k] * a;
+                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f) {
+                        const int d = ly * TW + lx;
+                        const int slot = atomicAdd(&cnt[d], 1);
+                        if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
+                    }
+                }
+            }
             __syncthreads();
-            const int over = __syncthreads_or(cnt[tid] > kDepth);
+            const int over = __syncthreads_or(cnt[tid] > kSmemDepth);
             if (!over || len == 1) break;
             len = (len + 1) >> 1;
         }
         const bool whole_bin = (cb == beg) && (cb + len == end);
-        const int my_cnt = min(cnt[tid], kDepth);
-        __syncthreads();
-        cnt[tid] = 0;
-        __syncthreads();
-        for_each_pair(cb, cb + len, [&](int d, unsigned p, float wa) {
-            const int k = atomicAdd(&cnt[d], 1);
-            if (k < kDepth) ell[k * TILE + d] = make_uint2(p, __float_as_uint(wa));
-        });
-        __syncthreads();
+        const int my_cnt = cnt[tid];
 
-        // my list -> registers (conflict-free LDS: consecutive lanes read consecutive pairs)
+        // my list -> registers (conflict-free LDS: consecutive lanes read consecutive pairs);
+        // unused slots point at the zero pixel with weight 0
         unsigned pk[kDepth];
         float wk[kDepth];
         const int kmax = __reduce_max_sync(0xffffffffu, my_cnt);
         #pragma unroll
         for (int k = 0; k < kDepth; ++k) {
             const uint2 e = ell[k * TILE + tid];
-            pk[k] = k < my_cnt ? e.x : 0u;
+            pk[k] = k < my_cnt ? e.x : (unsigned)P;
             wk[k] = k < my_cnt ? __uint_as_float(e.y) : 0.0f;
         }
         partial = partial || !whole_bin;
 
         GatherCtx ctx;
-        ctx.G = reinterpret_cast<const char*>(prm.G4);
-        ctx.S = prm.S; ctx.P = P; ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
-        ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote; ctx.my_cnt = my_cnt;
+        ctx.G = prm.G; ctx.S = prm.S; ctx.ell = ell + tid; ctx.P = P;
+        ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
+        ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote;
+        ctx.my_cnt = my_cnt; ctx.kmax = kmax;
         // the list length is warp-uniform after the max-reduce: pick the unroll that fits
-        if (kmax <= 2) gather_lists<NT, 2>(ctx, pk, wk, nrm, tl);
-        else if (kmax <= 4) gather_lists<NT, 4>(ctx, pk, wk, nrm, tl);
-        else if (kmax <= 8) gather_lists<NT, 8>(ctx, pk, wk, nrm, tl);
-        else gather_lists<NT, 16>(ctx, pk, wk, nrm, tl);
+        switch ((kmax + 1) >> 1) {
+            case 0: case 1: gather_dispatch<NT, 2>(ctx, pk, wk, nrm, tl); break;
+            case 2: gather_dispatch<NT, 4>(ctx, pk, wk, nrm, tl); break;
+            case 3: gather_dispatch<NT, 6>(ctx, pk, wk, nrm, tl); break;
+            case 4: gather_dispatch<NT, 8>(ctx, pk, wk, nrm, tl); break;
+            case 5: gather_dispatch<NT, 10>(ctx, pk, wk, nrm, tl); break;
+#if SLR_GATHER_DEPTH == 16
+            case 6: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
+            case 7: gather_dispatch<NT, 14>(ctx, pk, wk, nrm, tl); break;
+            default: gather_dispatch<NT, 16>(ctx, pk, wk, nrm, tl); break;
+#else
+            default: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
+#endif
+        }
         wrote = true;
         cb += len;
         __syncthreads();
@@ -543,7 +595,7 @@ extern "C" size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames)
 extern "C" size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W)
 {
     if (C <= 0 || n_tail < 0 || H <= 0 || W <= 0) return 0;
-    return sizeof(float) * (size_t)(((C + 3) / 4) * 4 + n_tail + 1) * (size_t)(H * W);
+    return sizeof(float) * (size_t)(((C + 3) / 4) * 4 + n_tail + 1) * (size_t)(H * W + 1);
 }
 
 extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zsub,
@@ -556,8 +608,8 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
     const int64_t P = H * W;
     const int groups = (int)((C + 3) / 4);
     float4* G4 = (float4*)scene;
-    float* S = (float*)scene + (int64_t)groups * 4 * P;
-    dim3 grid((unsigned)((P + 255) / 256), (unsigned)std::min(groups, 4), 1);
+    float* S = (float*)scene + (int64_t)groups * 4 * (P + 1);
+    dim3 grid((unsigned)((P + 1 + 255) / 256), (unsigned)std::min(groups, 4), 1);
     scene_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(feat, z, zsub, tail, n_tail, G4, S, (int)C, P);
     return SLR_LAUNCH_STATUS();
 }
@@ -603,8 +655,8 @@ extern "C" int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t
 
     GatherParams prm;
     const int groups = (int)((C + 3) / 4);
-    prm.G4 = (const float4*)scene;
-    prm.S = (const float*)scene + (int64_t)groups * 4 * P;
+    prm.G = (const char*)scene;
+    prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
     prm.ent_p = ws.ent_p; prm.ent_x = ws.ent_x; prm.ent_y = ws.ent_y; prm.offsets = ws.offsets;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
@@ -618,9 +670,16 @@ extern "C" int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t
     }
     dim3 grid((unsigned)n_tiles, (unsigned)n_frames, 1);
     cudaStream_t s = (cudaStream_t)stream_;
-    if (n_tail == 0) gather_kernel<0><<<grid, TILE, 0, s>>>(prm);
-    else if (n_tail == 1) gather_kernel<1><<<grid, TILE, 0, s>>>(prm);
-    else gather_kernel<2><<<grid, TILE, 0, s>>>(prm);
+    static bool attr_set = false;      // opt in to > 48 KB dynamic shared memory once
+    if (!attr_set) {
+        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        attr_set = true;
+    }
+    if (n_tail == 0) gather_kernel<0><<<grid, TILE, kGatherSmem, s>>>(prm);
+    else if (n_tail == 1) gather_kernel<1><<<grid, TILE, kGatherSmem, s>>>(prm);
+    else gather_kernel<2><<<grid, TILE, kGatherSmem, s>>>(prm);
     return SLR_LAUNCH_STATUS();
 }
 
