@@ -433,7 +433,8 @@ gather_kernel(const GatherParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* ell = reinterpret_cast<uint2*>(smem_raw);                 // ell[k * TILE + d], k < kSmemDepth
-    int* cnt = reinterpret_cast<int*>(ell + kSmemDepth * TILE);      // pairs per destination pixel
+    unsigned* cnt = reinterpret_cast<unsigned*>(ell + kSmemDepth * TILE);   // per destination pixel: bits 0-7 = used
+                                                                            // preferred slots, bits 8.. = overflow count
 
     const int tid = threadIdx.x;
     const int tile = blockIdx.x, f = blockIdx.y;
@@ -469,25 +470,34 @@ gather_kernel(const GatherParams prm)
                 const unsigned pd = __ldcs(ep + e);
                 const float ox = __ldcs(ex + e), oy = __ldcs(ey + e);
                 const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
-                const float a = (pd & kDirBit) ? a_b : a_f;
+                const unsigned dir = pd >> 31;
+                const float a = dir ? a_b : a_f;
                 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
                     const float wa = fp.w[k] * a;
                     if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f) {
+                        // Slot = (corner, direction) when free, so that slot k of neighbouring
+                        // destination pixels holds neighbouring sources (coalesced LDG.128 per slot,
+                        // and a deterministic summation order); collisions go to overflow slots >= 8.
                         const int d = ly * TW + lx;
-                        const int slot = atomicAdd(&cnt[d], 1);
+                        const unsigned pref = 2u * k + dir;
+                        const unsigned old = atomicOr(&cnt[d], 1u << pref);
+                        int slot = pref;
+                        if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
                         if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
                     }
                 }
             }
             __syncthreads();
-            const int over = __syncthreads_or(cnt[tid] > kSmemDepth);
+            const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
             if (!over || len == 1) break;
             len = (len + 1) >> 1;
         }
         const bool whole_bin = (cb == beg) && (cb + len == end);
-        const int my_cnt = cnt[tid];
+        const unsigned occ = cnt[tid] & 0xffu;          // which of the 8 preferred slots are used
+        const int n_ovf = (int)(cnt[tid] >> 8);         // overflow slots 8 .. 8 + n_ovf - 1
+        const int my_cnt = n_ovf > 0 ? 8 + n_ovf : 32 - __clz(occ);     // slots [0, my_cnt) may be used
 
         // my list -> registers (conflict-free LDS: consecutive lanes read consecutive pairs);
         // unused slots point at the zero pixel with weight 0
@@ -497,8 +507,9 @@ gather_kernel(const GatherParams prm)
         #pragma unroll
         for (int k = 0; k < kDepth; ++k) {
             const uint2 e = ell[k * TILE + tid];
-            pk[k] = k < my_cnt ? e.x : (unsigned)P;
-            wk[k] = k < my_cnt ? __uint_as_float(e.y) : 0.0f;
+            const bool used = k < 8 ? (occ >> k & 1u) : (k - 8 < n_ovf);
+            pk[k] = used ? e.x : (unsigned)P;
+            wk[k] = used ? __uint_as_float(e.y) : 0.0f;
         }
         partial = partial || !whole_bin;
 
