@@ -37,6 +37,9 @@ constexpr int TILE = TW * TH;          // threads per gather CTA, one destinatio
 #ifndef SLR_GATHER_DEPTH
 #define SLR_GATHER_DEPTH 16            // 12 or 16
 #endif
+#ifndef SLR_GATHER_PREFETCH
+#define SLR_GATHER_PREFETCH 0          // 1: prefetch the next channel group's lines into L1
+#endif
 #ifndef SLR_GATHER_MINBLOCKS
 #define SLR_GATHER_MINBLOCKS 2         // resident CTAs per SM the register budget is sized for
 #endif
@@ -373,6 +376,13 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
     float* o = c.out;
     for (int g = 0; g < c.groups; ++g, Gg += gstride, o += 4 * ostride) {
         float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#if SLR_GATHER_PREFETCH
+        if (g + 1 < c.groups) {
+            #pragma unroll
+            for (int k = 0; k < K; ++k)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(px16(Gg + gstride, pk[k])));
+        }
+#endif
         #pragma unroll
         for (int kb = 0; kb < K; kb += B) {
             float4 v[B];
@@ -503,7 +513,6 @@ gather_kernel(const GatherParams prm)
         // unused slots point at the zero pixel with weight 0
         unsigned pk[kDepth];
         float wk[kDepth];
-        const int kmax = __reduce_max_sync(0xffffffffu, my_cnt);
         #pragma unroll
         for (int k = 0; k < kDepth; ++k) {
             const uint2 e = ell[k * TILE + tid];
@@ -511,6 +520,16 @@ gather_kernel(const GatherParams prm)
             pk[k] = used ? e.x : (unsigned)P;
             wk[k] = used ? __uint_as_float(e.y) : 0.0f;
         }
+        // Static pixels: the forward and the backward source are the pixel itself (slots 0 and 1
+        // both NW with weight alpha and 1 - alpha).  Same source -> add the weights, free the slot.
+        int eff_cnt = my_cnt;
+        if (my_cnt == 2 && pk[0] == pk[1]) {
+            wk[0] += wk[1];
+            wk[1] = 0.0f;
+            pk[1] = (unsigned)P;
+            eff_cnt = 1;
+        }
+        const int kmax = __reduce_max_sync(0xffffffffu, eff_cnt);
         partial = partial || !whole_bin;
 
         GatherCtx ctx;
@@ -520,7 +539,10 @@ gather_kernel(const GatherParams prm)
         ctx.my_cnt = my_cnt; ctx.kmax = kmax;
         // the list length is warp-uniform after the max-reduce: pick the unroll that fits
         switch ((kmax + 1) >> 1) {
-            case 0: case 1: gather_dispatch<NT, 2>(ctx, pk, wk, nrm, tl); break;
+            case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
+            case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
+                    else gather_dispatch<NT, 2>(ctx, pk, wk, nrm, tl);
+                    break;
             case 2: gather_dispatch<NT, 4>(ctx, pk, wk, nrm, tl); break;
             case 3: gather_dispatch<NT, 6>(ctx, pk, wk, nrm, tl); break;
             case 4: gather_dispatch<NT, 8>(ctx, pk, wk, nrm, tl); break;
