@@ -37,9 +37,6 @@ constexpr int TILE = TW * TH;          // threads per gather CTA, one destinatio
 #ifndef SLR_GATHER_DEPTH
 #define SLR_GATHER_DEPTH 16            // 12 or 16
 #endif
-#ifndef SLR_GATHER_PREFETCH
-#define SLR_GATHER_PREFETCH 0          // 1: prefetch the next channel group's lines into L1
-#endif
 #ifndef SLR_GATHER_MINBLOCKS
 #define SLR_GATHER_MINBLOCKS 2         // resident CTAs per SM the register budget is sized for
 #endif
@@ -330,31 +327,31 @@ __device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
     return reinterpret_cast<const float4*>(a);
 }
 
-// One pass of a destination pixel over its (source, weight) list.  K = compile-time
-// number of register-resident list slots (the warp's longest list rounded up to
-// even, at most kDepth); longer lists continue from shared memory.  Loads are
-// issued in blocks of up to 8 independent LDG.128 before the FMAs that consume them.
-// FAST: the whole bin fits one pass and C % 4 == 0 -> plain normalised streaming stores.
-template <int NT, int K, bool FAST>
+// One pass of a destination pixel over its (source, weight) list.
+//   K    compile-time number of register-resident list slots (the warp's longest list
+//        rounded up, at most kDepth); longer lists continue from shared memory.
+//   GI   channel groups per iteration.  A warp pays one full HBM latency per iteration
+//        (some lane always misses L1), and the 16 resident warps per SM are too few to hide
+//        it, so every iteration puts K * GI <= 16 independent LDG.128 in flight.
+//   FAST the whole bin fits one pass and C % 4 == 0: plain normalised streaming stores.
+template <int NT, int K, int GI, bool FAST>
 __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned (&pk)[kDepth],
                                              const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
 {
-    constexpr int B = K <= 8 ? K : K / 2;
     const int64_t sstride = c.P + 1;
     // scalar planes: tail channels, then the e^Z weight (the normaliser)
-    #pragma unroll
-    for (int kb = 0; kb < K; kb += B) {
-        float sv[NT + 1][B];
+    {
+        float sv[NT + 1][K];
         #pragma unroll
-        for (int j = 0; j < B; ++j) {
+        for (int k = 0; k < K; ++k) {
             #pragma unroll
-            for (int t = 0; t <= NT; ++t) sv[t][j] = __ldg(c.S + (int64_t)t * sstride + pk[kb + j]);
+            for (int t = 0; t <= NT; ++t) sv[t][k] = __ldg(c.S + (int64_t)t * sstride + pk[k]);
         }
         #pragma unroll
-        for (int j = 0; j < B; ++j) {
+        for (int k = 0; k < K; ++k) {
             #pragma unroll
-            for (int t = 0; t < NT; ++t) tl[t] = fmaf(sv[t][j], wk[kb + j], tl[t]);
-            nrm = fmaf(sv[NT][j], wk[kb + j], nrm);
+            for (int t = 0; t < NT; ++t) tl[t] = fmaf(sv[t][k], wk[k], tl[t]);
+            nrm = fmaf(sv[NT][k], wk[k], nrm);
         }
     }
     if (K == kDepth) {
@@ -374,54 +371,63 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
     const size_t gstride = (size_t)(c.P + 1) * 16;
     const size_t ostride = (size_t)c.P;
     float* o = c.out;
-    for (int g = 0; g < c.groups; ++g, Gg += gstride, o += 4 * ostride) {
-        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#if SLR_GATHER_PREFETCH
-        if (g + 1 < c.groups) {
-            #pragma unroll
-            for (int k = 0; k < K; ++k)
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(px16(Gg + gstride, pk[k])));
-        }
-#endif
+    for (int g = 0; g < c.groups; g += GI, Gg += GI * gstride, o += 4 * GI * ostride) {
+        // K <= 8: all K * GI loads of the iteration are issued before the first FMA;
+        // longer lists (GI == 1) go in two halves to stay inside the register budget
+        constexpr int B = K <= 8 ? K : K / 2;
+        float4 accs[GI];
+        #pragma unroll
+        for (int gi = 0; gi < GI; ++gi) accs[gi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         #pragma unroll
         for (int kb = 0; kb < K; kb += B) {
-            float4 v[B];
+            float4 v[GI][B];
             #pragma unroll
-            for (int j = 0; j < B; ++j) v[j] = __ldg(px16(Gg, pk[kb + j]));
-            #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                acc.x = fmaf(v[j].x, wk[kb + j], acc.x);
-                acc.y = fmaf(v[j].y, wk[kb + j], acc.y);
-                acc.z = fmaf(v[j].z, wk[kb + j], acc.z);
-                acc.w = fmaf(v[j].w, wk[kb + j], acc.w);
-            }
-        }
-        if (K == kDepth) {
-            for (int k = kDepth; k < c.kmax; ++k) {       // rare: lists longer than the register file holds
-                const uint2 e = c.ell[k * TILE];
-                const bool on = k < c.my_cnt;
-                const float4 v = __ldg(px16(Gg, on ? e.x : (unsigned)c.P));
-                const float w = on ? __uint_as_float(e.y) : 0.0f;
-                acc.x = fmaf(v.x, w, acc.x);
-                acc.y = fmaf(v.y, w, acc.y);
-                acc.z = fmaf(v.z, w, acc.z);
-                acc.w = fmaf(v.w, w, acc.w);
-            }
-        }
-        if (c.inframe) {
-            if (FAST) {
-                __stcs(o, acc.x * inv);
-                __stcs(o + ostride, acc.y * inv);
-                __stcs(o + 2 * ostride, acc.z * inv);
-                __stcs(o + 3 * ostride, acc.w * inv);
-            } else {
-                const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+            for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (4 * g + j < c.C) {
-                        float* oj = o + j * ostride;
-                        if (c.whole_bin) __stcs(oj, r[j] * inv);
-                        else *oj = c.wrote ? *oj + r[j] : r[j];
+                for (int k = 0; k < B; ++k) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
+            }
+            #pragma unroll
+            for (int gi = 0; gi < GI; ++gi) {
+                #pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    accs[gi].x = fmaf(v[gi][k].x, wk[kb + k], accs[gi].x);
+                    accs[gi].y = fmaf(v[gi][k].y, wk[kb + k], accs[gi].y);
+                    accs[gi].z = fmaf(v[gi][k].z, wk[kb + k], accs[gi].z);
+                    accs[gi].w = fmaf(v[gi][k].w, wk[kb + k], accs[gi].w);
+                }
+            }
+        }
+        #pragma unroll
+        for (int gi = 0; gi < GI; ++gi) {
+            float4 acc = accs[gi];
+            if (K == kDepth) {
+                for (int k = kDepth; k < c.kmax; ++k) {       // rare: lists longer than the register file holds
+                    const uint2 e = c.ell[k * TILE];
+                    const bool on = k < c.my_cnt;
+                    const float4 t = __ldg(px16(Gg + gi * gstride, on ? e.x : (unsigned)c.P));
+                    const float w = on ? __uint_as_float(e.y) : 0.0f;
+                    acc.x = fmaf(t.x, w, acc.x);
+                    acc.y = fmaf(t.y, w, acc.y);
+                    acc.z = fmaf(t.z, w, acc.z);
+                    acc.w = fmaf(t.w, w, acc.w);
+                }
+            }
+            if (c.inframe) {
+                float* og = o + 4 * gi * ostride;
+                if (FAST) {
+                    __stcs(og, acc.x * inv);
+                    __stcs(og + ostride, acc.y * inv);
+                    __stcs(og + 2 * ostride, acc.z * inv);
+                    __stcs(og + 3 * ostride, acc.w * inv);
+                } else {
+                    const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (4 * (g + gi) + j < c.C) {
+                            float* oj = og + j * ostride;
+                            if (c.whole_bin) __stcs(oj, r[j] * inv);
+                            else *oj = c.wrote ? *oj + r[j] : r[j];
+                        }
                     }
                 }
             }
@@ -433,8 +439,13 @@ template <int NT, int K>
 __device__ __forceinline__ void gather_dispatch(const GatherCtx& c, const unsigned (&pk)[kDepth],
                                                 const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
 {
-    if (c.whole_bin && (c.C & 3) == 0) gather_lists<NT, K, true>(c, pk, wk, nrm, tl);
-    else gather_lists<NT, K, false>(c, pk, wk, nrm, tl);
+    constexpr int GI = K == 1 ? 16 : K == 2 ? 8 : K <= 4 ? 4 : K <= 8 ? 2 : 1;
+    if (c.whole_bin && (c.C & 3) == 0) {
+        if (c.groups % GI == 0) gather_lists<NT, K, GI, true>(c, pk, wk, nrm, tl);
+        else gather_lists<NT, K, 1, true>(c, pk, wk, nrm, tl);
+    } else {
+        gather_lists<NT, K, 1, false>(c, pk, wk, nrm, tl);
+    }
 }
 
 template <int NT>
