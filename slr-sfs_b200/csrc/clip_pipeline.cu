@@ -302,7 +302,7 @@ struct GatherParams {
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
-    int C, groups, H, W, tiles_x, n_tiles;
+    int C, groups, H, W, tiles_x, n_tiles, n_frames;
     int64_t P, cap;
     float eps;
     FrameAlphas alphas;
@@ -458,7 +458,11 @@ gather_kernel(const GatherParams prm)
                                                                             // preferred slots, bits 8.. = overflow count
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x, f = blockIdx.y;
+    // Frame index fastest: the CTAs resident at any moment work on the SAME destination
+    // tiles of all frames of the batch.  Their source regions differ only by the
+    // frame-to-frame displacement, so a source line is fetched from HBM once per batch and
+    // the other frames hit it in L2 (one frame's features alone, 204 MB, exceed the L2).
+    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
     const bool inframe = X < prm.W && Y < prm.H;
@@ -712,7 +716,8 @@ extern "C" int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t
         a = fminf(fmaxf(a, alpha_lo), alpha_hi);
         prm.alphas.a[f] = a;
     }
-    dim3 grid((unsigned)n_tiles, (unsigned)n_frames, 1);
+    prm.n_frames = n_frames;
+    dim3 grid((unsigned)n_tiles * (unsigned)n_frames, 1, 1);
     cudaStream_t s = (cudaStream_t)stream_;
     static bool attr_set = false;      // opt in to > 48 KB dynamic shared memory once
     if (!attr_set) {
