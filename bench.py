@@ -144,6 +144,44 @@ def cpu_frames_per_second(args, n_frames, threads=None):
     return n_frames / dt, info
 
 
+def reference_gpu_frames_per_second(args, scene, dev):
+    """Informational (not the reference arm): the reference's own CUDA kernel on this GPU
+    (oracle/_ref/libref_softsplat_gpu.so: kernel text templated by the reference's cupy_kernel())
+    driven like forward_flow -- eager torch Euler loop, torch glue, two launches per frame --
+    on a 3-frame sample.  None when the library was not prebuilt or the shape is not baked in."""
+    try:
+        import torch
+        from oracle import refgpu
+        feat, Z, motion = scene
+        if not refgpu.available() or (1, feat.shape[1] + 1, feat.shape[2], feat.shape[3]) not in refgpu.baked_shapes():
+            return None
+        N = args.frames
+        picks = [0, N // 2, N - 1]
+        refgpu.reference_frame(feat, Z, motion, (0, 1, N - 1))          # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in picks:
+            refgpu.reference_frame(feat, Z, motion, (0, t, N - 1))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        # kernel-only time of the two splat launches of one frame
+        fwd = refgpu.euler_integration(motion, N // 2)
+        x = torch.cat([feat, Z], 1).contiguous()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        refgpu.softsplat_sum(x, fwd)
+        e0.record()
+        for _ in range(4):
+            refgpu.softsplat_sum(x, fwd)
+        e1.record()
+        torch.cuda.synchronize()
+        return {"value": len(picks) / dt, "unit": UNIT, "sample": "frames t=%s, host wall clock" % picks,
+                "splat_launch_ms": e0.elapsed_time(e1) / 4,
+                "what": "reference kernel_Softsplat_updateOutput (unmodified text, reference templating, nvcc sm_100a) + "
+                        "eager-torch restatement of euler_integration and the forward_flow glue"}
+    except Exception as exc:                                                # informational only
+        return {"error": repr(exc)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -365,15 +403,17 @@ def main():
                     "share_of_step": share,
                     "all_kernels_ms_per_frame": {k: v[0] / max(1, (hi - lo) * world * args.steps) for k, v in ktimes.items()}}
         cpu = None
+        ref_gpu = None
         if not args.no_cpu_baseline and world == 1:
             fps, info = cpu_frames_per_second(args, max(1, args.cpu_frames))
             cpu = dict(info, value=fps, unit=UNIT)
+            ref_gpu = reference_gpu_frames_per_second(args, resident[0], dev)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, algo), "clocks": clocks, "gpu_launches": launches,
-            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
             "whole_path_roofline_frac": value / world / (peak * 1e9 / (4.0 * P * (4 * C + 5))),
         }
         print(json.dumps(line))

@@ -49,6 +49,22 @@ constexpr unsigned kDirBit = 0x80000000u;
 
 struct FrameAlphas { float a[kMaxFrames]; };
 
+#ifndef SLR_GATHER_PATCH_LOG2H
+#define SLR_GATHER_PATCH_LOG2H 1       // warp patch height = 1 << this (0: 32x1, 1: 16x2, 2: 8x4)
+#endif
+constexpr int kPH2 = SLR_GATHER_PATCH_LOG2H;      // log2 patch height
+constexpr int kPW2 = 5 - kPH2;                    // log2 patch width
+constexpr int kPatchesX = TW >> kPW2;             // patches per tile row
+// thread index <-> pixel inside the 32x8 tile
+__device__ __forceinline__ int tile_lx(int tid) { return (((tid >> 5) % kPatchesX) << kPW2) + (tid & ((1 << kPW2) - 1)); }
+__device__ __forceinline__ int tile_ly(int tid) { return (((tid >> 5) / kPatchesX) << kPH2) + ((tid & 31) >> kPW2); }
+__device__ __forceinline__ int tile_thread(int lx, int ly)
+{
+    const int warp = (ly >> kPH2) * kPatchesX + (lx >> kPW2);
+    const int lane = ((ly & ((1 << kPH2) - 1)) << kPW2) + (lx & ((1 << kPW2) - 1));
+    return warp * 32 + lane;
+}
+
 // Destination tiles touched by a footprint, in a fixed order shared by the count
 // and the fill pass.  East / south columns only count when their weight is
 // non-zero (landing exactly on a cell -- static pixels -- touches one cell).
@@ -464,7 +480,9 @@ gather_kernel(const GatherParams prm)
     // the other frames hit it in L2 (one frame's features alone, 204 MB, exceed the L2).
     const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
-    const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
+    // thread -> destination pixel: a warp covers a PW x PH patch (32x1, 16x2 or 8x4) so that the
+    // sources two vertically adjacent destination pixels share are touched by the same warp
+    const int X = tx * TW + tile_lx(tid), Y = ty * TH + tile_ly(tid);
     const bool inframe = X < prm.W && Y < prm.H;
     const int64_t P = prm.P;
     const int64_t pix = (int64_t)Y * prm.W + X;
@@ -505,7 +523,7 @@ gather_kernel(const GatherParams prm)
                         // Slot = (corner, direction) when free, so that slot k of neighbouring
                         // destination pixels holds neighbouring sources (coalesced LDG.128 per slot,
                         // and a deterministic summation order); collisions go to overflow slots >= 8.
-                        const int d = ly * TW + lx;
+                        const int d = tile_thread(lx, ly);
                         const unsigned pref = 2u * k + dir;
                         const unsigned old = atomicOr(&cnt[d], 1u << pref);
                         int slot = pref;
