@@ -37,11 +37,17 @@ constexpr int TILE = TW * TH;          // threads per gather CTA, one destinatio
 #ifndef SLR_GATHER_DEPTH
 #define SLR_GATHER_DEPTH 16            // 12 or 16
 #endif
+#ifndef SLR_GATHER_EXPERIMENT
+#define SLR_GATHER_EXPERIMENT 0        // 1 / 2: timing experiments (no stores / no feature loads), results invalid
+#endif
 #ifndef SLR_GATHER_MINBLOCKS
 #define SLR_GATHER_MINBLOCKS 2         // resident CTAs per SM the register budget is sized for
 #endif
 constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread holds in registers
-constexpr int kSmemDepth = 32;         // pairs per destination pixel the shared list table holds
+#ifndef SLR_GATHER_SMEM_DEPTH
+#define SLR_GATHER_SMEM_DEPTH 32
+#endif
+constexpr int kSmemDepth = SLR_GATHER_SMEM_DEPTH;   // pairs per destination pixel the shared list table holds
 constexpr int kChunk = 8192;           // bin entries expanded per pass
 constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
 constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the parameters)
@@ -50,7 +56,7 @@ constexpr unsigned kDirBit = 0x80000000u;
 struct FrameAlphas { float a[kMaxFrames]; };
 
 #ifndef SLR_GATHER_PATCH_LOG2H
-#define SLR_GATHER_PATCH_LOG2H 1       // warp patch height = 1 << this (0: 32x1, 1: 16x2, 2: 8x4)
+#define SLR_GATHER_PATCH_LOG2H 0       // warp patch height = 1 << this (0: 32x1, 1: 16x2, 2: 8x4)
 #endif
 constexpr int kPH2 = SLR_GATHER_PATCH_LOG2H;      // log2 patch height
 constexpr int kPW2 = 5 - kPH2;                    // log2 patch width
@@ -400,7 +406,11 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
+#if SLR_GATHER_EXPERIMENT == 2 || SLR_GATHER_EXPERIMENT == 3     // timing experiment only: no feature loads
+                for (int k = 0; k < B; ++k) v[gi][k] = make_float4(__uint_as_float(pk[kb + k]), 1.0f, 2.0f, 3.0f);
+#else
                 for (int k = 0; k < B; ++k) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
+#endif
             }
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
@@ -430,6 +440,9 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
             }
             if (c.inframe) {
                 float* og = o + 4 * gi * ostride;
+#if SLR_GATHER_EXPERIMENT == 1 || SLR_GATHER_EXPERIMENT == 3     // timing experiment only: no output stores
+                if (acc.x + acc.y + acc.z + acc.w == 1.2345e30f) *og = inv;
+#else
                 if (FAST) {
                     __stcs(og, acc.x * inv);
                     __stcs(og + ostride, acc.y * inv);
@@ -446,6 +459,7 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
                         }
                     }
                 }
+#endif
             }
         }
     }
@@ -571,6 +585,10 @@ gather_kernel(const GatherParams prm)
         ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote;
         ctx.my_cnt = my_cnt; ctx.kmax = kmax;
         // the list length is warp-uniform after the max-reduce: pick the unroll that fits
+#if SLR_GATHER_EXPERIMENT == 4      // timing experiment only: list building alone
+        if (kmax == 12345) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
+        if (wk[0] + wk[1] + wk[5] == 1.2345e30f) out[0] = wk[3];
+#else
         switch ((kmax + 1) >> 1) {
             case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
             case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
@@ -588,6 +606,7 @@ gather_kernel(const GatherParams prm)
             default: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
 #endif
         }
+#endif
         wrote = true;
         cb += len;
         __syncthreads();
