@@ -147,10 +147,11 @@ size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames);
  * workspace: slr_clip_workspace_bytes(H, W, n_frames) bytes, 16-byte aligned.
  * slr_clip_frames = slr_clip_plan (Euler chains, landing table, destination-tile
  * bins; depends on the motion only) followed by slr_clip_gather (the gather
- * kernel) on the same workspace. */
+ * kernel) on the same workspace and the same motion (pixels whose motion is
+ * exactly zero are not binned; the gather adds their self-contribution). */
 int slr_clip_plan(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
                   int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream);
-int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t H, int64_t W,
+int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
                     int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
                     float* out, float* aux, float* mask,
                     const void* workspace, size_t workspace_bytes, slr_stream_t stream);

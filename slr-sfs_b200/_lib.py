@@ -33,7 +33,7 @@ SIGNATURES = {
     "slr_scene_prep": [_f32p, _f32p, _f32p, _f32p, _int, _f32p, _i64, _i64, _i64, _strm],
     "slr_clip_workspace_bytes": [_i64, _i64, _int],
     "slr_clip_plan": [_f32p, _i64, _i64, _int, _int, _int, _int, _f32p, ctypes.c_size_t, _strm],
-    "slr_clip_gather": [_f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
+    "slr_clip_gather": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
                         _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_frames": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
                         _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],

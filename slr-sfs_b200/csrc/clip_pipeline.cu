@@ -52,6 +52,7 @@ constexpr int kChunk = 8192;           // bin entries expanded per pass
 constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
 constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the parameters)
 constexpr unsigned kDirBit = 0x80000000u;
+constexpr float kStaticLand = -1.0e30f;  // landing marker of pixels that are not binned
 
 struct FrameAlphas { float a[kMaxFrames]; };
 
@@ -181,10 +182,21 @@ euler_table_kernel(const float* __restrict__ motion, int H, int W, int steps_f0,
     const float xmax = (float)(W - 1), ymax = (float)(H - 1);
     const float sentinel = (float)(max(H, W) + 1);
 
+    // Static pixels (motion exactly 0 at the pixel: it never moves, in either direction) are
+    // not binned at all: the gather adds their self-contribution implicitly.  Their landing
+    // entry is a far-away marker, which the count and fill passes skip like any off-frame pixel.
+    const bool is_static = __ldg(motion + p) == 0.0f && __ldg(motion + P + p) == 0.0f;
+    if (__all_sync(0xffffffffu, is_static || !active)) {
+        if (active)
+            for (int i = 0; i < 4 * n; ++i) land[(int64_t)i * P + p] = kStaticLand;
+        return;
+    }
+
     auto emit = [&](const EulerState& s, int f, int dir) {
         const float ddx = s.invalid ? sentinel : __fsub_rn(s.dx, cx);
         const float ddy = s.invalid ? sentinel : __fsub_rn(s.dy, cy);
-        const float ox = __fadd_rn(cx, ddx), oy = __fadd_rn(cy, ddy);
+        const float ox = is_static ? kStaticLand : __fadd_rn(cx, ddx);
+        const float oy = is_static ? kStaticLand : __fadd_rn(cy, ddy);
         int tiles[4];
         if (active) {
             float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
@@ -270,8 +282,8 @@ bin_scan_kernel(unsigned* __restrict__ counts, unsigned* __restrict__ offsets, i
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ offsets,
-                unsigned* __restrict__ cursors, unsigned* __restrict__ ent_p, float* __restrict__ ent_x,
-                float* __restrict__ ent_y, int H, int W, int tiles_x, int n_tiles, int64_t cap)
+                unsigned* __restrict__ cursors, float4* __restrict__ ent,
+                int H, int W, int tiles_x, int n_tiles, int64_t cap)
 {
     const int64_t P = (int64_t)H * W;
     const int f = blockIdx.y;
@@ -280,9 +292,7 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
     const int64_t p = active ? p_raw : 0;
     const unsigned* off = offsets + (int64_t)f * (n_tiles + 1);
     unsigned* cur = cursors + (int64_t)f * n_tiles;
-    unsigned* ep = ent_p + (int64_t)f * cap;
-    float* ex = ent_x + (int64_t)f * cap;
-    float* ey = ent_y + (int64_t)f * cap;
+    float4* e = ent + (int64_t)f * cap;
     #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
         const float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
@@ -300,9 +310,7 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
             const unsigned slot = warp_reserve(cur, tiles[k]);
             if (tiles[k] >= 0) {
                 const int64_t at = (int64_t)off[tiles[k]] + slot;
-                ep[at] = (unsigned)p | (dir ? kDirBit : 0u);
-                ex[at] = ox;
-                ey[at] = oy;
+                e[at] = make_float4(__uint_as_float((unsigned)p | (dir ? kDirBit : 0u)), ox, oy, 0.0f);
             }
         }
     }
@@ -317,9 +325,8 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
 struct GatherParams {
     const char* G;             // [groups] planes of (P + 1) float4
     const float* S;            // [n_tail + 1] planes of (P + 1) float   (last plane = e^Z)
-    const unsigned* ent_p;     // [frames][cap]
-    const float* ent_x;
-    const float* ent_y;
+    const float4* ent;         // [frames][cap]  (pixel | dir << 31, landing x, landing y, -)
+    const float* motion;       // [2][P]: a destination pixel with zero motion contributes to itself
     const unsigned* offsets;   // [frames][n_tiles + 1]
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
@@ -504,9 +511,8 @@ gather_kernel(const GatherParams prm)
 
     const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
     const unsigned beg = off[tile], end = off[tile + 1];
-    const unsigned* ep = prm.ent_p + (int64_t)f * prm.cap;
-    const float* ex = prm.ent_x + (int64_t)f * prm.cap;
-    const float* ey = prm.ent_y + (int64_t)f * prm.cap;
+    const float4* ent = prm.ent + (int64_t)f * prm.cap;
+    const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
     float* out = prm.out + (int64_t)f * prm.C * P + pix;
 
     float nrm = 0.0f;
@@ -515,17 +521,22 @@ gather_kernel(const GatherParams prm)
     bool partial = false;        // outputs were written un-normalised (multi-pass bin)
 
     unsigned cb = beg;
-    while (cb < end) {
+    bool first_pass = true;
+    while (first_pass || cb < end) {
         // Expand entries [cb, cb+len) into per-destination lists.  If a destination pixel
         // overflows the table (> kSmemDepth pairs: sinks, strong compression) retry with half
         // the entries; one entry adds at most one pair per pixel, so this terminates.
         unsigned len = min((unsigned)kChunk, end - cb);
         for (;;) {
-            cnt[tid] = 0;
+            // a static destination pixel receives itself with weight alpha + (1 - alpha)
+            // (its forward and backward splat both land exactly on it), once per bin
+            cnt[tid] = (first_pass && self_static) ? 1u : 0u;
+            if (first_pass && self_static) ell[tid] = make_uint2((unsigned)pix, __float_as_uint(a_f + a_b));
             __syncthreads();
             for (unsigned e = cb + tid; e < cb + len; e += TILE) {
-                const unsigned pd = __ldcs(ep + e);
-                const float ox = __ldcs(ex + e), oy = __ldcs(ey + e);
+                const float4 en = __ldcs(ent + e);
+                const unsigned pd = __float_as_uint(en.x);
+                const float ox = en.y, oy = en.z;
                 const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
                 const unsigned dir = pd >> 31;
                 const float a = dir ? a_b : a_f;
@@ -608,6 +619,7 @@ gather_kernel(const GatherParams prm)
         }
 #endif
         wrote = true;
+        first_pass = false;
         cb += len;
         __syncthreads();
     }
@@ -643,9 +655,7 @@ struct Workspace {
     float* land;          // [n][2 dirs][2][P]
     unsigned* counts;     // [n][n_tiles]      (counts, then cursors)
     unsigned* offsets;    // [n][n_tiles + 1]
-    unsigned* ent_p;      // [n][cap]
-    float* ent_x;
-    float* ent_y;
+    float4* ent;          // [n][cap]
     size_t bytes;
 };
 
@@ -662,9 +672,7 @@ Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.land = (float*)(p + o);        o += align_up(sizeof(float) * 4 * P * n);
     w.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
     w.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
-    w.ent_p = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * cap * n);
-    w.ent_x = (float*)(p + o);       o += align_up(sizeof(float) * cap * n);
-    w.ent_y = (float*)(p + o);       o += align_up(sizeof(float) * cap * n);
+    w.ent = (float4*)(p + o);        o += align_up(sizeof(float4) * cap * n);
     w.bytes = o;
     return w;
 }
@@ -718,17 +726,17 @@ extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int star
     euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
                                                ws.land, ws.counts, tiles_x, n_tiles);
     bin_scan_kernel<<<n_frames, 1024, 0, s>>>(ws.counts, ws.offsets, n_tiles);
-    bin_fill_kernel<<<dim3(pblocks, n_frames), 256, 0, s>>>(ws.land, ws.offsets, ws.counts, ws.ent_p, ws.ent_x,
-                                                            ws.ent_y, (int)H, (int)W, tiles_x, n_tiles, 8 * P);
+    bin_fill_kernel<<<dim3(pblocks, n_frames), 256, 0, s>>>(ws.land, ws.offsets, ws.counts, ws.ent,
+                                                            (int)H, (int)W, tiles_x, n_tiles, 8 * P);
     return SLR_LAUNCH_STATUS();
 }
 
-extern "C" int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t H, int64_t W,
+extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
                                int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
                                float* out, float* aux, float* mask,
                                const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
 {
-    SLR_CHECK_ARGS(scene && out && workspace && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
+    SLR_CHECK_ARGS(scene && motion && out && workspace && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
                    n_tail >= 0 && n_tail <= 2 && n_frames > 0 && n_frames <= kMaxFrames &&
                    t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)workspace & 15) == 0,
                    "slr_clip_gather: bad arguments");
@@ -742,7 +750,7 @@ extern "C" int slr_clip_gather(const void* scene, int64_t C, int n_tail, int64_t
     const int groups = (int)((C + 3) / 4);
     prm.G = (const char*)scene;
     prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
-    prm.ent_p = ws.ent_p; prm.ent_x = ws.ent_x; prm.ent_y = ws.ent_y; prm.offsets = ws.offsets;
+    prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
@@ -777,6 +785,6 @@ extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C
 {
     int rc = slr_clip_plan(motion, H, W, start, end, t0, n_frames, workspace, workspace_bytes, stream_);
     if (rc) return rc;
-    return slr_clip_gather(scene, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+    return slr_clip_gather(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                            out, aux, mask, workspace, workspace_bytes, stream_);
 }

@@ -60,7 +60,7 @@ class JointSplat:
 
     #: frames per slr_clip_frames launch (bigger batches amortise the Euler chains,
     #: smaller ones keep the landing table and the bins inside the 126 MB L2)
-    batch = 6
+    batch = 12
 
     def __init__(self, features, Z, motion, z_mode="max", tail=None):
         assert features.dim() == 4 and features.shape[0] == 1
@@ -117,7 +117,7 @@ class JointSplat:
                 ws, ws_bytes = self._scratch(nb)
                 _lib.call("slr_clip_plan", _lib.ptr(self.motion), H, W, start, end, t0 + b0, nb,
                           _lib.ptr(ws), ws_bytes, s)
-                _lib.call("slr_clip_gather", _lib.ptr(scene), C, self.n_tail, H, W,
+                _lib.call("slr_clip_gather", _lib.ptr(scene), _lib.ptr(self.motion), C, self.n_tail, H, W,
                           start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1], _lib.ptr(out[b0:]),
                           None if aux is None else _lib.ptr(aux[b0:]),
                           None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes, s)

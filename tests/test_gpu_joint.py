@@ -205,3 +205,28 @@ def test_gather_matches_scatter_full_size_stress_motion(pkg):
         a = js.frame_scatter((0, t, N - 1))
         b = js.frame((0, t, N - 1))
         assert rel_err(b.cpu().numpy(), a.cpu().numpy()) <= TOL
+
+
+def test_static_pixels_are_implicit_self_contributions(pkg):
+    """Pixels with exactly zero motion are not binned; the gather adds their self-contribution.
+    All-static scene: output == features (weights cancel); half-static scene with sources
+    flowing onto static pixels: matches the oracle."""
+    H, W, C, N = 40, 70, 8, 12
+    rng = np.random.default_rng(21)
+    feat = rng.standard_normal((1, C, H, W)).astype(np.float32)
+    Z = rng.standard_normal((1, 1, H, W)).astype(np.float32)
+    zero = np.zeros((1, 2, H, W), np.float32)
+    js = pkg.JointSplat(cu(feat), cu(Z), cu(zero))
+    out = js.frames(0, N - 1, 0, N).cpu().numpy()
+    for t in (0, 5, N - 1):
+        assert rel_err(out[t:t + 1], feat) <= 1e-6
+    m = zero.copy()
+    m[0, 0, :, : W // 2] = 1.7          # left half streams right, onto the static right half
+    m[0, 1, : H // 2, : W // 2] = -0.6
+    m[0, 0, 3, 5] = -0.0                # negative zero is static too
+    m[0, 1, 3, 5] = 0.0
+    js = pkg.JointSplat(cu(feat), cu(Z), cu(m))
+    for t in (1, 6, N - 1):
+        want = oracle.joint_splat_baseline(feat, Z, m, (0, t, N - 1))
+        assert rel_err(js.frame((0, t, N - 1)).cpu().numpy(), want) <= TOL
+        assert rel_err(js.frame_scatter((0, t, N - 1)).cpu().numpy(), want) <= TOL
