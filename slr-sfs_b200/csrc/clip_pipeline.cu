@@ -49,7 +49,7 @@ constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread ho
 #endif
 constexpr int kSmemDepth = SLR_GATHER_SMEM_DEPTH;   // pairs per destination pixel the shared list table holds
 constexpr int kChunk = 8192;           // bin entries expanded per pass
-constexpr int kGatherSmem = kSmemDepth * TILE * 8 + 2 * TILE * 4 + 16;
+constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
 constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the parameters)
 constexpr unsigned kDirBit = 0x80000000u;
 constexpr float kStaticLand = -1.0e30f;  // landing marker of pixels that are not binned
@@ -485,233 +485,161 @@ __device__ __forceinline__ void gather_dispatch(const GatherCtx& c, const unsign
     }
 }
 
-// Work item = (destination tile, frame), frame index fastest: the CTAs resident at any
-// moment work on the SAME destination tiles of all frames of the batch.  Their source
-// regions differ only by the frame-to-frame displacement, so a source line is fetched from
-// HBM once per batch and the other frames hit it in L2 (one frame's features alone, 204 MB,
-// exceed the 126 MB L2).
-struct GatherItem {
-    int f, tx, ty;
-    int64_t pix;          // this thread's destination pixel (may be outside the frame)
-    bool inframe, self_static;
-    unsigned beg, end;    // bin entry range
-};
-
-__device__ __forceinline__ GatherItem load_item(const GatherParams& prm, int item, int tid)
-{
-    GatherItem it;
-    it.f = item % prm.n_frames;
-    const int tile = item / prm.n_frames;
-    it.tx = tile % prm.tiles_x;
-    it.ty = tile / prm.tiles_x;
-    const int X = it.tx * TW + tile_lx(tid), Y = it.ty * TH + tile_ly(tid);
-    it.inframe = X < prm.W && Y < prm.H;
-    it.pix = (int64_t)Y * prm.W + X;
-    // a destination pixel with exactly zero motion receives itself (it was not binned)
-    it.self_static = it.inframe && __ldg(prm.motion + it.pix) == 0.0f && __ldg(prm.motion + prm.P + it.pix) == 0.0f;
-    const unsigned* off = prm.offsets + (int64_t)it.f * (prm.n_tiles + 1) + tile;
-    it.beg = __ldg(off);
-    it.end = __ldg(off + 1);
-    return it;
-}
-
-// Persistent kernel: each CTA walks work items blockIdx.x, blockIdx.x + gridDim.x, ...
-// Per item: (1) expand the bin into per-destination-pixel lists in shared memory,
-// (2) every thread copies its list into registers, (3) gather.  The list table is dead once
-// copied, and the per-pixel counters are double-buffered, so warps that finish their rows early
-// start expanding the NEXT item while slower warps still gather: the latency-bound expansion
-// overlaps the bandwidth-bound gather instead of adding to it.
 template <int NT>
 __global__ void __launch_bounds__(TILE, SLR_GATHER_MINBLOCKS)
-gather_kernel(const GatherParams prm, int n_items)
+gather_kernel(const GatherParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* ell = reinterpret_cast<uint2*>(smem_raw);                 // ell[k * TILE + d], k < kSmemDepth
-    // per destination pixel: bits 0-7 = used preferred slots, bits 8.. = overflow count; two buffers
-    unsigned* cnt2 = reinterpret_cast<unsigned*>(ell + kSmemDepth * TILE);
-    unsigned* cursor = cnt2 + 2 * TILE;                              // next unexpanded bin entry; two buffers
+    unsigned* cnt = reinterpret_cast<unsigned*>(ell + kSmemDepth * TILE);   // per destination pixel: bits 0-7 = used
+                                                                            // preferred slots, bits 8.. = overflow count
 
     const int tid = threadIdx.x;
+    // Frame index fastest: the CTAs resident at any moment work on the SAME destination
+    // tiles of all frames of the batch.  Their source regions differ only by the
+    // frame-to-frame displacement, so a source line is fetched from HBM once per batch and
+    // the other frames hit it in L2 (one frame's features alone, 204 MB, exceed the L2).
+    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+    // thread -> destination pixel: a warp covers a PW x PH patch (32x1, 16x2 or 8x4) so that the
+    // sources two vertically adjacent destination pixels share are touched by the same warp
+    const int X = tx * TW + tile_lx(tid), Y = ty * TH + tile_ly(tid);
+    const bool inframe = X < prm.W && Y < prm.H;
     const int64_t P = prm.P;
-    int item = blockIdx.x;
-    if (item >= n_items) return;
-    GatherItem cur = load_item(prm, item, tid);
-    int par = 0;
-    {   // counters (and the implicit self-pair) of the first item
-        const float a0 = prm.alphas.a[cur.f];
-        cnt2[tid] = cur.self_static ? 1u : 0u;
-        if (cur.self_static) ell[tid] = make_uint2((unsigned)cur.pix, __float_as_uint(a0 + (1.0f - a0)));
-        if (tid == 0) cursor[0] = 0u;
+    const int64_t pix = (int64_t)Y * prm.W + X;
+    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+
+    const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+    const unsigned beg = off[tile], end = off[tile + 1];
+    const float4* ent = prm.ent + (int64_t)f * prm.cap;
+    const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
+    float* out = prm.out + (int64_t)f * prm.C * P + pix;
+
+    float nrm = 0.0f;
+    float tl[NT > 0 ? NT : 1] = {0.0f};
+    bool wrote = false;          // this thread's output planes hold partial sums already
+    bool partial = false;        // outputs were written un-normalised (multi-pass bin)
+
+    unsigned cb = beg;
+    bool first_pass = true;
+    while (first_pass || cb < end) {
+        // Expand entries [cb, cb+len) into per-destination lists.  If a destination pixel
+        // overflows the table (> kSmemDepth pairs: sinks, strong compression) retry with half
+        // the entries; one entry adds at most one pair per pixel, so this terminates.
+        unsigned len = min((unsigned)kChunk, end - cb);
+        for (;;) {
+            // a static destination pixel receives itself with weight alpha + (1 - alpha)
+            // (its forward and backward splat both land exactly on it), once per bin
+            cnt[tid] = (first_pass && self_static) ? 1u : 0u;
+            if (first_pass && self_static) ell[tid] = make_uint2((unsigned)pix, __float_as_uint(a_f + a_b));
+            __syncthreads();
+            for (unsigned e = cb + tid; e < cb + len; e += TILE) {
+                const float4 en = __ldcs(ent + e);
+                const unsigned pd = __float_as_uint(en.x);
+                const float ox = en.y, oy = en.z;
+                const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
+                const unsigned dir = pd >> 31;
+                const float a = dir ? a_b : a_f;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                    const float wa = fp.w[k] * a;
+                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f) {
+                        // Slot = (corner, direction) when free, so that slot k of neighbouring
+                        // destination pixels holds neighbouring sources (coalesced LDG.128 per slot,
+                        // and a deterministic summation order); collisions go to overflow slots >= 8.
+                        const int d = tile_thread(lx, ly);
+                        const unsigned pref = 2u * k + dir;
+                        const unsigned old = atomicOr(&cnt[d], 1u << pref);
+                        int slot = pref;
+                        if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
+                        if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
+                    }
+                }
+            }
+            __syncthreads();
+            const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
+            if (!over || len == 1) break;
+            len = (len + 1) >> 1;
+        }
+        const bool whole_bin = (cb == beg) && (cb + len == end);
+        const unsigned occ = cnt[tid] & 0xffu;          // which of the 8 preferred slots are used
+        const int n_ovf = (int)(cnt[tid] >> 8);         // overflow slots 8 .. 8 + n_ovf - 1
+        const int my_cnt = n_ovf > 0 ? 8 + n_ovf : 32 - __clz(occ);     // slots [0, my_cnt) may be used
+
+        // my list -> registers (conflict-free LDS: consecutive lanes read consecutive pairs);
+        // unused slots point at the zero pixel with weight 0
+        unsigned pk[kDepth];
+        float wk[kDepth];
+        #pragma unroll
+        for (int k = 0; k < kDepth; ++k) {
+            const uint2 e = ell[k * TILE + tid];
+            const bool used = k < 8 ? (occ >> k & 1u) : (k - 8 < n_ovf);
+            pk[k] = used ? e.x : (unsigned)P;
+            wk[k] = used ? __uint_as_float(e.y) : 0.0f;
+        }
+        // Static pixels: the forward and the backward source are the pixel itself (slots 0 and 1
+        // both NW with weight alpha and 1 - alpha).  Same source -> add the weights, free the slot.
+        int eff_cnt = my_cnt;
+        if (my_cnt == 2 && pk[0] == pk[1]) {
+            wk[0] += wk[1];
+            wk[1] = 0.0f;
+            pk[1] = (unsigned)P;
+            eff_cnt = 1;
+        }
+        const int kmax = __reduce_max_sync(0xffffffffu, eff_cnt);
+        partial = partial || !whole_bin;
+
+        GatherCtx ctx;
+        ctx.G = prm.G; ctx.S = prm.S; ctx.ell = ell + tid; ctx.P = P;
+        ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
+        ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote;
+        ctx.my_cnt = my_cnt; ctx.kmax = kmax;
+        // the list length is warp-uniform after the max-reduce: pick the unroll that fits
+#if SLR_GATHER_EXPERIMENT == 4      // timing experiment only: list building alone
+        if (kmax == 12345) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
+        if (wk[0] + wk[1] + wk[5] == 1.2345e30f) out[0] = wk[3];
+#else
+        switch ((kmax + 1) >> 1) {
+            case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
+            case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
+                    else gather_dispatch<NT, 2>(ctx, pk, wk, nrm, tl);
+                    break;
+            case 2: gather_dispatch<NT, 4>(ctx, pk, wk, nrm, tl); break;
+            case 3: gather_dispatch<NT, 6>(ctx, pk, wk, nrm, tl); break;
+            case 4: gather_dispatch<NT, 8>(ctx, pk, wk, nrm, tl); break;
+            case 5: gather_dispatch<NT, 10>(ctx, pk, wk, nrm, tl); break;
+#if SLR_GATHER_DEPTH == 16
+            case 6: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
+            case 7: gather_dispatch<NT, 14>(ctx, pk, wk, nrm, tl); break;
+            default: gather_dispatch<NT, 16>(ctx, pk, wk, nrm, tl); break;
+#else
+            default: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
+#endif
+        }
+#endif
+        wrote = true;
+        first_pass = false;
+        cb += len;
         __syncthreads();
     }
 
-    for (; item < n_items; item += gridDim.x, par ^= 1) {
-        unsigned* cnt = cnt2 + par * TILE;
-        const int next_item = item + gridDim.x;
-        const bool has_next = next_item < n_items;
-        GatherItem nxt = cur;
-        if (has_next) nxt = load_item(prm, next_item, tid);        // loads complete while we expand
-
-        const int f = cur.f, tx = cur.tx, ty = cur.ty;
-        const bool inframe = cur.inframe;
-        const int64_t pix = cur.pix;
-        const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
-        const unsigned beg = cur.beg, end = cur.end;
-        const float4* ent = prm.ent + (int64_t)f * prm.cap;
-        float* out = prm.out + (int64_t)f * prm.C * P + pix;
-
-        float nrm = 0.0f;
-        float tl[NT > 0 ? NT : 1] = {0.0f};
-        bool wrote = false;          // this thread's output planes hold partial sums already
-        bool partial = false;        // outputs were written un-normalised (multi-pass bin)
-
-        unsigned cb = beg;
-        bool first_pass = true;
-        while (first_pass || cb < end) {
-            // Expand entries [cb, cb+len) into per-destination lists.  If a destination pixel
-            // overflows the table (> kSmemDepth pairs: sinks, strong compression) retry with
-            // half the entries; one entry adds at most one pair per pixel, so this terminates.
-            unsigned len = min((unsigned)kChunk, end - cb);
-            if (!first_pass) {          // later passes over a long bin: fresh counters
-                cnt[tid] = 0u;
-                if (tid == 0) cursor[par] = 0u;
-                __syncthreads();
-            }
-            for (;;) {
-                // Warps pull 32 entries at a time from a shared cursor: a warp that finished the
-                // previous item early expands most of this one while the others still gather.
-                for (;;) {
-                    unsigned base = 0;
-                    if ((tid & 31) == 0) base = atomicAdd(&cursor[par], 32u);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base >= len) break;
-                    const unsigned e = base + (tid & 31);
-                    if (e >= len) continue;
-                    const float4 en = __ldcs(ent + cb + e);
-                    const unsigned pd = __float_as_uint(en.x);
-                    const float ox = en.y, oy = en.z;
-                    const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
-                    const unsigned dir = pd >> 31;
-                    const float a = dir ? a_b : a_f;
-                    #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-                        const float wa = fp.w[k] * a;
-                        if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f) {
-                            // Slot = (corner, direction) when free, so that slot k of neighbouring
-                            // destination pixels holds neighbouring sources (coalesced LDG.128 per
-                            // slot, deterministic summation order); collisions go to slots >= 8.
-                            const int d = tile_thread(lx, ly);
-                            const unsigned pref = 2u * k + dir;
-                            const unsigned old = atomicOr(&cnt[d], 1u << pref);
-                            int slot = pref;
-                            if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
-                            if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
-                        }
-                    }
-                }
-                const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
-                if (!over || len <= 1) break;
-                len = (len + 1) >> 1;
-                const bool self = first_pass && cur.self_static;
-                cnt[tid] = self ? 1u : 0u;
-                if (self) ell[tid] = make_uint2((unsigned)pix, __float_as_uint(a_f + a_b));
-                if (tid == 0) cursor[par] = 0u;
-                __syncthreads();
-            }
-            const bool whole_bin = (cb == beg) && (cb + len == end);
-            const unsigned occ = cnt[tid] & 0xffu;          // which of the 8 preferred slots are used
-            const int n_ovf = (int)(cnt[tid] >> 8);         // overflow slots 8 .. 8 + n_ovf - 1
-            const int my_cnt = n_ovf > 0 ? 8 + n_ovf : 32 - __clz(occ);     // slots [0, my_cnt) may be used
-
-            // my list -> registers (conflict-free LDS: consecutive lanes read consecutive pairs);
-            // unused slots point at the zero pixel with weight 0
-            unsigned pk[kDepth];
-            float wk[kDepth];
-            #pragma unroll
-            for (int k = 0; k < kDepth; ++k) {
-                const uint2 e = ell[k * TILE + tid];
-                const bool used = k < 8 ? (occ >> k & 1u) : (k - 8 < n_ovf);
-                pk[k] = used ? e.x : (unsigned)P;
-                wk[k] = used ? __uint_as_float(e.y) : 0.0f;
-            }
-            const bool last_pass = cb + len >= end;
-            // Counters (other buffer) and self-pair of the NEXT item; own column of slot 0 is mine alone.
-            if (last_pass && has_next) {
-                const float an = prm.alphas.a[nxt.f];
-                cnt2[(par ^ 1) * TILE + tid] = nxt.self_static ? 1u : 0u;
-                if (nxt.self_static) ell[tid] = make_uint2((unsigned)nxt.pix, __float_as_uint(an + (1.0f - an)));
-                if (tid == 0) cursor[par ^ 1] = 0u;
-            }
-            // everyone has copied: the table may be overwritten -- unless some list continues in it
-            const int tail = __syncthreads_or(my_cnt > kDepth);
-#if SLR_GATHER_EXPERIMENT == 5      // timing experiment only: every feature load hits L1, aligned and coalesced
-            #pragma unroll
-            for (int k = 0; k < kDepth; ++k) if (wk[k] != 0.0f) pk[k] = (unsigned)((tid & 31) + 32 * k);
-#endif
-            // Same source twice (a static pixel hit by its own forward and backward splat):
-            // add the weights, free the slot.
-            int eff_cnt = my_cnt;
-            if (my_cnt == 2 && pk[0] == pk[1]) {
-                wk[0] += wk[1];
-                wk[1] = 0.0f;
-                pk[1] = (unsigned)P;
-                eff_cnt = 1;
-            }
-            const int kmax = __reduce_max_sync(0xffffffffu, eff_cnt);
-            partial = partial || !whole_bin;
-
-            GatherCtx ctx;
-            ctx.G = prm.G; ctx.S = prm.S; ctx.ell = ell + tid; ctx.P = P;
-            ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
-            ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote;
-            ctx.my_cnt = my_cnt; ctx.kmax = kmax;
-            // the list length is warp-uniform after the max-reduce: pick the unroll that fits
-#if SLR_GATHER_EXPERIMENT == 4      // timing experiment only: list building alone
-            if (kmax == 12345) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
-            if (wk[0] + wk[1] + wk[5] == 1.2345e30f) out[0] = wk[3];
-#else
-            switch ((kmax + 1) >> 1) {
-                case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
-                case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
-                        else gather_dispatch<NT, 2>(ctx, pk, wk, nrm, tl);
-                        break;
-                case 2: gather_dispatch<NT, 4>(ctx, pk, wk, nrm, tl); break;
-                case 3: gather_dispatch<NT, 6>(ctx, pk, wk, nrm, tl); break;
-                case 4: gather_dispatch<NT, 8>(ctx, pk, wk, nrm, tl); break;
-                case 5: gather_dispatch<NT, 10>(ctx, pk, wk, nrm, tl); break;
-#if SLR_GATHER_DEPTH == 16
-                case 6: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
-                case 7: gather_dispatch<NT, 14>(ctx, pk, wk, nrm, tl); break;
-                default: gather_dispatch<NT, 16>(ctx, pk, wk, nrm, tl); break;
-#else
-                default: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
-#endif
-            }
-#endif
-            wrote = true;
-            first_pass = false;
-            cb += len;
-            // lists that continued in the table, or another pass over this bin: nobody may
-            // touch the table or the counters before all warps are done with them
-            if (tail || !last_pass) __syncthreads();
-        }
-
-        if (inframe) {
-            if (partial) {
-                const float inv = 1.0f / fmaxf(nrm, prm.eps);
-                for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] *= inv;
-            }
-            if (prm.aux) {
-                float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
-                #pragma unroll
-                for (int j = 0; j < NT; ++j) a[(int64_t)j * P] = tl[j];
-                a[(int64_t)NT * P] = nrm;
-            }
-            if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
-        }
-        cur = nxt;
+    if (!inframe) return;
+    const float den = fmaxf(nrm, prm.eps);
+    if (!wrote) {
+        // empty bin: the whole tile is a hole
+        for (int c = 0; c < prm.C; ++c) __stcs(out + (int64_t)c * P, 0.0f);
+    } else if (partial) {
+        const float inv = 1.0f / den;
+        for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] *= inv;
     }
+    if (prm.aux) {
+        float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
+        #pragma unroll
+        for (int j = 0; j < NT; ++j) a[(int64_t)j * P] = tl[j];
+        a[(int64_t)NT * P] = nrm;
+    }
+    if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
 }
 
 }  // namespace slr
@@ -834,28 +762,18 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
         prm.alphas.a[f] = a;
     }
     prm.n_frames = n_frames;
+    dim3 grid((unsigned)n_tiles * (unsigned)n_frames, 1, 1);
     cudaStream_t s = (cudaStream_t)stream_;
-    // persistent grid: as many CTAs as are resident at once (registers allow 2 per SM)
-    static int resident[3] = {0, 0, 0};     // per n_tail; opt in to > 48 KB dynamic shared memory once
-    if (resident[n_tail] == 0) {
-        int per_sm = 0;
-        if (n_tail == 0) {
-            SLR_CUDA(cudaFuncSetAttribute(gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-            SLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel<0>, TILE, kGatherSmem));
-        } else if (n_tail == 1) {
-            SLR_CUDA(cudaFuncSetAttribute(gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-            SLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel<1>, TILE, kGatherSmem));
-        } else {
-            SLR_CUDA(cudaFuncSetAttribute(gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-            SLR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel<2>, TILE, kGatherSmem));
-        }
-        resident[n_tail] = per_sm > 0 ? per_sm : 1;
+    static bool attr_set = false;      // opt in to > 48 KB dynamic shared memory once
+    if (!attr_set) {
+        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        attr_set = true;
     }
-    const int n_items = n_tiles * n_frames;
-    const int grid = std::min(n_items, resident[n_tail] * slr_host::sm_count());
-    if (n_tail == 0) gather_kernel<0><<<grid, TILE, kGatherSmem, s>>>(prm, n_items);
-    else if (n_tail == 1) gather_kernel<1><<<grid, TILE, kGatherSmem, s>>>(prm, n_items);
-    else gather_kernel<2><<<grid, TILE, kGatherSmem, s>>>(prm, n_items);
+    if (n_tail == 0) gather_kernel<0><<<grid, TILE, kGatherSmem, s>>>(prm);
+    else if (n_tail == 1) gather_kernel<1><<<grid, TILE, kGatherSmem, s>>>(prm);
+    else gather_kernel<2><<<grid, TILE, kGatherSmem, s>>>(prm);
     return SLR_LAUNCH_STATUS();
 }
 
