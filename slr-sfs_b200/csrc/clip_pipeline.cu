@@ -328,6 +328,9 @@ struct GatherParams {
     const float4* ent;         // [frames][cap]  (pixel | dir << 31, landing x, landing y, -)
     const float* motion;       // [2][P]: a destination pixel with zero motion contributes to itself
     const unsigned* offsets;   // [frames][n_tiles + 1]
+    uint2* lists;              // [frames][n_rows][kSmemDepth][32]: per 32-pixel row, slot-major (source, weight)
+    unsigned* row_k;           // [frames][n_rows]: slots in use in that row (warp-uniform list length)
+    unsigned* tile_flag;       // [frames][n_tiles]: 1 = lists overflowed, tile is done by the multi-pass kernel
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -340,7 +343,8 @@ struct GatherParams {
 struct GatherCtx {
     const char* G;       // group plane 0
     const float* S;      // scalar plane 0
-    const uint2* ell;    // this thread's column of the shared list table (stride TILE)
+    const uint2* ell;    // this thread's column of the list table (slot stride ell_stride), for slots >= kDepth
+    int ell_stride;
     float* out;          // this thread's pixel in plane 0 of the frame
     int64_t P;
     int groups, C, my_cnt, kmax;
@@ -385,10 +389,9 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
     }
     if (K == kDepth) {
         for (int k = kDepth; k < c.kmax; ++k) {
-            const uint2 e = c.ell[k * TILE];
-            const bool on = k < c.my_cnt;
-            const unsigned p = on ? e.x : (unsigned)c.P;
-            const float w = on ? __uint_as_float(e.y) : 0.0f;
+            const uint2 e = c.ell[k * c.ell_stride];         // unused slots hold (zero pixel, 0)
+            const unsigned p = e.x;
+            const float w = __uint_as_float(e.y);
             #pragma unroll
             for (int t = 0; t < NT; ++t) tl[t] = fmaf(__ldg(c.S + (int64_t)t * sstride + p), w, tl[t]);
             nrm = fmaf(__ldg(c.S + (int64_t)NT * sstride + p), w, nrm);
@@ -435,10 +438,9 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
             float4 acc = accs[gi];
             if (K == kDepth) {
                 for (int k = kDepth; k < c.kmax; ++k) {       // rare: lists longer than the register file holds
-                    const uint2 e = c.ell[k * TILE];
-                    const bool on = k < c.my_cnt;
-                    const float4 t = __ldg(px16(Gg + gi * gstride, on ? e.x : (unsigned)c.P));
-                    const float w = on ? __uint_as_float(e.y) : 0.0f;
+                    const uint2 e = c.ell[k * c.ell_stride];
+                    const float4 t = __ldg(px16(Gg + gi * gstride, e.x));
+                    const float w = __uint_as_float(e.y);
                     acc.x = fmaf(t.x, w, acc.x);
                     acc.y = fmaf(t.y, w, acc.y);
                     acc.z = fmaf(t.z, w, acc.z);
@@ -487,7 +489,7 @@ __device__ __forceinline__ void gather_dispatch(const GatherCtx& c, const unsign
 
 template <int NT>
 __global__ void __launch_bounds__(TILE, SLR_GATHER_MINBLOCKS)
-gather_kernel(const GatherParams prm)
+multipass_gather_kernel(const GatherParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* ell = reinterpret_cast<uint2*>(smem_raw);                 // ell[k * TILE + d], k < kSmemDepth
@@ -495,11 +497,9 @@ gather_kernel(const GatherParams prm)
                                                                             // preferred slots, bits 8.. = overflow count
 
     const int tid = threadIdx.x;
-    // Frame index fastest: the CTAs resident at any moment work on the SAME destination
-    // tiles of all frames of the batch.  Their source regions differ only by the
-    // frame-to-frame displacement, so a source line is fetched from HBM once per batch and
-    // the other frames hit it in L2 (one frame's features alone, 204 MB, exceed the L2).
     const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    // only tiles whose lists overflowed in expand_kernel (sinks, strong compression) are done here
+    if (__ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile) == 0u) return;
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     // thread -> destination pixel: a warp covers a PW x PH patch (32x1, 16x2 or 8x4) so that the
     // sources two vertically adjacent destination pixels share are touched by the same warp
@@ -590,8 +590,10 @@ gather_kernel(const GatherParams prm)
         const int kmax = __reduce_max_sync(0xffffffffu, eff_cnt);
         partial = partial || !whole_bin;
 
+        // slots past this thread's own list that the warp's tail loop will read
+        for (int k = max(my_cnt, kDepth); k < kSmemDepth; ++k) ell[k * TILE + tid] = make_uint2((unsigned)P, 0u);
         GatherCtx ctx;
-        ctx.G = prm.G; ctx.S = prm.S; ctx.ell = ell + tid; ctx.P = P;
+        ctx.G = prm.G; ctx.S = prm.S; ctx.ell = ell + tid; ctx.ell_stride = TILE; ctx.P = P;
         ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
         ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote;
         ctx.my_cnt = my_cnt; ctx.kmax = kmax;
@@ -642,6 +644,156 @@ gather_kernel(const GatherParams prm)
     if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
 }
 
+// ---------------------------------------------------------------------------
+// expand_kernel: one CTA per (destination tile, frame).  Expands the tile's bin into
+// per-destination-pixel (source, weight) lists in shared memory (canonical slots, see
+// multipass_gather_kernel) and writes them out per 32-pixel row, slot-major, so that the
+// gather kernel needs no shared memory and no barriers.  Small register footprint: several
+// CTAs per SM hide the latency of this pointer-chasing part.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE, 3)
+expand_kernel(const GatherParams prm)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* ell = reinterpret_cast<uint2*>(smem_raw);
+    unsigned* cnt = reinterpret_cast<unsigned*>(ell + kSmemDepth * TILE);
+
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+    const int X = tx * TW + tile_lx(tid), Y = ty * TH + tile_ly(tid);
+    const bool inframe = X < prm.W && Y < prm.H;
+    const int64_t P = prm.P;
+    const int64_t pix = (int64_t)Y * prm.W + X;
+    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+    const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+    const unsigned beg = __ldg(off + tile), end = __ldg(off + tile + 1);
+    const float4* ent = prm.ent + (int64_t)f * prm.cap;
+    // a destination pixel with exactly zero motion receives itself with weight alpha + (1 - alpha)
+    // (its forward and backward splat both land exactly on it); it was not binned
+    const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
+
+    cnt[tid] = self_static ? 1u : 0u;
+    if (self_static) ell[tid] = make_uint2((unsigned)pix, __float_as_uint(a_f + a_b));
+    __syncthreads();
+    for (unsigned e = beg + tid; e < end; e += TILE) {
+        const float4 en = __ldcs(ent + e);
+        const unsigned pd = __float_as_uint(en.x);
+        const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+        const unsigned dir = pd >> 31;
+        const float a = dir ? a_b : a_f;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+            const float wa = fp.w[k] * a;
+            if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f) {
+                const int d = tile_thread(lx, ly);
+                const unsigned pref = 2u * k + dir;
+                const unsigned old = atomicOr(&cnt[d], 1u << pref);
+                int slot = pref;
+                if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
+                if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
+            }
+        }
+    }
+    __syncthreads();
+    const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
+    if (tid == 0) prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
+    if (over) return;
+
+    const unsigned occ = cnt[tid] & 0xffu;
+    const int n_ovf = (int)(cnt[tid] >> 8);
+    const int my_cnt = n_ovf > 0 ? 8 + n_ovf : 32 - __clz(occ);
+    uint2 e0 = ell[tid], e1 = ell[TILE + tid];
+    // same source in slots 0 and 1 (a static pixel's forward and backward self-splat): one slot
+    const bool merged = my_cnt == 2 && occ == 3u && e0.x == e1.x;
+    if (merged) e0.y = __float_as_uint(__uint_as_float(e0.y) + __uint_as_float(e1.y));
+    const int kmax = __reduce_max_sync(0xffffffffu, merged ? 1 : my_cnt);
+    const int n_rows = prm.n_tiles * TH;
+    const int64_t row = (int64_t)f * n_rows + (int64_t)tile * TH + (tid >> 5);
+    if ((tid & 31) == 0) prm.row_k[row] = (unsigned)kmax;
+    uint2* dst = prm.lists + row * (kSmemDepth * 32) + (tid & 31);
+    const uint2 none = make_uint2((unsigned)P, 0u);       // the zero pixel, weight 0
+    for (int k = 0; k < kmax; ++k) {
+        uint2 e = k == 0 ? e0 : ell[k * TILE + tid];
+        bool used = k < 8 ? (occ >> k & 1u) : (k - 8 < n_ovf);
+        if (merged && k == 1) used = false;
+        __stcg(dst + k * 32, used ? e : none);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// rowgather_kernel: the hot kernel.  One warp per 32-pixel destination row (the 8 warps of a
+// CTA are the 8 rows of one tile, so vertically shared sources stay in this SM's L1).  No
+// shared memory, no barriers: every warp is an independent stream of
+//   read its list -> [K*GI LDG.128 -> 4*K*GI FMA -> 4*GI STG] per iteration,
+// so the loads of some warps overlap the FMAs and stores of others.
+// CTA order is frame-fastest: the CTAs resident at any moment work on the SAME destination
+// tiles of all frames of the batch; their source regions differ only by the frame-to-frame
+// displacement, so a source line is fetched from HBM once per batch and the other frames hit
+// it in L2 (one frame's features alone, 204 MB, exceed the 126 MB L2).
+// ---------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(TILE, SLR_GATHER_MINBLOCKS)
+rowgather_kernel(const GatherParams prm)
+{
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    if (__ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile) != 0u) return;    // multi-pass kernel's tile
+    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+    const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
+    const bool inframe = X < prm.W && Y < prm.H;
+    const int64_t P = prm.P;
+    const int64_t pix = (int64_t)Y * prm.W + X;
+    const int n_rows = prm.n_tiles * TH;
+    const int64_t row = (int64_t)f * n_rows + (int64_t)tile * TH + (tid >> 5);
+    const int kmax = (int)__ldg(prm.row_k + row);
+    const uint2* src = prm.lists + row * (kSmemDepth * 32) + (tid & 31);
+
+    unsigned pk[kDepth];
+    float wk[kDepth];
+    #pragma unroll
+    for (int k = 0; k < kDepth; ++k) {
+        uint2 e = make_uint2((unsigned)P, 0u);
+        if (k < kmax) e = __ldcg(src + k * 32);
+        pk[k] = e.x;
+        wk[k] = __uint_as_float(e.y);
+    }
+    float nrm = 0.0f;
+    float tl[NT > 0 ? NT : 1] = {0.0f};
+    GatherCtx ctx;
+    ctx.G = prm.G; ctx.S = prm.S; ctx.ell = src; ctx.ell_stride = 32; ctx.P = P;
+    ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
+    ctx.out = prm.out + (int64_t)f * prm.C * P + pix;
+    ctx.inframe = inframe; ctx.whole_bin = true; ctx.wrote = false;
+    ctx.my_cnt = kmax; ctx.kmax = kmax;
+    switch ((kmax + 1) >> 1) {
+        case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
+        case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
+                else gather_dispatch<NT, 2>(ctx, pk, wk, nrm, tl);
+                break;
+        case 2: gather_dispatch<NT, 4>(ctx, pk, wk, nrm, tl); break;
+        case 3: gather_dispatch<NT, 6>(ctx, pk, wk, nrm, tl); break;
+        case 4: gather_dispatch<NT, 8>(ctx, pk, wk, nrm, tl); break;
+        case 5: gather_dispatch<NT, 10>(ctx, pk, wk, nrm, tl); break;
+#if SLR_GATHER_DEPTH == 16
+        case 6: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
+        case 7: gather_dispatch<NT, 14>(ctx, pk, wk, nrm, tl); break;
+        default: gather_dispatch<NT, 16>(ctx, pk, wk, nrm, tl); break;
+#else
+        default: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
+#endif
+    }
+    if (!inframe) return;
+    if (prm.aux) {
+        float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
+        #pragma unroll
+        for (int j = 0; j < NT; ++j) a[(int64_t)j * P] = tl[j];
+        a[(int64_t)NT * P] = nrm;
+    }
+    if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
+}
+
 }  // namespace slr
 
 // ===========================================================================
@@ -656,6 +808,9 @@ struct Workspace {
     unsigned* counts;     // [n][n_tiles]      (counts, then cursors)
     unsigned* offsets;    // [n][n_tiles + 1]
     float4* ent;          // [n][cap]
+    uint2* lists;         // [n][n_rows][kSmemDepth][32]
+    unsigned* row_k;      // [n][n_rows]
+    unsigned* tile_flag;  // [n][n_tiles]
     size_t bytes;
 };
 
@@ -673,6 +828,9 @@ Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
     w.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
     w.ent = (float4*)(p + o);        o += align_up(sizeof(float4) * cap * n);
+    w.lists = (uint2*)(p + o);       o += align_up(sizeof(uint2) * 32 * kSmemDepth * (size_t)(tiles * TH) * n);
+    w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * TH * n);
+    w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.bytes = o;
     return w;
 }
@@ -751,6 +909,7 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     prm.G = (const char*)scene;
     prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
+    prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
@@ -766,14 +925,23 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     cudaStream_t s = (cudaStream_t)stream_;
     static bool attr_set = false;      // opt in to > 48 KB dynamic shared memory once
     if (!attr_set) {
-        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-        SLR_CUDA(cudaFuncSetAttribute(gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(multipass_gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(multipass_gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
+        SLR_CUDA(cudaFuncSetAttribute(multipass_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
         attr_set = true;
     }
-    if (n_tail == 0) gather_kernel<0><<<grid, TILE, kGatherSmem, s>>>(prm);
-    else if (n_tail == 1) gather_kernel<1><<<grid, TILE, kGatherSmem, s>>>(prm);
-    else gather_kernel<2><<<grid, TILE, kGatherSmem, s>>>(prm);
+    expand_kernel<<<grid, TILE, kGatherSmem, s>>>(prm);
+    if (n_tail == 0) {
+        rowgather_kernel<0><<<grid, TILE, 0, s>>>(prm);
+        multipass_gather_kernel<0><<<grid, TILE, kGatherSmem, s>>>(prm);
+    } else if (n_tail == 1) {
+        rowgather_kernel<1><<<grid, TILE, 0, s>>>(prm);
+        multipass_gather_kernel<1><<<grid, TILE, kGatherSmem, s>>>(prm);
+    } else {
+        rowgather_kernel<2><<<grid, TILE, 0, s>>>(prm);
+        multipass_gather_kernel<2><<<grid, TILE, kGatherSmem, s>>>(prm);
+    }
     return SLR_LAUNCH_STATUS();
 }
 
