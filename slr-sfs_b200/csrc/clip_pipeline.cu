@@ -331,6 +331,8 @@ struct GatherParams {
     uint2* lists;              // [frames][n_rows][kSmemDepth][32]: per 32-pixel row, slot-major (source, weight)
     unsigned* row_k;           // [frames][n_rows]: slots in use in that row (warp-uniform list length)
     unsigned* tile_flag;       // [frames][n_tiles]: 1 = lists overflowed, tile is done by the multi-pass kernel
+    unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
+    unsigned* flag_count;      // [1], zeroed by slr_clip_plan
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -497,9 +499,12 @@ multipass_gather_kernel(const GatherParams prm)
                                                                             // preferred slots, bits 8.. = overflow count
 
     const int tid = threadIdx.x;
-    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
-    // only tiles whose lists overflowed in expand_kernel (sinks, strong compression) are done here
-    if (__ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile) == 0u) return;
+    // only tiles whose lists overflowed in expand_kernel (sinks, strong compression) are done
+    // here: expand_kernel appended them to flag_list; a small fixed grid walks that list
+    const unsigned n_flagged = *prm.flag_count;
+    for (unsigned item_i = blockIdx.x; item_i < n_flagged; item_i += gridDim.x) {
+    const unsigned item = prm.flag_list[item_i];
+    const int f = (int)(item % (unsigned)prm.n_frames), tile = (int)(item / (unsigned)prm.n_frames);
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     // thread -> destination pixel: a warp covers a PW x PH patch (32x1, 16x2 or 8x4) so that the
     // sources two vertically adjacent destination pixels share are touched by the same warp
@@ -626,22 +631,22 @@ multipass_gather_kernel(const GatherParams prm)
         __syncthreads();
     }
 
-    if (!inframe) return;
-    const float den = fmaxf(nrm, prm.eps);
-    if (!wrote) {
-        // empty bin: the whole tile is a hole
-        for (int c = 0; c < prm.C; ++c) __stcs(out + (int64_t)c * P, 0.0f);
-    } else if (partial) {
-        const float inv = 1.0f / den;
-        for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] *= inv;
+    if (inframe) {
+        const float den = fmaxf(nrm, prm.eps);
+        if (partial) {
+            const float inv = 1.0f / den;
+            for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] *= inv;
+        }
+        if (prm.aux) {
+            float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
+            #pragma unroll
+            for (int j = 0; j < NT; ++j) a[(int64_t)j * P] = tl[j];
+            a[(int64_t)NT * P] = nrm;
+        }
+        if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
     }
-    if (prm.aux) {
-        float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
-        #pragma unroll
-        for (int j = 0; j < NT; ++j) a[(int64_t)j * P] = tl[j];
-        a[(int64_t)NT * P] = nrm;
-    }
-    if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
+    __syncthreads();
+    }   // flagged items
 }
 
 // ---------------------------------------------------------------------------
@@ -698,7 +703,10 @@ expand_kernel(const GatherParams prm)
     }
     __syncthreads();
     const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
-    if (tid == 0) prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
+    if (tid == 0) {
+        prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
+        if (over) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
+    }
     if (over) return;
 
     const unsigned occ = cnt[tid] & 0xffu;
@@ -811,6 +819,8 @@ struct Workspace {
     uint2* lists;         // [n][n_rows][kSmemDepth][32]
     unsigned* row_k;      // [n][n_rows]
     unsigned* tile_flag;  // [n][n_tiles]
+    unsigned* flag_list;  // [n * n_tiles]
+    unsigned* flag_count; // [1]
     size_t bytes;
 };
 
@@ -831,6 +841,8 @@ Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.lists = (uint2*)(p + o);       o += align_up(sizeof(uint2) * 32 * kSmemDepth * (size_t)(tiles * TH) * n);
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * TH * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
+    w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
+    w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.bytes = o;
     return w;
 }
@@ -880,6 +892,7 @@ extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int star
     cudaStream_t s = (cudaStream_t)stream_;
 
     SLR_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
+    SLR_CUDA(cudaMemsetAsync(ws.flag_count, 0, sizeof(unsigned), s));
     const unsigned pblocks = (unsigned)((P + 255) / 256);
     euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
                                                ws.land, ws.counts, tiles_x, n_tiles);
@@ -910,6 +923,7 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
+    prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
@@ -932,15 +946,16 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
         attr_set = true;
     }
     expand_kernel<<<grid, TILE, kGatherSmem, s>>>(prm);
+    const unsigned mp_grid = std::min<unsigned>(grid.x, 2u * (unsigned)slr_host::sm_count());
     if (n_tail == 0) {
         rowgather_kernel<0><<<grid, TILE, 0, s>>>(prm);
-        multipass_gather_kernel<0><<<grid, TILE, kGatherSmem, s>>>(prm);
+        multipass_gather_kernel<0><<<mp_grid, TILE, kGatherSmem, s>>>(prm);
     } else if (n_tail == 1) {
         rowgather_kernel<1><<<grid, TILE, 0, s>>>(prm);
-        multipass_gather_kernel<1><<<grid, TILE, kGatherSmem, s>>>(prm);
+        multipass_gather_kernel<1><<<mp_grid, TILE, kGatherSmem, s>>>(prm);
     } else {
         rowgather_kernel<2><<<grid, TILE, 0, s>>>(prm);
-        multipass_gather_kernel<2><<<grid, TILE, kGatherSmem, s>>>(prm);
+        multipass_gather_kernel<2><<<mp_grid, TILE, kGatherSmem, s>>>(prm);
     }
     return SLR_LAUNCH_STATUS();
 }
