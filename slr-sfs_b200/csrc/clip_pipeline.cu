@@ -50,6 +50,7 @@ constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread ho
 constexpr int kSmemDepth = SLR_GATHER_SMEM_DEPTH;   // pairs per destination pixel the shared list table holds
 constexpr int kChunk = 8192;           // bin entries expanded per pass
 constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
+constexpr int kSpillCap = 1024;        // per tile: pairs beyond kSmemDepth per pixel (convergence points)
 constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the parameters)
 constexpr unsigned kDirBit = 0x80000000u;
 constexpr float kStaticLand = -1.0e30f;  // landing marker of pixels that are not binned
@@ -331,6 +332,8 @@ struct GatherParams {
     uint2* lists;              // [frames][n_rows][kSmemDepth][32]: per 32-pixel row, slot-major (source, weight)
     unsigned* row_k;           // [frames][n_rows]: slots in use in that row (warp-uniform list length)
     unsigned* tile_flag;       // [frames][n_tiles]: 1 = lists overflowed, tile is done by the multi-pass kernel
+    uint4* spill;              // [frames][n_tiles][kSpillCap]: (dest thread, source, weight, -) beyond the table depth
+    unsigned* spill_n;         // [frames][n_tiles]
     unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
     unsigned* flag_count;      // [1], zeroed by slr_clip_plan
     float* out;                // [frames][C][P]
@@ -347,6 +350,8 @@ struct GatherCtx {
     const float* S;      // scalar plane 0
     const uint2* ell;    // this thread's column of the list table (slot stride ell_stride), for slots >= kDepth
     int ell_stride;
+    const uint4* spill;  // the tile's spill list: pairs of pixels whose list is deeper than the table
+    int n_spill, tid;
     float* out;          // this thread's pixel in plane 0 of the frame
     int64_t P;
     int groups, C, my_cnt, kmax;
@@ -369,7 +374,7 @@ __device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
 //        (some lane always misses L1), and the 16 resident warps per SM are too few to hide
 //        it, so every iteration puts K * GI <= 16 independent LDG.128 in flight.
 //   FAST the whole bin fits one pass and C % 4 == 0: plain normalised streaming stores.
-template <int NT, int K, int GI, bool FAST>
+template <int NT, int K, int GI, bool FAST, bool SPILL = false>
 __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned (&pk)[kDepth],
                                              const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
 {
@@ -397,6 +402,15 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
             #pragma unroll
             for (int t = 0; t < NT; ++t) tl[t] = fmaf(__ldg(c.S + (int64_t)t * sstride + p), w, tl[t]);
             nrm = fmaf(__ldg(c.S + (int64_t)NT * sstride + p), w, nrm);
+        }
+    }
+    for (int i = 0; SPILL && i < c.n_spill; ++i) {          // rare: convergence points
+        const uint4 e = __ldg(c.spill + i);
+        if ((int)e.x == c.tid) {
+            const float w = __uint_as_float(e.z);
+            #pragma unroll
+            for (int t = 0; t < NT; ++t) tl[t] = fmaf(__ldg(c.S + (int64_t)t * sstride + e.y), w, tl[t]);
+            nrm = fmaf(__ldg(c.S + (int64_t)NT * sstride + e.y), w, nrm);
         }
     }
     const float inv = c.whole_bin ? 1.0f / fmaxf(nrm, c.eps) : 1.0f;
@@ -443,6 +457,17 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
                     const uint2 e = c.ell[k * c.ell_stride];
                     const float4 t = __ldg(px16(Gg + gi * gstride, e.x));
                     const float w = __uint_as_float(e.y);
+                    acc.x = fmaf(t.x, w, acc.x);
+                    acc.y = fmaf(t.y, w, acc.y);
+                    acc.z = fmaf(t.z, w, acc.z);
+                    acc.w = fmaf(t.w, w, acc.w);
+                }
+            }
+            for (int i = 0; SPILL && i < c.n_spill; ++i) {
+                const uint4 e = __ldg(c.spill + i);
+                if ((int)e.x == c.tid) {
+                    const float4 t = __ldg(px16(Gg + gi * gstride, e.y));
+                    const float w = __uint_as_float(e.z);
                     acc.x = fmaf(t.x, w, acc.x);
                     acc.y = fmaf(t.y, w, acc.y);
                     acc.z = fmaf(t.z, w, acc.z);
@@ -599,6 +624,7 @@ multipass_gather_kernel(const GatherParams prm)
         for (int k = max(my_cnt, kDepth); k < kSmemDepth; ++k) ell[k * TILE + tid] = make_uint2((unsigned)P, 0u);
         GatherCtx ctx;
         ctx.G = prm.G; ctx.S = prm.S; ctx.ell = ell + tid; ctx.ell_stride = TILE; ctx.P = P;
+        ctx.spill = nullptr; ctx.n_spill = 0; ctx.tid = tid;
         ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
         ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote;
         ctx.my_cnt = my_cnt; ctx.kmax = kmax;
@@ -662,6 +688,7 @@ expand_kernel(const GatherParams prm)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* ell = reinterpret_cast<uint2*>(smem_raw);
     unsigned* cnt = reinterpret_cast<unsigned*>(ell + kSmemDepth * TILE);
+    __shared__ unsigned n_spill_s;
 
     const int tid = threadIdx.x;
     const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
@@ -673,6 +700,8 @@ expand_kernel(const GatherParams prm)
     const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
     const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
     const unsigned beg = __ldg(off + tile), end = __ldg(off + tile + 1);
+    uint4* spill = prm.spill + ((int64_t)f * prm.n_tiles + tile) * kSpillCap;
+    if (tid == 0) n_spill_s = 0u;
     const float4* ent = prm.ent + (int64_t)f * prm.cap;
     // a destination pixel with exactly zero motion receives itself with weight alpha + (1 - alpha)
     // (its forward and backward splat both land exactly on it); it was not binned
@@ -697,20 +726,27 @@ expand_kernel(const GatherParams prm)
                 const unsigned old = atomicOr(&cnt[d], 1u << pref);
                 int slot = pref;
                 if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
-                if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
+                if (slot < kSmemDepth) {
+                    ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
+                } else {
+                    // deeper than the table (a convergence point): goes to the tile's spill list
+                    const unsigned i = atomicAdd(&n_spill_s, 1u);
+                    if (i < (unsigned)kSpillCap) spill[i] = make_uint4((unsigned)d, pd & ~kDirBit, __float_as_uint(wa), 0u);
+                }
             }
         }
     }
     __syncthreads();
-    const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
+    const int over = n_spill_s > (unsigned)kSpillCap;       // a true sink: the multi-pass kernel takes the tile
     if (tid == 0) {
         prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
+        prm.spill_n[(int64_t)f * prm.n_tiles + tile] = over ? 0u : n_spill_s;
         if (over) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
     }
     if (over) return;
 
     const unsigned occ = cnt[tid] & 0xffu;
-    const int n_ovf = (int)(cnt[tid] >> 8);
+    const int n_ovf = min((int)(cnt[tid] >> 8), kSmemDepth - 8);      // the rest is in the spill list
     const int my_cnt = n_ovf > 0 ? 8 + n_ovf : 32 - __clz(occ);
     uint2 e0 = ell[tid], e1 = ell[TILE + tid];
     // same source in slots 0 and 1 (a static pixel's forward and backward self-splat): one slot
@@ -771,10 +807,18 @@ rowgather_kernel(const GatherParams prm)
     float tl[NT > 0 ? NT : 1] = {0.0f};
     GatherCtx ctx;
     ctx.G = prm.G; ctx.S = prm.S; ctx.ell = src; ctx.ell_stride = 32; ctx.P = P;
+    ctx.n_spill = (int)__ldg(prm.spill_n + (int64_t)f * prm.n_tiles + tile);
+    ctx.spill = prm.spill + ((int64_t)f * prm.n_tiles + tile) * kSpillCap;
+    ctx.tid = tid;
     ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
     ctx.out = prm.out + (int64_t)f * prm.C * P + pix;
     ctx.inframe = inframe; ctx.whole_bin = true; ctx.wrote = false;
     ctx.my_cnt = kmax; ctx.kmax = kmax;
+    if (ctx.n_spill > 0) {
+        // a tile with convergence points: one generic variant that also walks the spill list
+        if ((prm.C & 3) == 0) gather_lists<NT, kDepth, 1, true, true>(ctx, pk, wk, nrm, tl);
+        else gather_lists<NT, kDepth, 1, false, true>(ctx, pk, wk, nrm, tl);
+    } else
     switch ((kmax + 1) >> 1) {
         case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
         case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
@@ -819,6 +863,8 @@ struct Workspace {
     uint2* lists;         // [n][n_rows][kSmemDepth][32]
     unsigned* row_k;      // [n][n_rows]
     unsigned* tile_flag;  // [n][n_tiles]
+    uint4* spill;         // [n][n_tiles][kSpillCap]
+    unsigned* spill_n;    // [n][n_tiles]
     unsigned* flag_list;  // [n * n_tiles]
     unsigned* flag_count; // [1]
     size_t bytes;
@@ -841,6 +887,8 @@ Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.lists = (uint2*)(p + o);       o += align_up(sizeof(uint2) * 32 * kSmemDepth * (size_t)(tiles * TH) * n);
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * TH * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
+    w.spill = (uint4*)(p + o);       o += align_up(sizeof(uint4) * kSpillCap * tiles * n);
+    w.spill_n = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.bytes = o;
@@ -924,6 +972,7 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count;
+    prm.spill = ws.spill; prm.spill_n = ws.spill_n;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
