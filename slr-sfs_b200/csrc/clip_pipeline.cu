@@ -50,7 +50,6 @@ constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread ho
 constexpr int kSmemDepth = SLR_GATHER_SMEM_DEPTH;   // pairs per destination pixel the shared list table holds
 constexpr int kChunk = 8192;           // bin entries expanded per pass
 constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
-constexpr int kSpillCap = 1024;        // per tile: pairs beyond kSmemDepth per pixel (convergence points)
 constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the parameters)
 constexpr unsigned kDirBit = 0x80000000u;
 constexpr float kStaticLand = -1.0e30f;  // landing marker of pixels that are not binned
@@ -332,8 +331,6 @@ struct GatherParams {
     uint2* lists;              // [frames][n_rows][kSmemDepth][32]: per 32-pixel row, slot-major (source, weight)
     unsigned* row_k;           // [frames][n_rows]: slots in use in that row (warp-uniform list length)
     unsigned* tile_flag;       // [frames][n_tiles]: 1 = lists overflowed, tile is done by the multi-pass kernel
-    uint4* spill;              // [frames][n_tiles][kSpillCap]: (dest thread, source, weight, -) beyond the table depth
-    unsigned* spill_n;         // [frames][n_tiles]
     unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
     unsigned* flag_count;      // [1], zeroed by slr_clip_plan
     float* out;                // [frames][C][P]
@@ -350,8 +347,6 @@ struct GatherCtx {
     const float* S;      // scalar plane 0
     const uint2* ell;    // this thread's column of the list table (slot stride ell_stride), for slots >= kDepth
     int ell_stride;
-    const uint4* spill;  // the tile's spill list: pairs of pixels whose list is deeper than the table
-    int n_spill, tid;
     float* out;          // this thread's pixel in plane 0 of the frame
     int64_t P;
     int groups, C, my_cnt, kmax;
@@ -374,7 +369,7 @@ __device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
 //        (some lane always misses L1), and the 16 resident warps per SM are too few to hide
 //        it, so every iteration puts K * GI <= 16 independent LDG.128 in flight.
 //   FAST the whole bin fits one pass and C % 4 == 0: plain normalised streaming stores.
-template <int NT, int K, int GI, bool FAST, bool SPILL = false>
+template <int NT, int K, int GI, bool FAST>
 __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned (&pk)[kDepth],
                                              const float (&wk)[kDepth], float& nrm, float (&tl)[NT > 0 ? NT : 1])
 {
@@ -402,15 +397,6 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
             #pragma unroll
             for (int t = 0; t < NT; ++t) tl[t] = fmaf(__ldg(c.S + (int64_t)t * sstride + p), w, tl[t]);
             nrm = fmaf(__ldg(c.S + (int64_t)NT * sstride + p), w, nrm);
-        }
-    }
-    for (int i = 0; SPILL && i < c.n_spill; ++i) {          // rare: convergence points
-        const uint4 e = __ldg(c.spill + i);
-        if ((int)e.x == c.tid) {
-            const float w = __uint_as_float(e.z);
-            #pragma unroll
-            for (int t = 0; t < NT; ++t) tl[t] = fmaf(__ldg(c.S + (int64_t)t * sstride + e.y), w, tl[t]);
-            nrm = fmaf(__ldg(c.S + (int64_t)NT * sstride + e.y), w, nrm);
         }
     }
     const float inv = c.whole_bin ? 1.0f / fmaxf(nrm, c.eps) : 1.0f;
@@ -463,17 +449,6 @@ __device__ __forceinline__ void gather_lists(const GatherCtx& c, const unsigned 
                     acc.w = fmaf(t.w, w, acc.w);
                 }
             }
-            for (int i = 0; SPILL && i < c.n_spill; ++i) {
-                const uint4 e = __ldg(c.spill + i);
-                if ((int)e.x == c.tid) {
-                    const float4 t = __ldg(px16(Gg + gi * gstride, e.y));
-                    const float w = __uint_as_float(e.z);
-                    acc.x = fmaf(t.x, w, acc.x);
-                    acc.y = fmaf(t.y, w, acc.y);
-                    acc.z = fmaf(t.z, w, acc.z);
-                    acc.w = fmaf(t.w, w, acc.w);
-                }
-            }
             if (c.inframe) {
                 float* og = o + 4 * gi * ostride;
 #if SLR_GATHER_EXPERIMENT == 1 || SLR_GATHER_EXPERIMENT == 3     // timing experiment only: no output stores
@@ -514,165 +489,101 @@ __device__ __forceinline__ void gather_dispatch(const GatherCtx& c, const unsign
     }
 }
 
+// ---------------------------------------------------------------------------
+// heavy_tile_kernel: destination tiles in which some pixel receives more pairs than the list
+// table holds (convergence zones of the flow: the synthetic 60-step fields pile up to ~100
+// sources on single pixels and 10x the average number of pairs on single tiles).  Work is
+// assigned per PAIR instead of per destination pixel: every thread walks bin entries and adds
+// into a per-tile accumulator in shared memory with shared-memory atomics, one channel group
+// at a time, so the cost is linear in the number of pairs whatever their distribution.  A small
+// fixed grid walks the compacted list of flagged tiles that expand_kernel produced.
+// ---------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(TILE, SLR_GATHER_MINBLOCKS)
-multipass_gather_kernel(const GatherParams prm)
+__global__ void __launch_bounds__(TILE)
+heavy_tile_kernel(const GatherParams prm)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint2* ell = reinterpret_cast<uint2*>(smem_raw);                 // ell[k * TILE + d], k < kSmemDepth
-    unsigned* cnt = reinterpret_cast<unsigned*>(ell + kSmemDepth * TILE);   // per destination pixel: bits 0-7 = used
-                                                                            // preferred slots, bits 8.. = overflow count
+    __shared__ float acc[TILE * 4];
+    __shared__ float sn[(NT + 1) * TILE];
 
     const int tid = threadIdx.x;
-    // only tiles whose lists overflowed in expand_kernel (sinks, strong compression) are done
-    // here: expand_kernel appended them to flag_list; a small fixed grid walks that list
+    const int64_t P = prm.P;
+    const int64_t sstride = P + 1;
+    const size_t gstride = (size_t)(P + 1) * 16;
     const unsigned n_flagged = *prm.flag_count;
     for (unsigned item_i = blockIdx.x; item_i < n_flagged; item_i += gridDim.x) {
-    const unsigned item = prm.flag_list[item_i];
-    const int f = (int)(item % (unsigned)prm.n_frames), tile = (int)(item / (unsigned)prm.n_frames);
-    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
-    // thread -> destination pixel: a warp covers a PW x PH patch (32x1, 16x2 or 8x4) so that the
-    // sources two vertically adjacent destination pixels share are touched by the same warp
-    const int X = tx * TW + tile_lx(tid), Y = ty * TH + tile_ly(tid);
-    const bool inframe = X < prm.W && Y < prm.H;
-    const int64_t P = prm.P;
-    const int64_t pix = (int64_t)Y * prm.W + X;
-    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+        const unsigned item = prm.flag_list[item_i];
+        const int f = (int)(item % (unsigned)prm.n_frames), tile = (int)(item / (unsigned)prm.n_frames);
+        const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+        const int X = tx * TW + tile_lx(tid), Y = ty * TH + tile_ly(tid);
+        const bool inframe = X < prm.W && Y < prm.H;
+        const int64_t pix = (int64_t)Y * prm.W + X;
+        const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+        const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+        const unsigned beg = off[tile], end = off[tile + 1];
+        const float4* ent = prm.ent + (int64_t)f * prm.cap;
+        const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
+        const float w_self = a_f + a_b;
+        float* out = prm.out + (int64_t)f * prm.C * P + pix;
 
-    const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
-    const unsigned beg = off[tile], end = off[tile + 1];
-    const float4* ent = prm.ent + (int64_t)f * prm.cap;
-    const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
-    float* out = prm.out + (int64_t)f * prm.C * P + pix;
-
-    float nrm = 0.0f;
-    float tl[NT > 0 ? NT : 1] = {0.0f};
-    bool wrote = false;          // this thread's output planes hold partial sums already
-    bool partial = false;        // outputs were written un-normalised (multi-pass bin)
-
-    unsigned cb = beg;
-    bool first_pass = true;
-    while (first_pass || cb < end) {
-        // Expand entries [cb, cb+len) into per-destination lists.  If a destination pixel
-        // overflows the table (> kSmemDepth pairs: sinks, strong compression) retry with half
-        // the entries; one entry adds at most one pair per pixel, so this terminates.
-        unsigned len = min((unsigned)kChunk, end - cb);
-        for (;;) {
-            // a static destination pixel receives itself with weight alpha + (1 - alpha)
-            // (its forward and backward splat both land exactly on it), once per bin
-            cnt[tid] = (first_pass && self_static) ? 1u : 0u;
-            if (first_pass && self_static) ell[tid] = make_uint2((unsigned)pix, __float_as_uint(a_f + a_b));
-            __syncthreads();
-            for (unsigned e = cb + tid; e < cb + len; e += TILE) {
-                const float4 en = __ldcs(ent + e);
+        // visits every (destination thread, source pixel, weight) pair of the bin that lands in this tile
+        auto for_each_pair = [&](auto&& fn) {
+            if (self_static) fn(tid, (unsigned)pix, w_self);
+            for (unsigned e = beg + tid; e < end; e += TILE) {
+                const float4 en = __ldg(ent + e);
                 const unsigned pd = __float_as_uint(en.x);
-                const float ox = en.y, oy = en.z;
-                const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
-                const unsigned dir = pd >> 31;
-                const float a = dir ? a_b : a_f;
+                const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+                const float a = (pd >> 31) ? a_b : a_f;
                 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
                     const float wa = fp.w[k] * a;
-                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f) {
-                        // Slot = (corner, direction) when free, so that slot k of neighbouring
-                        // destination pixels holds neighbouring sources (coalesced LDG.128 per slot,
-                        // and a deterministic summation order); collisions go to overflow slots >= 8.
-                        const int d = tile_thread(lx, ly);
-                        const unsigned pref = 2u * k + dir;
-                        const unsigned old = atomicOr(&cnt[d], 1u << pref);
-                        int slot = pref;
-                        if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
-                        if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
-                    }
+                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                        fn(tile_thread(lx, ly), pd & ~kDirBit, wa);
                 }
             }
-            __syncthreads();
-            const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
-            if (!over || len == 1) break;
-            len = (len + 1) >> 1;
-        }
-        const bool whole_bin = (cb == beg) && (cb + len == end);
-        const unsigned occ = cnt[tid] & 0xffu;          // which of the 8 preferred slots are used
-        const int n_ovf = (int)(cnt[tid] >> 8);         // overflow slots 8 .. 8 + n_ovf - 1
-        const int my_cnt = n_ovf > 0 ? 8 + n_ovf : 32 - __clz(occ);     // slots [0, my_cnt) may be used
+        };
 
-        // my list -> registers (conflict-free LDS: consecutive lanes read consecutive pairs);
-        // unused slots point at the zero pixel with weight 0
-        unsigned pk[kDepth];
-        float wk[kDepth];
         #pragma unroll
-        for (int k = 0; k < kDepth; ++k) {
-            const uint2 e = ell[k * TILE + tid];
-            const bool used = k < 8 ? (occ >> k & 1u) : (k - 8 < n_ovf);
-            pk[k] = used ? e.x : (unsigned)P;
-            wk[k] = used ? __uint_as_float(e.y) : 0.0f;
-        }
-        // Static pixels: the forward and the backward source are the pixel itself (slots 0 and 1
-        // both NW with weight alpha and 1 - alpha).  Same source -> add the weights, free the slot.
-        int eff_cnt = my_cnt;
-        if (my_cnt == 2 && pk[0] == pk[1]) {
-            wk[0] += wk[1];
-            wk[1] = 0.0f;
-            pk[1] = (unsigned)P;
-            eff_cnt = 1;
-        }
-        const int kmax = __reduce_max_sync(0xffffffffu, eff_cnt);
-        partial = partial || !whole_bin;
+        for (int t = 0; t <= NT; ++t) sn[t * TILE + tid] = 0.0f;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) acc[tid * 4 + j] = 0.0f;
+        __syncthreads();
+        for_each_pair([&](int d, unsigned p, float w) {
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) atomicAdd(&sn[t * TILE + d], __ldg(prm.S + (int64_t)t * sstride + p) * w);
+        });
+        __syncthreads();
+        const float nrm = sn[NT * TILE + tid];
+        const float inv = 1.0f / fmaxf(nrm, prm.eps);
 
-        // slots past this thread's own list that the warp's tail loop will read
-        for (int k = max(my_cnt, kDepth); k < kSmemDepth; ++k) ell[k * TILE + tid] = make_uint2((unsigned)P, 0u);
-        GatherCtx ctx;
-        ctx.G = prm.G; ctx.S = prm.S; ctx.ell = ell + tid; ctx.ell_stride = TILE; ctx.P = P;
-        ctx.spill = nullptr; ctx.n_spill = 0; ctx.tid = tid;
-        ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
-        ctx.out = out; ctx.inframe = inframe; ctx.whole_bin = whole_bin; ctx.wrote = wrote;
-        ctx.my_cnt = my_cnt; ctx.kmax = kmax;
-        // the list length is warp-uniform after the max-reduce: pick the unroll that fits
-#if SLR_GATHER_EXPERIMENT == 4      // timing experiment only: list building alone
-        if (kmax == 12345) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
-        if (wk[0] + wk[1] + wk[5] == 1.2345e30f) out[0] = wk[3];
-#else
-        switch ((kmax + 1) >> 1) {
-            case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
-            case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
-                    else gather_dispatch<NT, 2>(ctx, pk, wk, nrm, tl);
-                    break;
-            case 2: gather_dispatch<NT, 4>(ctx, pk, wk, nrm, tl); break;
-            case 3: gather_dispatch<NT, 6>(ctx, pk, wk, nrm, tl); break;
-            case 4: gather_dispatch<NT, 8>(ctx, pk, wk, nrm, tl); break;
-            case 5: gather_dispatch<NT, 10>(ctx, pk, wk, nrm, tl); break;
-#if SLR_GATHER_DEPTH == 16
-            case 6: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
-            case 7: gather_dispatch<NT, 14>(ctx, pk, wk, nrm, tl); break;
-            default: gather_dispatch<NT, 16>(ctx, pk, wk, nrm, tl); break;
-#else
-            default: gather_dispatch<NT, 12>(ctx, pk, wk, nrm, tl); break;
-#endif
+        const char* Gg = prm.G;
+        for (int g = 0; g < prm.groups; ++g, Gg += gstride) {
+            for_each_pair([&](int d, unsigned p, float w) {
+                const float4 v = __ldg(px16(Gg, p));
+                atomicAdd(&acc[d * 4 + 0], v.x * w);
+                atomicAdd(&acc[d * 4 + 1], v.y * w);
+                atomicAdd(&acc[d * 4 + 2], v.z * w);
+                atomicAdd(&acc[d * 4 + 3], v.w * w);
+            });
+            __syncthreads();
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 4 * g + j;
+                if (inframe && c < prm.C) __stcs(out + (int64_t)c * P, acc[tid * 4 + j] * inv);
+                acc[tid * 4 + j] = 0.0f;
+            }
+            __syncthreads();
         }
-#endif
-        wrote = true;
-        first_pass = false;
-        cb += len;
+        if (inframe) {
+            if (prm.aux) {
+                float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
+                #pragma unroll
+                for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sn[j * TILE + tid];
+            }
+            if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
+        }
         __syncthreads();
     }
-
-    if (inframe) {
-        const float den = fmaxf(nrm, prm.eps);
-        if (partial) {
-            const float inv = 1.0f / den;
-            for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] *= inv;
-        }
-        if (prm.aux) {
-            float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
-            #pragma unroll
-            for (int j = 0; j < NT; ++j) a[(int64_t)j * P] = tl[j];
-            a[(int64_t)NT * P] = nrm;
-        }
-        if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
-    }
-    __syncthreads();
-    }   // flagged items
 }
 
 // ---------------------------------------------------------------------------
@@ -688,7 +599,6 @@ expand_kernel(const GatherParams prm)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* ell = reinterpret_cast<uint2*>(smem_raw);
     unsigned* cnt = reinterpret_cast<unsigned*>(ell + kSmemDepth * TILE);
-    __shared__ unsigned n_spill_s;
 
     const int tid = threadIdx.x;
     const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
@@ -700,8 +610,6 @@ expand_kernel(const GatherParams prm)
     const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
     const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
     const unsigned beg = __ldg(off + tile), end = __ldg(off + tile + 1);
-    uint4* spill = prm.spill + ((int64_t)f * prm.n_tiles + tile) * kSpillCap;
-    if (tid == 0) n_spill_s = 0u;
     const float4* ent = prm.ent + (int64_t)f * prm.cap;
     // a destination pixel with exactly zero motion receives itself with weight alpha + (1 - alpha)
     // (its forward and backward splat both land exactly on it); it was not binned
@@ -726,27 +634,20 @@ expand_kernel(const GatherParams prm)
                 const unsigned old = atomicOr(&cnt[d], 1u << pref);
                 int slot = pref;
                 if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
-                if (slot < kSmemDepth) {
-                    ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
-                } else {
-                    // deeper than the table (a convergence point): goes to the tile's spill list
-                    const unsigned i = atomicAdd(&n_spill_s, 1u);
-                    if (i < (unsigned)kSpillCap) spill[i] = make_uint4((unsigned)d, pd & ~kDirBit, __float_as_uint(wa), 0u);
-                }
+                if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
             }
         }
     }
     __syncthreads();
-    const int over = n_spill_s > (unsigned)kSpillCap;       // a true sink: the multi-pass kernel takes the tile
+    const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
     if (tid == 0) {
         prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
-        prm.spill_n[(int64_t)f * prm.n_tiles + tile] = over ? 0u : n_spill_s;
         if (over) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
     }
     if (over) return;
 
     const unsigned occ = cnt[tid] & 0xffu;
-    const int n_ovf = min((int)(cnt[tid] >> 8), kSmemDepth - 8);      // the rest is in the spill list
+    const int n_ovf = (int)(cnt[tid] >> 8);
     const int my_cnt = n_ovf > 0 ? 8 + n_ovf : 32 - __clz(occ);
     uint2 e0 = ell[tid], e1 = ell[TILE + tid];
     // same source in slots 0 and 1 (a static pixel's forward and backward self-splat): one slot
@@ -807,18 +708,10 @@ rowgather_kernel(const GatherParams prm)
     float tl[NT > 0 ? NT : 1] = {0.0f};
     GatherCtx ctx;
     ctx.G = prm.G; ctx.S = prm.S; ctx.ell = src; ctx.ell_stride = 32; ctx.P = P;
-    ctx.n_spill = (int)__ldg(prm.spill_n + (int64_t)f * prm.n_tiles + tile);
-    ctx.spill = prm.spill + ((int64_t)f * prm.n_tiles + tile) * kSpillCap;
-    ctx.tid = tid;
     ctx.groups = prm.groups; ctx.C = prm.C; ctx.eps = prm.eps;
     ctx.out = prm.out + (int64_t)f * prm.C * P + pix;
     ctx.inframe = inframe; ctx.whole_bin = true; ctx.wrote = false;
     ctx.my_cnt = kmax; ctx.kmax = kmax;
-    if (ctx.n_spill > 0) {
-        // a tile with convergence points: one generic variant that also walks the spill list
-        if ((prm.C & 3) == 0) gather_lists<NT, kDepth, 1, true, true>(ctx, pk, wk, nrm, tl);
-        else gather_lists<NT, kDepth, 1, false, true>(ctx, pk, wk, nrm, tl);
-    } else
     switch ((kmax + 1) >> 1) {
         case 0: gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl); break;
         case 1: if (kmax == 1) gather_dispatch<NT, 1>(ctx, pk, wk, nrm, tl);
@@ -863,8 +756,6 @@ struct Workspace {
     uint2* lists;         // [n][n_rows][kSmemDepth][32]
     unsigned* row_k;      // [n][n_rows]
     unsigned* tile_flag;  // [n][n_tiles]
-    uint4* spill;         // [n][n_tiles][kSpillCap]
-    unsigned* spill_n;    // [n][n_tiles]
     unsigned* flag_list;  // [n * n_tiles]
     unsigned* flag_count; // [1]
     size_t bytes;
@@ -887,8 +778,6 @@ Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.lists = (uint2*)(p + o);       o += align_up(sizeof(uint2) * 32 * kSmemDepth * (size_t)(tiles * TH) * n);
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * TH * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
-    w.spill = (uint4*)(p + o);       o += align_up(sizeof(uint4) * kSpillCap * tiles * n);
-    w.spill_n = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.bytes = o;
@@ -972,7 +861,6 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count;
-    prm.spill = ws.spill; prm.spill_n = ws.spill_n;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
@@ -989,22 +877,19 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     static bool attr_set = false;      // opt in to > 48 KB dynamic shared memory once
     if (!attr_set) {
         SLR_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-        SLR_CUDA(cudaFuncSetAttribute(multipass_gather_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-        SLR_CUDA(cudaFuncSetAttribute(multipass_gather_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
-        SLR_CUDA(cudaFuncSetAttribute(multipass_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGatherSmem));
         attr_set = true;
     }
     expand_kernel<<<grid, TILE, kGatherSmem, s>>>(prm);
-    const unsigned mp_grid = std::min<unsigned>(grid.x, 2u * (unsigned)slr_host::sm_count());
+    const unsigned mp_grid = std::min<unsigned>(grid.x, 4u * (unsigned)slr_host::sm_count());
     if (n_tail == 0) {
         rowgather_kernel<0><<<grid, TILE, 0, s>>>(prm);
-        multipass_gather_kernel<0><<<mp_grid, TILE, kGatherSmem, s>>>(prm);
+        heavy_tile_kernel<0><<<mp_grid, TILE, 0, s>>>(prm);
     } else if (n_tail == 1) {
         rowgather_kernel<1><<<grid, TILE, 0, s>>>(prm);
-        multipass_gather_kernel<1><<<mp_grid, TILE, kGatherSmem, s>>>(prm);
+        heavy_tile_kernel<1><<<mp_grid, TILE, 0, s>>>(prm);
     } else {
         rowgather_kernel<2><<<grid, TILE, 0, s>>>(prm);
-        multipass_gather_kernel<2><<<mp_grid, TILE, kGatherSmem, s>>>(prm);
+        heavy_tile_kernel<2><<<mp_grid, TILE, 0, s>>>(prm);
     }
     return SLR_LAUNCH_STATUS();
 }
