@@ -47,6 +47,7 @@ constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread ho
 #ifndef SLR_GATHER_SMEM_DEPTH
 #define SLR_GATHER_SMEM_DEPTH 32
 #endif
+constexpr int kHeavyGroups = 2;         // channel groups per work item of heavy_tile_kernel
 constexpr int kSmemDepth = SLR_GATHER_SMEM_DEPTH;   // pairs per destination pixel the shared list table holds
 constexpr int kChunk = 8192;           // bin entries expanded per pass
 constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
@@ -509,9 +510,13 @@ heavy_tile_kernel(const GatherParams prm)
     const int64_t P = prm.P;
     const int64_t sstride = P + 1;
     const size_t gstride = (size_t)(P + 1) * 16;
-    const unsigned n_flagged = *prm.flag_count;
-    for (unsigned item_i = blockIdx.x; item_i < n_flagged; item_i += gridDim.x) {
-        const unsigned item = prm.flag_list[item_i];
+    // work item = (flagged tile, chunk of kHeavyGroups channel groups): the few heavy tiles are
+    // spread over many CTAs so that the slowest one does not serialise the launch
+    const unsigned n_chunks = (unsigned)((prm.groups + kHeavyGroups - 1) / kHeavyGroups);
+    const unsigned n_work = *prm.flag_count * n_chunks;
+    for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const unsigned item = prm.flag_list[wi / n_chunks];
+        const int g_lo = (int)(wi % n_chunks) * kHeavyGroups, g_hi = min(prm.groups, g_lo + kHeavyGroups);
         const int f = (int)(item % (unsigned)prm.n_frames), tile = (int)(item / (unsigned)prm.n_frames);
         const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
         const int X = tx * TW + tile_lx(tid), Y = ty * TH + tile_ly(tid);
@@ -556,8 +561,8 @@ heavy_tile_kernel(const GatherParams prm)
         const float nrm = sn[NT * TILE + tid];
         const float inv = 1.0f / fmaxf(nrm, prm.eps);
 
-        const char* Gg = prm.G;
-        for (int g = 0; g < prm.groups; ++g, Gg += gstride) {
+        const char* Gg = prm.G + (size_t)g_lo * gstride;
+        for (int g = g_lo; g < g_hi; ++g, Gg += gstride) {
             for_each_pair([&](int d, unsigned p, float w) {
                 const float4 v = __ldg(px16(Gg, p));
                 atomicAdd(&acc[d * 4 + 0], v.x * w);
@@ -574,7 +579,7 @@ heavy_tile_kernel(const GatherParams prm)
             }
             __syncthreads();
         }
-        if (inframe) {
+        if (inframe && g_lo == 0) {
             if (prm.aux) {
                 float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
                 #pragma unroll
@@ -880,7 +885,7 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
         attr_set = true;
     }
     expand_kernel<<<grid, TILE, kGatherSmem, s>>>(prm);
-    const unsigned mp_grid = std::min<unsigned>(grid.x, 4u * (unsigned)slr_host::sm_count());
+    const unsigned mp_grid = std::min<unsigned>(grid.x, 8u * (unsigned)slr_host::sm_count());
     if (n_tail == 0) {
         rowgather_kernel<0><<<grid, TILE, 0, s>>>(prm);
         heavy_tile_kernel<0><<<mp_grid, TILE, 0, s>>>(prm);
