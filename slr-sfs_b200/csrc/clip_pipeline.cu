@@ -47,7 +47,7 @@ constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread ho
 #ifndef SLR_GATHER_SMEM_DEPTH
 #define SLR_GATHER_SMEM_DEPTH 32
 #endif
-constexpr int kHeavyGroups = 2;         // channel groups per work item of heavy_tile_kernel
+constexpr int kHeavyGroups = 4;         // channel groups per work item of heavy_tile_kernel
 constexpr int kSmemDepth = SLR_GATHER_SMEM_DEPTH;   // pairs per destination pixel the shared list table holds
 constexpr int kChunk = 8192;           // bin entries expanded per pass
 constexpr int kGatherSmem = kSmemDepth * TILE * 8 + TILE * 4;
@@ -503,7 +503,7 @@ template <int NT>
 __global__ void __launch_bounds__(TILE)
 heavy_tile_kernel(const GatherParams prm)
 {
-    __shared__ float acc[TILE * 4];
+    __shared__ float acc[kHeavyGroups * TILE * 4];      // [group in chunk][pixel][4 channels]
     __shared__ float sn[(NT + 1) * TILE];
 
     const int tid = threadIdx.x;
@@ -551,33 +551,39 @@ heavy_tile_kernel(const GatherParams prm)
         #pragma unroll
         for (int t = 0; t <= NT; ++t) sn[t * TILE + tid] = 0.0f;
         #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[tid * 4 + j] = 0.0f;
+        for (int j = 0; j < 4 * kHeavyGroups; ++j) acc[j * TILE + tid] = 0.0f;
         __syncthreads();
         for_each_pair([&](int d, unsigned p, float w) {
             #pragma unroll
             for (int t = 0; t <= NT; ++t) atomicAdd(&sn[t * TILE + d], __ldg(prm.S + (int64_t)t * sstride + p) * w);
         });
+        // all channel groups of the chunk in one pass over the pairs: kHeavyGroups loads in flight
+        const char* Gg = prm.G + (size_t)g_lo * gstride;
+        for_each_pair([&](int d, unsigned p, float w) {
+            float4 v[kHeavyGroups];
+            #pragma unroll
+            for (int gi = 0; gi < kHeavyGroups; ++gi)
+                v[gi] = g_lo + gi < g_hi ? __ldg(px16(Gg + gi * gstride, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            #pragma unroll
+            for (int gi = 0; gi < kHeavyGroups; ++gi) {
+                float* a = acc + (gi * TILE + d) * 4;
+                atomicAdd(a + 0, v[gi].x * w);
+                atomicAdd(a + 1, v[gi].y * w);
+                atomicAdd(a + 2, v[gi].z * w);
+                atomicAdd(a + 3, v[gi].w * w);
+            }
+        });
         __syncthreads();
         const float nrm = sn[NT * TILE + tid];
         const float inv = 1.0f / fmaxf(nrm, prm.eps);
-
-        const char* Gg = prm.G + (size_t)g_lo * gstride;
-        for (int g = g_lo; g < g_hi; ++g, Gg += gstride) {
-            for_each_pair([&](int d, unsigned p, float w) {
-                const float4 v = __ldg(px16(Gg, p));
-                atomicAdd(&acc[d * 4 + 0], v.x * w);
-                atomicAdd(&acc[d * 4 + 1], v.y * w);
-                atomicAdd(&acc[d * 4 + 2], v.z * w);
-                atomicAdd(&acc[d * 4 + 3], v.w * w);
-            });
-            __syncthreads();
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = 4 * g + j;
-                if (inframe && c < prm.C) __stcs(out + (int64_t)c * P, acc[tid * 4 + j] * inv);
-                acc[tid * 4 + j] = 0.0f;
+        if (inframe) {
+            for (int g = g_lo; g < g_hi; ++g) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 4 * g + j;
+                    if (c < prm.C) __stcs(out + (int64_t)c * P, acc[((g - g_lo) * TILE + tid) * 4 + j] * inv);
+                }
             }
-            __syncthreads();
         }
         if (inframe && g_lo == 0) {
             if (prm.aux) {
