@@ -47,6 +47,7 @@ constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread ho
 #ifndef SLR_GATHER_SMEM_DEPTH
 #define SLR_GATHER_SMEM_DEPTH 32
 #endif
+constexpr int kListDepth = 64;          // slots per pixel in the global row lists (>= kSmemDepth; deeper = heavy tile)
 constexpr int kHeavyGroups = 4;         // channel groups per work item of heavy_tile_kernel
 constexpr int kSmemDepth = SLR_GATHER_SMEM_DEPTH;   // pairs per destination pixel the shared list table holds
 constexpr int kChunk = 8192;           // bin entries expanded per pass
@@ -329,7 +330,7 @@ struct GatherParams {
     const float4* ent;         // [frames][cap]  (pixel | dir << 31, landing x, landing y, -)
     const float* motion;       // [2][P]: a destination pixel with zero motion contributes to itself
     const unsigned* offsets;   // [frames][n_tiles + 1]
-    uint2* lists;              // [frames][n_rows][kSmemDepth][32]: per 32-pixel row, slot-major (source, weight)
+    uint2* lists;              // [frames][n_rows][kListDepth][32]: per 32-pixel row, slot-major (source, weight)
     unsigned* row_k;           // [frames][n_rows]: slots in use in that row (warp-uniform list length)
     unsigned* tile_flag;       // [frames][n_tiles]: 1 = lists overflowed, tile is done by the multi-pass kernel
     unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
@@ -626,6 +627,8 @@ expand_kernel(const GatherParams prm)
     // (its forward and backward splat both land exactly on it); it was not binned
     const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
 
+    const int n_rows = prm.n_tiles * TH;
+    uint2* lists_tile = prm.lists + ((int64_t)f * n_rows + (int64_t)tile * TH) * (kListDepth * 32);
     cnt[tid] = self_static ? 1u : 0u;
     if (self_static) ell[tid] = make_uint2((unsigned)pix, __float_as_uint(a_f + a_b));
     __syncthreads();
@@ -645,12 +648,18 @@ expand_kernel(const GatherParams prm)
                 const unsigned old = atomicOr(&cnt[d], 1u << pref);
                 int slot = pref;
                 if (old >> pref & 1u) slot = 8 + (int)(atomicAdd(&cnt[d], 256u) >> 8);
-                if (slot < kSmemDepth) ell[slot * TILE + d] = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
+                const uint2 pair = make_uint2(pd & ~kDirBit, __float_as_uint(wa));
+                if (slot < kSmemDepth) {
+                    ell[slot * TILE + d] = pair;
+                } else if (slot < kListDepth) {
+                    // deeper than the shared table: straight to its place in the global row list
+                    __stcg(lists_tile + ((int64_t)(d >> 5) * kListDepth + slot) * 32 + (d & 31), pair);
+                }
             }
         }
     }
     __syncthreads();
-    const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kSmemDepth);
+    const int over = __syncthreads_or(8 + (int)(cnt[tid] >> 8) > kListDepth);
     if (tid == 0) {
         prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
         if (over) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
@@ -665,17 +674,18 @@ expand_kernel(const GatherParams prm)
     const bool merged = my_cnt == 2 && occ == 3u && e0.x == e1.x;
     if (merged) e0.y = __float_as_uint(__uint_as_float(e0.y) + __uint_as_float(e1.y));
     const int kmax = __reduce_max_sync(0xffffffffu, merged ? 1 : my_cnt);
-    const int n_rows = prm.n_tiles * TH;
     const int64_t row = (int64_t)f * n_rows + (int64_t)tile * TH + (tid >> 5);
     if ((tid & 31) == 0) prm.row_k[row] = (unsigned)kmax;
-    uint2* dst = prm.lists + row * (kSmemDepth * 32) + (tid & 31);
+    uint2* dst = prm.lists + row * (kListDepth * 32) + (tid & 31);
     const uint2 none = make_uint2((unsigned)P, 0u);       // the zero pixel, weight 0
-    for (int k = 0; k < kmax; ++k) {
+    for (int k = 0; k < min(kmax, kSmemDepth); ++k) {
         uint2 e = k == 0 ? e0 : ell[k * TILE + tid];
         bool used = k < 8 ? (occ >> k & 1u) : (k - 8 < n_ovf);
         if (merged && k == 1) used = false;
         __stcg(dst + k * 32, used ? e : none);
     }
+    // slots past the shared table were written in place; pad this lane's unused ones
+    for (int k = max(my_cnt, kSmemDepth); k < kmax; ++k) __stcg(dst + k * 32, none);
 }
 
 // ---------------------------------------------------------------------------
@@ -704,7 +714,7 @@ rowgather_kernel(const GatherParams prm)
     const int n_rows = prm.n_tiles * TH;
     const int64_t row = (int64_t)f * n_rows + (int64_t)tile * TH + (tid >> 5);
     const int kmax = (int)__ldg(prm.row_k + row);
-    const uint2* src = prm.lists + row * (kSmemDepth * 32) + (tid & 31);
+    const uint2* src = prm.lists + row * (kListDepth * 32) + (tid & 31);
 
     unsigned pk[kDepth];
     float wk[kDepth];
@@ -764,7 +774,7 @@ struct Workspace {
     unsigned* counts;     // [n][n_tiles]      (counts, then cursors)
     unsigned* offsets;    // [n][n_tiles + 1]
     float4* ent;          // [n][cap]
-    uint2* lists;         // [n][n_rows][kSmemDepth][32]
+    uint2* lists;         // [n][n_rows][kListDepth][32]
     unsigned* row_k;      // [n][n_rows]
     unsigned* tile_flag;  // [n][n_tiles]
     unsigned* flag_list;  // [n * n_tiles]
@@ -786,7 +796,7 @@ Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
     w.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
     w.ent = (float4*)(p + o);        o += align_up(sizeof(float4) * cap * n);
-    w.lists = (uint2*)(p + o);       o += align_up(sizeof(uint2) * 32 * kSmemDepth * (size_t)(tiles * TH) * n);
+    w.lists = (uint2*)(p + o);       o += align_up(sizeof(uint2) * 32 * kListDepth * (size_t)(tiles * TH) * n);
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * TH * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
