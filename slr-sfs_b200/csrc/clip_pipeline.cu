@@ -45,7 +45,10 @@ constexpr int TILE = TW * TH;          // threads per gather CTA, one destinatio
 #endif
 constexpr int kDepth = SLR_GATHER_DEPTH;   // (source, weight) pairs a thread holds in registers
 #ifndef SLR_GATHER_SMEM_DEPTH
-#define SLR_GATHER_SMEM_DEPTH 32
+#define SLR_GATHER_SMEM_DEPTH 12
+#endif
+#ifndef SLR_EXPAND_MINBLOCKS
+#define SLR_EXPAND_MINBLOCKS 8
 #endif
 constexpr int kListDepth = 64;          // slots per pixel in the global row lists (>= kSmemDepth; deeper = heavy tile)
 constexpr int kHeavyGroups = 4;         // channel groups per work item of heavy_tile_kernel
@@ -605,7 +608,7 @@ heavy_tile_kernel(const GatherParams prm)
 // gather kernel needs no shared memory and no barriers.  Small register footprint: several
 // CTAs per SM hide the latency of this pointer-chasing part.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE, 3)
+__global__ void __launch_bounds__(TILE, SLR_EXPAND_MINBLOCKS)
 expand_kernel(const GatherParams prm)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
