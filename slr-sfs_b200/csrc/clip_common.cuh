@@ -1,0 +1,116 @@
+// Shared definitions of the clip pipeline (csrc/clip_plan.cu, csrc/clip_gather.cu).
+#pragma once
+#include "slr_common.cuh"
+#include "slr_host.h"
+#include <algorithm>
+
+namespace slr {
+
+constexpr int TW = 32;                 // destination tile width  (one warp per tile row)
+constexpr int TH = 8;                  // destination tile height
+constexpr int TILE = TW * TH;          // destination pixels per tile
+constexpr int kMaxFrames = 64;         // frames per launch (alpha table lives in the kernel parameters)
+constexpr unsigned kDirBit = 0x80000000u;   // bin entry: source pixel | direction << 31
+constexpr float kStaticLand = -1.0e30f;     // landing marker of pixels that are not binned
+
+// Row-pair lists (the interface between expand_kernel and rowgather_kernel): a destination
+// tile is 4 row pairs; a lane of a row pair owns the pixels (x, y) and (x, y + 1).  Per row
+// pair the lists are slot-major: slot k holds, for each of the 32 lanes, one source pixel and
+// its weights for the top and the bottom pixel.
+constexpr int kPairsPerTile = TH / 2;
+constexpr int kCanon = 12;             // canonical slots (direction x source-row offset x east/west)
+constexpr int kListDepth = 48;         // slots per lane in the global lists; deeper = heavy tile
+
+struct FrameAlphas { float a[kMaxFrames]; };
+
+// Destination tiles touched by a footprint, in a fixed order shared by the count
+// and the fill pass.  East / south columns only count when their weight is
+// non-zero (landing exactly on a cell -- static pixels -- touches one cell).
+__device__ __forceinline__ void touched_tiles(const Footprint& f, float ox, float oy, int H, int W,
+                                              int tiles_x, int out[4])
+{
+    out[0] = out[1] = out[2] = out[3] = -1;
+    if (f.ok == 0u) return;
+    const bool c0 = f.x0 >= 0 && f.x0 < W;
+    const bool c1 = f.x0 + 1 >= 0 && f.x0 + 1 < W && ox > (float)f.x0;
+    const bool r0 = f.y0 >= 0 && f.y0 < H;
+    const bool r1 = f.y0 + 1 >= 0 && f.y0 + 1 < H && oy > (float)f.y0;
+    const int tc0 = c0 ? f.x0 / TW : -1;
+    int tc1 = c1 ? (f.x0 + 1) / TW : -1;
+    const int tr0 = r0 ? f.y0 / TH : -1;
+    int tr1 = r1 ? (f.y0 + 1) / TH : -1;
+    if (tc1 == tc0) tc1 = -1;
+    if (tr1 == tr0) tr1 = -1;
+    if (tr0 >= 0 && tc0 >= 0) out[0] = tr0 * tiles_x + tc0;
+    if (tr0 >= 0 && tc1 >= 0) out[1] = tr0 * tiles_x + tc1;
+    if (tr1 >= 0 && tc0 >= 0) out[2] = tr1 * tiles_x + tc0;
+    if (tr1 >= 0 && tc1 >= 0) out[3] = tr1 * tiles_x + tc1;
+}
+
+// Warp-aggregated "reserve one slot in counters[key]" for the lanes whose key >= 0.
+// All 32 lanes must call.  Returns the lane's slot (undefined for key < 0).
+__device__ __forceinline__ unsigned warp_reserve(unsigned* counters, int key)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (key >= 0 && (int)lane == leader) base = atomicAdd(counters + key, (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+}
+
+
+// address of pixel `p` in a float4 plane: one IMAD.WIDE
+__device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
+{
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(p), "l"(plane));
+    return reinterpret_cast<const float4*>(a);
+}
+
+}  // namespace slr
+
+// ---------------------------------------------------------------------------
+// host side: layout of the caller-provided workspace
+// ---------------------------------------------------------------------------
+namespace slr_host {
+
+struct Workspace {
+    float* land;          // [n][2 dirs][2][P]   landing coordinates
+    unsigned* counts;     // [n][n_tiles]        entries per destination tile (then fill cursors)
+    unsigned* offsets;    // [n][n_tiles + 1]    bin offsets
+    float4* ent;          // [n][cap]            bin entries (pixel | dir << 31, landing x, landing y, -)
+    uint4* lists;         // [n][n_tiles * 4][kListDepth][32]  row-pair lists (source, w_top, w_bottom, -)
+    unsigned* row_k;      // [n][n_tiles * 4]    slots in use per row pair
+    unsigned* tile_flag;  // [n][n_tiles]        1 = heavy tile
+    unsigned* flag_list;  // [n * n_tiles]       compacted heavy tiles
+    unsigned* flag_count; // [1]
+    size_t bytes;
+};
+
+inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+inline Workspace carve(void* base, int64_t H, int64_t W, int n)
+{
+    using namespace slr;
+    const int64_t P = H * W;
+    const int64_t tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+    const int64_t cap = 8 * P;      // every (pixel, direction) touches at most 4 tiles
+    char* p = (char*)base;
+    size_t o = 0;
+    Workspace w;
+    w.land = (float*)(p + o);        o += align_up(sizeof(float) * 4 * P * n);
+    w.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
+    w.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
+    w.ent = (float4*)(p + o);        o += align_up(sizeof(float4) * cap * n);
+    w.lists = (uint4*)(p + o);       o += align_up(sizeof(uint4) * 32 * kListDepth * (size_t)(tiles * kPairsPerTile) * n);
+    w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * kPairsPerTile * n);
+    w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
+    w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
+    w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
+    w.bytes = o;
+    return w;
+}
+
+}  // namespace slr_host

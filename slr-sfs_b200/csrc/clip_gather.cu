@@ -1,0 +1,531 @@
+// Clip pipeline, part 2 ("algorithm G"): the joint block of the reference models
+// (/root/reference/models/animating_softmax_splating.py:862-924: two summation splats of
+// [fs*e^Z*a, e^Z*a], their sum, clamp and divide) as bin-by-destination + GATHER.
+//
+// Why not scatter: a frame at 768x1024x65 is 2 directions x 4 corners x 51 M elements =
+// 409 M fp32 atomics; the measured L2 reduction rate on B200 (profiles/r01: 0.65 ms per
+// frame) is 10x the HBM time of the same bytes.  The splat weights do not depend on the
+// channel, so the scatter is a sparse (destination x source) operator applied to all
+// channels: its structure is built once per frame from the displacement alone, and then
+// every destination pixel PULLS its contributions, accumulates them in registers and
+// writes the normalised result once.  No feature atomics, no accumulator round trip
+// through HBM, no separate normalise pass.
+//
+//   expand_kernel     one CTA per (destination tile 32x8, frame): turns the tile's bin into
+//                     per-lane (source, w_top, w_bottom) lists for its 4 row pairs.  Small
+//                     register footprint, 8 CTAs/SM: hides the latency of this pointer-chasing.
+//   rowgather_kernel  the hot kernel.  One warp per row pair (2 x 32 destination pixels), no
+//                     shared memory, no barriers.  A lane owns the pixels (x, y) and (x, y+1):
+//                     a source that feeds both (its north corners land on y, its south
+//                     corners on y+1) is loaded ONCE -- 12 loads instead of 16 per pixel pair
+//                     in regular flow.  Per channel group: <=12 independent LDG.128 in flight,
+//                     then the FMAs, then streaming stores.
+//   heavy_tile_kernel tiles with a pixel deeper than the lists hold (convergence zones of the
+//                     flow): per-pair accumulation in shared memory, cost linear in pairs.
+#include "clip_common.cuh"
+
+namespace slr {
+
+#ifndef SLR_GATHER_MINBLOCKS
+#define SLR_GATHER_MINBLOCKS 4         // resident 128-thread CTAs per SM the register budget is sized for
+#endif
+#ifndef SLR_EXPAND_MINBLOCKS
+#define SLR_EXPAND_MINBLOCKS 6
+#endif
+constexpr int kRegSlots = 16;          // list slots a lane keeps in registers; deeper ones are re-read per group
+constexpr int kSmemSlots = 16;         // list slots expand_kernel stages in shared memory (>= kCanon)
+constexpr int kCols = TW * kPairsPerTile;   // 128 lanes (columns of row pairs) per tile
+constexpr int kHeavyGroups = 4;        // channel groups per work item of heavy_tile_kernel
+constexpr unsigned kEmpty = 0xffffffffu;
+
+struct GatherParams {
+    const char* G;             // [groups] planes of (P + 1) float4; pixel P of every plane is all-zero
+    const float* S;            // [n_tail + 1] planes of (P + 1) float (last plane = e^Z)
+    const float4* ent;         // [frames][cap] bin entries
+    const float* motion;       // [2][P]: a destination pixel with zero motion contributes to itself
+    const unsigned* offsets;   // [frames][n_tiles + 1]
+    uint4* lists;              // [frames][n_tiles * 4][kListDepth][32]
+    unsigned* row_k;           // [frames][n_tiles * 4]
+    unsigned* tile_flag;       // [frames][n_tiles]
+    unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the heavy tiles
+    unsigned* flag_count;      // [1], zeroed by slr_clip_plan
+    float* out;                // [frames][C][P]
+    float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
+    float* mask;               // [frames][P] norm > eps, or NULL
+    int C, groups, H, W, tiles_x, n_tiles, n_frames;
+    int64_t P, cap;
+    float eps;
+    FrameAlphas alphas;
+};
+
+// Canonical slot of a pair: direction, row offset of the source's north-west cell relative
+// to the lane's TOP pixel (-1, 0, +1) and whether the pair is a west (dx = 0) or east corner.
+//   slots 0..7  : dx*4 + dir*2 + cy      cy = 0: feeds top (north corner) AND bottom (south corner)
+//                                         cy = 1: feeds the bottom pixel only (north corner)
+//   slots 8..11 : 8 + dir*2 + dx         cy = -1: feeds the top pixel only (south corner)
+// Slot 0 / 1 are where a static pixel's own contribution goes, so static rows need 2 slots.
+__device__ __forceinline__ int canon_slot(unsigned dir, int cy, int dx)
+{
+    return cy < 0 ? 8 + 2 * (int)dir + dx : (dx << 2) | ((int)dir << 1) | cy;
+}
+enum SlotRole { kBoth, kTopOnly, kBottomOnly };
+__host__ __device__ constexpr SlotRole slot_role(int k)
+{
+    return k < 8 ? ((k & 1) ? kBottomOnly : kBoth) : (k < kCanon ? kTopOnly : kBoth);
+}
+
+// ---------------------------------------------------------------------------
+// expand_kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE, SLR_EXPAND_MINBLOCKS)
+expand_kernel(const GatherParams prm)
+{
+    __shared__ uint4 tab[kSmemSlots * kCols];      // tab[slot * kCols + col] = (source, w_top, w_bottom, -)
+    __shared__ unsigned occ[kCols];                // used canonical slots (bit mask)
+    __shared__ unsigned ovf[kCols];                // overflow slots in use (kCanon, kCanon + 1, ...)
+
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+    const int64_t P = prm.P;
+    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+    const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+    const unsigned beg = __ldg(off + tile), end = __ldg(off + tile + 1);
+    const float4* ent = prm.ent + (int64_t)f * prm.cap;
+    const int64_t pair0 = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile;
+    uint4* lists_tile = prm.lists + pair0 * (kListDepth * 32);
+
+    for (int i = tid; i < kCanon * kCols; i += TILE) tab[i] = make_uint4(kEmpty, 0u, 0u, 0u);
+    if (tid < kCols) { occ[tid] = 0u; ovf[tid] = 0u; }
+    __syncthreads();
+
+    // one (destination pixel, source, weight) pair -> its lane's list
+    auto insert = [&](int lx, int ly, unsigned p, float w, unsigned dir, int dx, int dy) {
+        const int col = (ly >> 1) * TW + lx, r = ly & 1;
+        const int s = canon_slot(dir, r - dy, dx);
+        uint4* cell = tab + s * kCols + col;
+        const unsigned old = atomicCAS(&cell->x, kEmpty, p);
+        if (old == kEmpty) atomicOr(&occ[col], 1u << s);
+        if (old == kEmpty || old == p) {
+            // the slot is this source's: the other row's corner of the same source shares it
+            (r ? cell->z : cell->y) = __float_as_uint(w);
+        } else {
+            const int so = kCanon + (int)atomicAdd(&ovf[col], 1u);
+            const uint4 e = make_uint4(p, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, 0u);
+            if (so < kSmemSlots) tab[so * kCols + col] = e;
+            else if (so < kListDepth)     // deeper than the shared table: straight to its place in the global list
+                __stcg(lists_tile + ((int64_t)(ly >> 1) * kListDepth + so) * 32 + lx, e);
+        }
+    };
+
+    {   // a destination pixel with exactly zero motion receives itself with weight a + (1 - a)
+        // (its forward and backward splat both land exactly on it); it was not binned
+        const int lx = tid & 31, ly = tid >> 5;
+        const int X = tx * TW + lx, Y = ty * TH + ly;
+        if (X < prm.W && Y < prm.H) {
+            const int64_t pix = (int64_t)Y * prm.W + X;
+            if (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f)
+                insert(lx, ly, (unsigned)pix, a_f + a_b, 0u, 0, 0);
+        }
+    }
+    for (unsigned e = beg + tid; e < end; e += TILE) {
+        const float4 en = __ldcs(ent + e);
+        const unsigned pd = __float_as_uint(en.x);
+        const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+        const unsigned dir = pd >> 31;
+        const float a = dir ? a_b : a_f;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+            const float wa = fp.w[k] * a;
+            if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                insert(lx, ly, pd & ~kDirBit, wa, dir, k & 1, k >> 1);
+        }
+    }
+    __syncthreads();
+    const bool deep = tid < kCols && kCanon + (int)ovf[tid] > kListDepth;
+    const int over = __syncthreads_or(deep);
+    if (tid == 0) {
+        prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
+        if (over) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
+    }
+    if (over || tid >= kCols) return;
+
+    // write the lists out, slot-major per row pair
+    const unsigned my_occ = occ[tid];
+    const int n_ovf = (int)ovf[tid];
+    const int my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz(my_occ);    // slots [0, my_hi) may be used
+    const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
+    const int64_t pair = pair0 + (tid >> 5);
+    if ((tid & 31) == 0) prm.row_k[pair] = (unsigned)kmax;
+    uint4* dst = prm.lists + pair * (kListDepth * 32) + (tid & 31);
+    const uint4 none = make_uint4((unsigned)P, 0u, 0u, 0u);     // the zero pixel, weights 0
+    for (int k = 0; k < min(kmax, kSmemSlots); ++k) {
+        const bool used = k < kCanon ? (my_occ >> k & 1u) : (k - kCanon < n_ovf);
+        __stcg(dst + k * 32, used ? tab[k * kCols + tid] : none);
+    }
+    // slots past the shared table were written in place; pad this lane's unused ones
+    for (int k = max(my_hi, kSmemSlots); k < kmax; ++k) __stcg(dst + k * 32, none);
+}
+
+// ---------------------------------------------------------------------------
+// rowgather_kernel
+// CTA = 4 warps = the 4 row pairs of one destination tile (vertically shared sources stay in
+// this SM's L1).  CTA order is frame-fastest: the CTAs resident at any moment work on the
+// SAME destination tiles of all frames of the batch; their source regions differ only by the
+// frame-to-frame displacement, so a source line is fetched from HBM once per batch and the
+// other frames hit it in L2 (one frame's features alone, 204 MB, exceed the 126 MB L2).
+// ---------------------------------------------------------------------------
+struct RowCtx {
+    const char* G;        // group plane 0
+    const float* S;       // scalar plane 0
+    const uint4* list;    // this lane's column of the row-pair list (slot stride 32)
+    float* out_top;       // this lane's top pixel in plane 0 of the frame (bottom = + W)
+    int64_t P;
+    int W, groups, C, kmax;
+    float eps;
+    bool in_top, in_bot;
+};
+
+// K  = compile-time number of register-resident slots (the warp's list length rounded up);
+// GI = channel groups per iteration: K * GI <= 12 independent LDG.128 are issued before the
+//      first FMA that consumes them (a warp pays one full memory latency per iteration).
+template <int NT, int K, int GI>
+__device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk)[kRegSlots],
+                                            const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
+                                            float (&sum_t)[NT + 1], float (&sum_b)[NT + 1])
+{
+    const int64_t sstride = c.P + 1;
+    // scalar planes: tail channels, then the e^Z weight (the normaliser)
+    {
+        float sv[NT + 1][K];
+        #pragma unroll
+        for (int k = 0; k < K; ++k) {
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) sv[t][k] = __ldg(c.S + (int64_t)t * sstride + pk[k]);
+        }
+        #pragma unroll
+        for (int k = 0; k < K; ++k) {
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) {
+                if (slot_role(k) != kBottomOnly) sum_t[t] = fmaf(sv[t][k], wt[k], sum_t[t]);
+                if (slot_role(k) != kTopOnly) sum_b[t] = fmaf(sv[t][k], wb[k], sum_b[t]);
+            }
+        }
+    }
+    if (K == kRegSlots) {
+        for (int k = kRegSlots; k < c.kmax; ++k) {          // rare: lists deeper than the registers hold
+            const uint4 e = __ldcg(c.list + k * 32);
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) {
+                const float s = __ldg(c.S + (int64_t)t * sstride + e.x);
+                sum_t[t] = fmaf(s, __uint_as_float(e.y), sum_t[t]);
+                sum_b[t] = fmaf(s, __uint_as_float(e.z), sum_b[t]);
+            }
+        }
+    }
+    const float inv_t = 1.0f / fmaxf(sum_t[NT], c.eps), inv_b = 1.0f / fmaxf(sum_b[NT], c.eps);
+
+    const char* Gg = c.G;
+    const size_t gstride = (size_t)(c.P + 1) * 16;
+    const size_t ostride = (size_t)c.P;
+    float* o = c.out_top;
+    for (int g = 0; g < c.groups; g += GI, Gg += GI * gstride, o += 4 * GI * ostride) {
+        constexpr int B = K <= 12 ? K : K / 2;       // the deepest bucket loads in two halves
+        float4 at[GI], ab[GI];
+        #pragma unroll
+        for (int gi = 0; gi < GI; ++gi) at[gi] = ab[gi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        #pragma unroll
+        for (int kb = 0; kb < K; kb += B) {
+            float4 v[GI][B];
+            #pragma unroll
+            for (int gi = 0; gi < GI; ++gi) {
+                #pragma unroll
+                for (int k = 0; k < B; ++k) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
+            }
+            #pragma unroll
+            for (int gi = 0; gi < GI; ++gi) {
+                #pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    if (slot_role(kb + k) != kBottomOnly) {
+                        at[gi].x = fmaf(v[gi][k].x, wt[kb + k], at[gi].x);
+                        at[gi].y = fmaf(v[gi][k].y, wt[kb + k], at[gi].y);
+                        at[gi].z = fmaf(v[gi][k].z, wt[kb + k], at[gi].z);
+                        at[gi].w = fmaf(v[gi][k].w, wt[kb + k], at[gi].w);
+                    }
+                    if (slot_role(kb + k) != kTopOnly) {
+                        ab[gi].x = fmaf(v[gi][k].x, wb[kb + k], ab[gi].x);
+                        ab[gi].y = fmaf(v[gi][k].y, wb[kb + k], ab[gi].y);
+                        ab[gi].z = fmaf(v[gi][k].z, wb[kb + k], ab[gi].z);
+                        ab[gi].w = fmaf(v[gi][k].w, wb[kb + k], ab[gi].w);
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int gi = 0; gi < GI; ++gi) {
+            if (K == kRegSlots) {
+                for (int k = kRegSlots; k < c.kmax; ++k) {
+                    const uint4 e = __ldcg(c.list + k * 32);
+                    const float4 t = __ldg(px16(Gg + gi * gstride, e.x));
+                    const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
+                    at[gi].x = fmaf(t.x, w0, at[gi].x); at[gi].y = fmaf(t.y, w0, at[gi].y);
+                    at[gi].z = fmaf(t.z, w0, at[gi].z); at[gi].w = fmaf(t.w, w0, at[gi].w);
+                    ab[gi].x = fmaf(t.x, w1, ab[gi].x); ab[gi].y = fmaf(t.y, w1, ab[gi].y);
+                    ab[gi].z = fmaf(t.z, w1, ab[gi].z); ab[gi].w = fmaf(t.w, w1, ab[gi].w);
+                }
+            }
+            float* og = o + 4 * gi * ostride;
+            const float rt[4] = {at[gi].x * inv_t, at[gi].y * inv_t, at[gi].z * inv_t, at[gi].w * inv_t};
+            const float rb[4] = {ab[gi].x * inv_b, ab[gi].y * inv_b, ab[gi].z * inv_b, ab[gi].w * inv_b};
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (4 * (g + gi) + j < c.C) {
+                    if (c.in_top) __stcs(og + j * ostride, rt[j]);
+                    if (c.in_bot) __stcs(og + j * ostride + c.W, rb[j]);
+                }
+            }
+        }
+    }
+}
+
+template <int NT, int K>
+__device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsigned (&pk)[kRegSlots],
+                                                     const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
+                                                     float (&sum_t)[NT + 1], float (&sum_b)[NT + 1])
+{
+    constexpr int GI = K <= 2 ? 4 : K <= 6 ? 2 : 1;
+    if (c.groups % GI == 0) gather_rows<NT, K, GI>(c, pk, wt, wb, sum_t, sum_b);
+    else gather_rows<NT, K, 1>(c, pk, wt, wb, sum_t, sum_b);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kCols, SLR_GATHER_MINBLOCKS)
+rowgather_kernel(const GatherParams prm)
+{
+    const int tid = threadIdx.x;
+    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    if (__ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile) != 0u) return;    // heavy_tile_kernel's tile
+    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+    const int X = tx * TW + (tid & 31), Y = ty * TH + 2 * (tid >> 5);
+    const int64_t P = prm.P;
+    const int64_t pix = (int64_t)Y * prm.W + X;
+    const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + (tid >> 5);
+    const int kmax = (int)__ldg(prm.row_k + pair);
+
+    RowCtx c;
+    c.G = prm.G; c.S = prm.S; c.P = P; c.W = prm.W; c.groups = prm.groups; c.C = prm.C; c.eps = prm.eps;
+    c.list = prm.lists + pair * (kListDepth * 32) + (tid & 31);
+    c.out_top = prm.out + (int64_t)f * prm.C * P + pix;
+    c.in_top = X < prm.W && Y < prm.H;
+    c.in_bot = X < prm.W && Y + 1 < prm.H;
+    c.kmax = kmax;
+
+    unsigned pk[kRegSlots];
+    float wt[kRegSlots], wb[kRegSlots];
+    #pragma unroll
+    for (int k = 0; k < kRegSlots; ++k) {
+        uint4 e = make_uint4((unsigned)P, 0u, 0u, 0u);
+        if (k < kmax) e = __ldcg(c.list + k * 32);
+        pk[k] = e.x;
+        wt[k] = __uint_as_float(e.y);
+        wb[k] = __uint_as_float(e.z);
+    }
+    float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
+    // the list length is warp-uniform: pick the unroll that fits
+    if (kmax <= 2) gather_rows_dispatch<NT, 2>(c, pk, wt, wb, sum_t, sum_b);
+    else if (kmax <= 4) gather_rows_dispatch<NT, 4>(c, pk, wt, wb, sum_t, sum_b);
+    else if (kmax <= 6) gather_rows_dispatch<NT, 6>(c, pk, wt, wb, sum_t, sum_b);
+    else if (kmax <= 8) gather_rows_dispatch<NT, 8>(c, pk, wt, wb, sum_t, sum_b);
+    else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b);
+    else gather_rows_dispatch<NT, 16>(c, pk, wt, wb, sum_t, sum_b);
+
+    #pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (!(r ? c.in_bot : c.in_top)) continue;
+        const float* sum = r ? sum_b : sum_t;
+        const int64_t px = pix + (r ? prm.W : 0);
+        if (prm.aux) {
+            float* a = prm.aux + (int64_t)f * (NT + 1) * P + px;
+            #pragma unroll
+            for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sum[j];
+        }
+        if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// heavy_tile_kernel: destination tiles in which some lane's list is deeper than kListDepth
+// (convergence zones of the flow: the synthetic 60-step fields pile up to ~100 sources on
+// single pixels and 10x the average number of pairs on single tiles).  Work is assigned per
+// PAIR instead of per destination pixel: every thread walks bin entries and adds into a
+// per-tile accumulator in shared memory, kHeavyGroups channel groups per pass, so the cost
+// is linear in the number of pairs whatever their distribution.  A fixed grid walks the
+// compacted list of (heavy tile, chunk of channel groups) work items.
+// ---------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(TILE)
+heavy_tile_kernel(const GatherParams prm)
+{
+    __shared__ float acc[kHeavyGroups * TILE * 4];      // [group in chunk][pixel][4 channels]
+    __shared__ float sn[(NT + 1) * TILE];
+
+    const int tid = threadIdx.x;
+    const int64_t P = prm.P;
+    const int64_t sstride = P + 1;
+    const size_t gstride = (size_t)(P + 1) * 16;
+    const unsigned n_chunks = (unsigned)((prm.groups + kHeavyGroups - 1) / kHeavyGroups);
+    const unsigned n_work = *prm.flag_count * n_chunks;
+    for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const unsigned item = prm.flag_list[wi / n_chunks];
+        const int g_lo = (int)(wi % n_chunks) * kHeavyGroups, g_hi = min(prm.groups, g_lo + kHeavyGroups);
+        const int f = (int)(item % (unsigned)prm.n_frames), tile = (int)(item / (unsigned)prm.n_frames);
+        const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+        const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
+        const bool inframe = X < prm.W && Y < prm.H;
+        const int64_t pix = (int64_t)Y * prm.W + X;
+        const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+        const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+        const unsigned beg = off[tile], end = off[tile + 1];
+        const float4* ent = prm.ent + (int64_t)f * prm.cap;
+        const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
+        const float w_self = a_f + a_b;
+        float* out = prm.out + (int64_t)f * prm.C * P + pix;
+
+        // visits every (destination thread, source pixel, weight) pair of the bin that lands in this tile
+        auto for_each_pair = [&](auto&& fn) {
+            if (self_static) fn(tid, (unsigned)pix, w_self);
+            for (unsigned e = beg + tid; e < end; e += TILE) {
+                const float4 en = __ldg(ent + e);
+                const unsigned pd = __float_as_uint(en.x);
+                const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+                const float a = (pd >> 31) ? a_b : a_f;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                    const float wa = fp.w[k] * a;
+                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                        fn(ly * TW + lx, pd & ~kDirBit, wa);
+                }
+            }
+        };
+
+        #pragma unroll
+        for (int t = 0; t <= NT; ++t) sn[t * TILE + tid] = 0.0f;
+        #pragma unroll
+        for (int j = 0; j < 4 * kHeavyGroups; ++j) acc[j * TILE + tid] = 0.0f;
+        __syncthreads();
+        for_each_pair([&](int d, unsigned p, float w) {
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) atomicAdd(&sn[t * TILE + d], __ldg(prm.S + (int64_t)t * sstride + p) * w);
+        });
+        // all channel groups of the chunk in one pass over the pairs: kHeavyGroups loads in flight
+        const char* Gg = prm.G + (size_t)g_lo * gstride;
+        for_each_pair([&](int d, unsigned p, float w) {
+            float4 v[kHeavyGroups];
+            #pragma unroll
+            for (int gi = 0; gi < kHeavyGroups; ++gi)
+                v[gi] = g_lo + gi < g_hi ? __ldg(px16(Gg + gi * gstride, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            #pragma unroll
+            for (int gi = 0; gi < kHeavyGroups; ++gi) {
+                float* a = acc + (gi * TILE + d) * 4;
+                atomicAdd(a + 0, v[gi].x * w);
+                atomicAdd(a + 1, v[gi].y * w);
+                atomicAdd(a + 2, v[gi].z * w);
+                atomicAdd(a + 3, v[gi].w * w);
+            }
+        });
+        __syncthreads();
+        const float nrm = sn[NT * TILE + tid];
+        const float inv = 1.0f / fmaxf(nrm, prm.eps);
+        if (inframe) {
+            for (int g = g_lo; g < g_hi; ++g) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 4 * g + j;
+                    if (c < prm.C) __stcs(out + (int64_t)c * P, acc[((g - g_lo) * TILE + tid) * 4 + j] * inv);
+                }
+            }
+            if (g_lo == 0) {
+                if (prm.aux) {
+                    float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
+                    #pragma unroll
+                    for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sn[j * TILE + tid];
+                }
+                if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace slr
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace slr;
+using slr_host::carve;
+using slr_host::Workspace;
+
+extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
+                               int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                               float* out, float* aux, float* mask,
+                               const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(scene && motion && out && workspace && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   n_tail >= 0 && n_tail <= 2 && n_frames > 0 && n_frames <= kMaxFrames &&
+                   t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)workspace & 15) == 0,
+                   "slr_clip_gather: bad arguments");
+    const int64_t P = H * W;
+    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
+    const int n_tiles = tiles_x * tiles_y;
+    const Workspace ws = carve(const_cast<void*>(workspace), H, W, n_frames);
+    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_gather: workspace too small (see slr_clip_workspace_bytes)");
+
+    GatherParams prm;
+    const int groups = (int)((C + 3) / 4);
+    prm.G = (const char*)scene;
+    prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
+    prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
+    prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
+    prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count;
+    prm.out = out; prm.aux = aux; prm.mask = mask;
+    prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
+    prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.n_frames = n_frames;
+    prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
+    for (int f = 0; f < n_frames; ++f) {
+        // alpha = 1 - (t - start) / (end - start + 1) in fp32 (animating_softmax_splating.py:860),
+        // optionally clamped (2layers...py:952)
+        float a = 1.0f - (float)(t0 + f - start) / (float)(end - start + 1);
+        a = fminf(fmaxf(a, alpha_lo), alpha_hi);
+        prm.alphas.a[f] = a;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    const unsigned grid = (unsigned)n_tiles * (unsigned)n_frames;
+    const unsigned heavy_grid = std::min<unsigned>(grid, 8u * (unsigned)slr_host::sm_count());
+    expand_kernel<<<grid, TILE, 0, s>>>(prm);
+    if (n_tail == 0) {
+        rowgather_kernel<0><<<grid, kCols, 0, s>>>(prm);
+        heavy_tile_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
+    } else if (n_tail == 1) {
+        rowgather_kernel<1><<<grid, kCols, 0, s>>>(prm);
+        heavy_tile_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
+    } else {
+        rowgather_kernel<2><<<grid, kCols, 0, s>>>(prm);
+        heavy_tile_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
+    }
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tail,
+                               int64_t H, int64_t W, int start, int end, int t0, int n_frames,
+                               float alpha_lo, float alpha_hi,
+                               float* out, float* aux, float* mask,
+                               void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    int rc = slr_clip_plan(motion, H, W, start, end, t0, n_frames, workspace, workspace_bytes, stream_);
+    if (rc) return rc;
+    return slr_clip_gather(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                           out, aux, mask, workspace, workspace_bytes, stream_);
+}

@@ -1,0 +1,289 @@
+// Clip pipeline, part 1: everything that depends on the scene or on the motion only.
+//
+//   scene_prep      once per scene: G4[g][p] = feat[4g..4g+3][p] * e^(Z[p]-zsub) as float4
+//                   (one 16-byte load later fetches 4 channels of a source pixel),
+//                   S[j][p] = scalar planes (2-layer tail channels, e^Z).
+//   euler_table     once per batch of frames: both Euler chains in registers, landing
+//                   coordinates of every (frame, direction, pixel), and per-(frame,
+//                   destination tile) entry counts.  Pixels with exactly zero motion never
+//                   move: they are not binned (clip_gather.cu adds their self-contribution).
+//   bin_scan        exclusive scan of the counts -> bin offsets.
+//   bin_fill        every moving (pixel, direction) is appended to the bins of the
+//                   destination tiles its 2x2 footprint touches.
+//
+// Reference: the Euler + splat-input part of forward_flow,
+// /root/reference/models/animating_softmax_splating.py:847-862,895 and
+// /root/reference/models/projection/euler_integration_manipulator.py:18-56.
+#include "clip_common.cuh"
+
+namespace slr {
+
+// ---------------------------------------------------------------------------
+// scene_prep: pre-weighted, channel-interleaved features
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, const float* __restrict__ zsub,
+                  const float* __restrict__ tail, int n_tail, float4* __restrict__ G4, float* __restrict__ S,
+                  int C, int64_t P)
+{
+    // planes have stride P + 1: pixel P is the all-zero pixel unused gather slots read
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p > P) return;
+    if (p == P) {
+        const int groups = (C + 3) >> 2;
+        if (blockIdx.y == 0) {
+            for (int g = 0; g < groups; ++g) G4[(int64_t)g * (P + 1) + P] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int j = 0; j <= n_tail; ++j) S[(int64_t)j * (P + 1) + P] = 0.0f;
+        }
+        return;
+    }
+    const float ez = expf(z[p] - (zsub ? *zsub : 0.0f));
+    const int groups = (C + 3) >> 2;
+    const int g0 = blockIdx.y * ((groups + gridDim.y - 1) / gridDim.y);
+    const int g1 = min(groups, g0 + (groups + (int)gridDim.y - 1) / (int)gridDim.y);
+    for (int g = g0; g < g1; ++g) {
+        float v[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = 4 * g + j;
+            v[j] = c < C ? feat[(int64_t)c * P + p] * ez : 0.0f;
+        }
+        G4[(int64_t)g * (P + 1) + p] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (blockIdx.y == 0) {
+        for (int j = 0; j < n_tail; ++j) S[(int64_t)j * (P + 1) + p] = tail[(int64_t)j * P + p];
+        S[(int64_t)n_tail * (P + 1) + p] = ez;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// euler_table: both chains for frames f = 0..n-1 of the batch.
+//   forward  steps of frame f: steps_f0 + f      (t - start)
+//   backward steps of frame f: steps_b0 - f      (end - t + 1)
+// Same arithmetic as euler_kernel (bit-identical displacements); the landing
+// coordinate stored is x + (dest - x), i.e. exactly what the reference splat
+// computes from the displacement (softsplat.py:169-170).
+// ---------------------------------------------------------------------------
+struct EulerState { float dx, dy; bool invalid; };
+
+__device__ __forceinline__ void euler_step(EulerState& s, const float* __restrict__ motion, float sign,
+                                           float cx, float cy, float xmax, float ymax, int W, int64_t P)
+{
+    const int64_t at = (int64_t)rintf(s.dy) * W + (int64_t)rintf(s.dx);
+    const float mx = __fmul_rn(sign, __ldg(motion + at));
+    const float my = __fmul_rn(sign, __ldg(motion + P + at));
+    s.dx = __fadd_rn(s.dx, mx);
+    s.dy = __fadd_rn(s.dy, my);
+    s.invalid = s.invalid || s.dx > xmax || s.dx < 0.0f || s.dy > ymax || s.dy < 0.0f;
+    if (s.invalid) { s.dx = cx; s.dy = cy; }
+}
+
+__global__ void __launch_bounds__(256)
+euler_table_kernel(const float* __restrict__ motion, int H, int W, int steps_f0, int steps_b0, int n,
+                   float* __restrict__ land, unsigned* __restrict__ counts, int tiles_x, int n_tiles)
+{
+    const int64_t P = (int64_t)H * W;
+    const int64_t p_raw = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : 0;
+    const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    const float cx = (float)x, cy = (float)y;
+    const float xmax = (float)(W - 1), ymax = (float)(H - 1);
+    const float sentinel = (float)(max(H, W) + 1);
+
+    // Static pixels (motion exactly 0 at the pixel: it never moves, in either direction) are
+    // not binned at all: the gather adds their self-contribution implicitly.  Their landing
+    // entry is a far-away marker, which the count and fill passes skip like any off-frame pixel.
+    const bool is_static = __ldg(motion + p) == 0.0f && __ldg(motion + P + p) == 0.0f;
+    if (__all_sync(0xffffffffu, is_static || !active)) {
+        if (active)
+            for (int i = 0; i < 4 * n; ++i) land[(int64_t)i * P + p] = kStaticLand;
+        return;
+    }
+
+    auto emit = [&](const EulerState& s, int f, int dir) {
+        const float ddx = s.invalid ? sentinel : __fsub_rn(s.dx, cx);
+        const float ddy = s.invalid ? sentinel : __fsub_rn(s.dy, cy);
+        const float ox = is_static ? kStaticLand : __fadd_rn(cx, ddx);
+        const float oy = is_static ? kStaticLand : __fadd_rn(cy, ddy);
+        int tiles[4];
+        if (active) {
+            float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
+            l[0] = ox;
+            l[P] = oy;
+            const Footprint fp = footprint_at(ox, oy, H, W);
+            touched_tiles(fp, ox, oy, H, W, tiles_x, tiles);
+        } else {
+            tiles[0] = tiles[1] = tiles[2] = tiles[3] = -1;
+        }
+        unsigned* cnt = counts + (int64_t)f * n_tiles;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (__any_sync(0xffffffffu, tiles[k] >= 0)) warp_reserve(cnt, tiles[k]);
+    };
+
+    // forward chain
+    EulerState s = {cx, cy, false};
+    if (steps_f0 == 0) emit(s, 0, 0);
+    const int last_f = steps_f0 + n - 1;
+    for (int k = 1; k <= last_f; ++k) {
+        euler_step(s, motion, 1.0f, cx, cy, xmax, ymax, W, P);
+        if (k >= steps_f0) emit(s, k - steps_f0, 0);
+    }
+    // backward chain (-motion); frame f needs steps_b0 - f steps
+    s = {cx, cy, false};
+    const int first_b = steps_b0 - (n - 1);          // >= 0, checked by the host
+    if (first_b == 0) emit(s, n - 1, 1);
+    for (int k = 1; k <= steps_b0; ++k) {
+        euler_step(s, motion, -1.0f, cx, cy, xmax, ymax, W, P);
+        if (k >= first_b) emit(s, steps_b0 - k, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bin_scan: per frame, exclusive scan of tile counts -> offsets; counts are zeroed
+// so that the fill pass can reuse them as cursors.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+bin_scan_kernel(unsigned* __restrict__ counts, unsigned* __restrict__ offsets, int n_tiles)
+{
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry_s;
+    unsigned* cnt = counts + (int64_t)blockIdx.x * n_tiles;
+    unsigned* off = offsets + (int64_t)blockIdx.x * (n_tiles + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned v = i < n_tiles ? cnt[i] : 0u;
+        unsigned incl = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sums[lane];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_sums[lane] = w;        // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned carry = carry_s;
+        const unsigned before = carry + (warp ? warp_sums[warp - 1] : 0u) + incl - v;
+        if (i < n_tiles) { off[i] = before; cnt[i] = 0u; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n_tiles] = carry_s;
+}
+
+// ---------------------------------------------------------------------------
+// bin_fill: append (pixel | direction, landing x, landing y) to every touched tile.
+// grid: (ceil(P/256), frames)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ offsets,
+                unsigned* __restrict__ cursors, float4* __restrict__ ent,
+                int H, int W, int tiles_x, int n_tiles, int64_t cap)
+{
+    const int64_t P = (int64_t)H * W;
+    const int f = blockIdx.y;
+    const int64_t p_raw = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : 0;
+    const unsigned* off = offsets + (int64_t)f * (n_tiles + 1);
+    unsigned* cur = cursors + (int64_t)f * n_tiles;
+    float4* e = ent + (int64_t)f * cap;
+    #pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
+        const float ox = __ldcs(l), oy = __ldcs(l + P);
+        int tiles[4];
+        if (active) {
+            const Footprint fp = footprint_at(ox, oy, H, W);
+            touched_tiles(fp, ox, oy, H, W, tiles_x, tiles);
+        } else {
+            tiles[0] = tiles[1] = tiles[2] = tiles[3] = -1;
+        }
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!__any_sync(0xffffffffu, tiles[k] >= 0)) continue;
+            const unsigned slot = warp_reserve(cur, tiles[k]);
+            if (tiles[k] >= 0) {
+                const int64_t at = (int64_t)off[tiles[k]] + slot;
+                e[at] = make_float4(__uint_as_float((unsigned)p | (dir ? kDirBit : 0u)), ox, oy, 0.0f);
+            }
+        }
+    }
+}
+
+}  // namespace slr
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace slr;
+using slr_host::carve;
+using slr_host::Workspace;
+
+extern "C" size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames)
+{
+    if (H <= 0 || W <= 0 || n_frames <= 0) return 0;
+    return carve(nullptr, H, W, n_frames).bytes;
+}
+
+extern "C" size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W)
+{
+    if (C <= 0 || n_tail < 0 || H <= 0 || W <= 0) return 0;
+    return sizeof(float) * (size_t)(((C + 3) / 4) * 4 + n_tail + 1) * (size_t)(H * W + 1);
+}
+
+extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zsub,
+                              const float* tail, int n_tail, void* scene,
+                              int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(feat && z && scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 15) == 0,
+                   "slr_scene_prep: bad arguments");
+    const int64_t P = H * W;
+    const int groups = (int)((C + 3) / 4);
+    float4* G4 = (float4*)scene;
+    float* S = (float*)scene + (int64_t)groups * 4 * (P + 1);
+    dim3 grid((unsigned)((P + 1 + 255) / 256), (unsigned)std::min(groups, 4), 1);
+    scene_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(feat, z, zsub, tail, n_tail, G4, S, (int)C, P);
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
+                             int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(motion && workspace && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   n_frames > 0 && n_frames <= kMaxFrames &&
+                   t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)workspace & 15) == 0,
+                   "slr_clip_plan: bad arguments");
+    const int64_t P = H * W;
+    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
+    const int n_tiles = tiles_x * tiles_y;
+    const Workspace ws = carve(workspace, H, W, n_frames);
+    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_plan: workspace too small (see slr_clip_workspace_bytes)");
+    cudaStream_t s = (cudaStream_t)stream_;
+
+    SLR_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
+    SLR_CUDA(cudaMemsetAsync(ws.flag_count, 0, sizeof(unsigned), s));
+    const unsigned pblocks = (unsigned)((P + 255) / 256);
+    euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
+                                               ws.land, ws.counts, tiles_x, n_tiles);
+    bin_scan_kernel<<<n_frames, 1024, 0, s>>>(ws.counts, ws.offsets, n_tiles);
+    bin_fill_kernel<<<dim3(pblocks, n_frames), 256, 0, s>>>(ws.land, ws.offsets, ws.counts, ws.ent,
+                                                            (int)H, (int)W, tiles_x, n_tiles, 8 * P);
+    return SLR_LAUNCH_STATUS();
+}
+
