@@ -19,7 +19,7 @@ constexpr float kStaticLand = -1.0e30f;     // landing marker of pixels that are
 // its weights for the top and the bottom pixel.
 constexpr int kPairsPerTile = TH / 2;
 constexpr int kCanon = 12;             // canonical slots (direction x source-row offset x east/west)
-constexpr int kListDepth = 48;         // slots per lane in the global lists; deeper = heavy tile
+constexpr int kListDepth = 96;         // slots per lane in the global lists; deeper = heavy tile
 
 struct FrameAlphas { float a[kMaxFrames]; };
 
@@ -86,6 +86,7 @@ struct Workspace {
     unsigned* tile_flag;  // [n][n_tiles]        1 = heavy tile
     unsigned* flag_list;  // [n * n_tiles]       compacted heavy tiles
     unsigned* flag_count; // [1]
+    float* heavy_sums;    // [n][3][P]           (tail..., norm) sums of heavy tiles
     size_t bytes;
 };
 
@@ -109,6 +110,7 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
+    w.heavy_sums = (float*)(p + o);  o += align_up(sizeof(float) * 3 * P * n);
     w.bytes = o;
     return w;
 }

@@ -20,8 +20,8 @@
 //                     corners on y+1) is loaded ONCE -- 12 loads instead of 16 per pixel pair
 //                     in regular flow.  Per channel group: <=12 independent LDG.128 in flight,
 //                     then the FMAs, then streaming stores.
-//   heavy_tile_kernel tiles with a pixel deeper than the lists hold (convergence zones of the
-//                     flow): per-pair accumulation in shared memory, cost linear in pairs.
+//   heavy_*_kernel    tiles with a lane deeper than the lists hold (convergence zones of the
+//                     flow): per-pair fp32 reductions at L2, cost linear in pairs.
 #include "clip_common.cuh"
 
 namespace slr {
@@ -49,6 +49,7 @@ struct GatherParams {
     unsigned* tile_flag;       // [frames][n_tiles]
     unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the heavy tiles
     unsigned* flag_count;      // [1], zeroed by slr_clip_plan
+    float* heavy_sums;         // [frames][3][P] (tail..., norm) sums of heavy tiles
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -355,107 +356,137 @@ rowgather_kernel(const GatherParams prm)
 }
 
 // ---------------------------------------------------------------------------
-// heavy_tile_kernel: destination tiles in which some lane's list is deeper than kListDepth
-// (convergence zones of the flow: the synthetic 60-step fields pile up to ~100 sources on
-// single pixels and 10x the average number of pairs on single tiles).  Work is assigned per
-// PAIR instead of per destination pixel: every thread walks bin entries and adds into a
-// per-tile accumulator in shared memory, kHeavyGroups channel groups per pass, so the cost
-// is linear in the number of pairs whatever their distribution.  A fixed grid walks the
-// compacted list of (heavy tile, chunk of channel groups) work items.
+// Heavy tiles: destination tiles in which some lane's list is deeper than kListDepth
+// (convergence zones of the flow: the synthetic 60-step fields pile up to ~150 sources on
+// single pixels and 10x the average number of pairs on single tiles).  They are done the way
+// the reference does everything: scatter with fp32 reductions at L2 (native RED.ADD.F32;
+// shared-memory float atomics are CAS loops and collapse under this contention).  Work is
+// per PAIR, so the cost is linear in the number of pairs whatever their distribution:
+//   heavy_prepare  zeroes the tile's outputs and its (tail..., norm) sums,
+//   heavy_scatter  one CTA per (heavy tile, chunk of channel groups): RED every pair in,
+//   heavy_finish   divides by the norm.
+// Fixed grids walk the compacted list of heavy tiles that expand_kernel produced.
 // ---------------------------------------------------------------------------
+struct HeavyTile {
+    int f, tx, ty;
+    int64_t pix;
+    bool inframe;
+};
+
+__device__ __forceinline__ HeavyTile heavy_tile(const GatherParams& prm, unsigned item, int tid)
+{
+    HeavyTile t;
+    t.f = (int)(item % (unsigned)prm.n_frames);
+    const int tile = (int)(item / (unsigned)prm.n_frames);
+    t.tx = tile % prm.tiles_x;
+    t.ty = tile / prm.tiles_x;
+    const int X = t.tx * TW + (tid & 31), Y = t.ty * TH + (tid >> 5);
+    t.inframe = X < prm.W && Y < prm.H;
+    t.pix = (int64_t)Y * prm.W + X;
+    return t;
+}
+
+__global__ void __launch_bounds__(TILE)
+heavy_prepare_kernel(const GatherParams prm, int n_sums)
+{
+    const unsigned n = *prm.flag_count;
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
+        const HeavyTile t = heavy_tile(prm, prm.flag_list[i], threadIdx.x);
+        if (!t.inframe) continue;
+        float* out = prm.out + (int64_t)t.f * prm.C * prm.P + t.pix;
+        for (int c = 0; c < prm.C; ++c) out[(int64_t)c * prm.P] = 0.0f;
+        float* sums = prm.heavy_sums + (int64_t)t.f * 3 * prm.P + t.pix;
+        for (int j = 0; j < n_sums; ++j) sums[(int64_t)j * prm.P] = 0.0f;
+    }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(TILE)
-heavy_tile_kernel(const GatherParams prm)
+heavy_scatter_kernel(const GatherParams prm)
 {
-    __shared__ float acc[kHeavyGroups * TILE * 4];      // [group in chunk][pixel][4 channels]
-    __shared__ float sn[(NT + 1) * TILE];
-
     const int tid = threadIdx.x;
     const int64_t P = prm.P;
     const int64_t sstride = P + 1;
     const size_t gstride = (size_t)(P + 1) * 16;
-    const unsigned n_chunks = (unsigned)((prm.groups + kHeavyGroups - 1) / kHeavyGroups);
+    // chunk 0 = the scalar planes (tail..., e^Z); chunk c > 0 = channel groups [(c-1)*kHeavyGroups, ...)
+    const unsigned n_chunks = 1u + (unsigned)((prm.groups + kHeavyGroups - 1) / kHeavyGroups);
     const unsigned n_work = *prm.flag_count * n_chunks;
     for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const unsigned item = prm.flag_list[wi / n_chunks];
-        const int g_lo = (int)(wi % n_chunks) * kHeavyGroups, g_hi = min(prm.groups, g_lo + kHeavyGroups);
-        const int f = (int)(item % (unsigned)prm.n_frames), tile = (int)(item / (unsigned)prm.n_frames);
-        const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
-        const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
-        const bool inframe = X < prm.W && Y < prm.H;
-        const int64_t pix = (int64_t)Y * prm.W + X;
-        const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
-        const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+        const int chunk = (int)(wi % n_chunks);
+        const HeavyTile t = heavy_tile(prm, item, tid);
+        const int tile = t.ty * prm.tiles_x + t.tx;
+        const float a_f = prm.alphas.a[t.f], a_b = 1.0f - a_f;
+        const unsigned* off = prm.offsets + (int64_t)t.f * (prm.n_tiles + 1);
         const unsigned beg = off[tile], end = off[tile + 1];
-        const float4* ent = prm.ent + (int64_t)f * prm.cap;
-        const bool self_static = inframe && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
-        const float w_self = a_f + a_b;
-        float* out = prm.out + (int64_t)f * prm.C * P + pix;
+        const float4* ent = prm.ent + (int64_t)t.f * prm.cap;
+        const bool self_static = t.inframe && __ldg(prm.motion + t.pix) == 0.0f && __ldg(prm.motion + P + t.pix) == 0.0f;
+        float* out = prm.out + (int64_t)t.f * prm.C * P;
+        float* sums = prm.heavy_sums + (int64_t)t.f * 3 * P;
+        const int g_lo = (chunk - 1) * kHeavyGroups, g_hi = min(prm.groups, g_lo + kHeavyGroups);
+        const char* Gg = prm.G + (size_t)max(g_lo, 0) * gstride;
 
-        // visits every (destination thread, source pixel, weight) pair of the bin that lands in this tile
-        auto for_each_pair = [&](auto&& fn) {
-            if (self_static) fn(tid, (unsigned)pix, w_self);
-            for (unsigned e = beg + tid; e < end; e += TILE) {
-                const float4 en = __ldg(ent + e);
-                const unsigned pd = __float_as_uint(en.x);
-                const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
-                const float a = (pd >> 31) ? a_b : a_f;
+        // one (destination pixel, source pixel, weight) pair
+        auto add_pair = [&](int64_t dpix, unsigned p, float w) {
+            if (chunk == 0) {
                 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-                    const float wa = fp.w[k] * a;
-                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
-                        fn(ly * TW + lx, pd & ~kDirBit, wa);
+                for (int j = 0; j <= NT; ++j)
+                    red_add(sums + (int64_t)j * P + dpix, __ldg(prm.S + (int64_t)j * sstride + p) * w);
+            } else {
+                float4 v[kHeavyGroups];
+                #pragma unroll
+                for (int gi = 0; gi < kHeavyGroups; ++gi)
+                    v[gi] = g_lo + gi < g_hi ? __ldg(px16(Gg + gi * gstride, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                #pragma unroll
+                for (int gi = 0; gi < kHeavyGroups; ++gi) {
+                    const float r[4] = {v[gi].x * w, v[gi].y * w, v[gi].z * w, v[gi].w * w};
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 4 * (g_lo + gi) + j;
+                        if (c < prm.C) red_add(out + (int64_t)c * P + dpix, r[j]);
+                    }
                 }
             }
         };
 
-        #pragma unroll
-        for (int t = 0; t <= NT; ++t) sn[t * TILE + tid] = 0.0f;
-        #pragma unroll
-        for (int j = 0; j < 4 * kHeavyGroups; ++j) acc[j * TILE + tid] = 0.0f;
-        __syncthreads();
-        for_each_pair([&](int d, unsigned p, float w) {
+        if (self_static) add_pair(t.pix, (unsigned)t.pix, a_f + a_b);
+        for (unsigned e = beg + tid; e < end; e += TILE) {
+            const float4 en = __ldg(ent + e);
+            const unsigned pd = __float_as_uint(en.x);
+            const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+            const float a = (pd >> 31) ? a_b : a_f;
             #pragma unroll
-            for (int t = 0; t <= NT; ++t) atomicAdd(&sn[t * TILE + d], __ldg(prm.S + (int64_t)t * sstride + p) * w);
-        });
-        // all channel groups of the chunk in one pass over the pairs: kHeavyGroups loads in flight
-        const char* Gg = prm.G + (size_t)g_lo * gstride;
-        for_each_pair([&](int d, unsigned p, float w) {
-            float4 v[kHeavyGroups];
-            #pragma unroll
-            for (int gi = 0; gi < kHeavyGroups; ++gi)
-                v[gi] = g_lo + gi < g_hi ? __ldg(px16(Gg + gi * gstride, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            #pragma unroll
-            for (int gi = 0; gi < kHeavyGroups; ++gi) {
-                float* a = acc + (gi * TILE + d) * 4;
-                atomicAdd(a + 0, v[gi].x * w);
-                atomicAdd(a + 1, v[gi].y * w);
-                atomicAdd(a + 2, v[gi].z * w);
-                atomicAdd(a + 3, v[gi].w * w);
-            }
-        });
-        __syncthreads();
-        const float nrm = sn[NT * TILE + tid];
-        const float inv = 1.0f / fmaxf(nrm, prm.eps);
-        if (inframe) {
-            for (int g = g_lo; g < g_hi; ++g) {
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = 4 * g + j;
-                    if (c < prm.C) __stcs(out + (int64_t)c * P, acc[((g - g_lo) * TILE + tid) * 4 + j] * inv);
-                }
-            }
-            if (g_lo == 0) {
-                if (prm.aux) {
-                    float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
-                    #pragma unroll
-                    for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sn[j * TILE + tid];
-                }
-                if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
+            for (int k = 0; k < 4; ++k) {
+                const int cx = fp.x0 + (k & 1), cy = fp.y0 + (k >> 1);
+                const int lx = cx - t.tx * TW, ly = cy - t.ty * TH;
+                const float wa = fp.w[k] * a;
+                if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                    add_pair((int64_t)cy * prm.W + cx, pd & ~kDirBit, wa);
             }
         }
-        __syncthreads();
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TILE)
+heavy_finish_kernel(const GatherParams prm)
+{
+    const unsigned n = *prm.flag_count;
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
+        const HeavyTile t = heavy_tile(prm, prm.flag_list[i], threadIdx.x);
+        if (!t.inframe) continue;
+        const int64_t P = prm.P;
+        const float* sums = prm.heavy_sums + (int64_t)t.f * 3 * P + t.pix;
+        const float nrm = __ldcg(sums + (int64_t)NT * P);
+        const float inv = 1.0f / fmaxf(nrm, prm.eps);
+        float* out = prm.out + (int64_t)t.f * prm.C * P + t.pix;
+        for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] = __ldcg(out + (int64_t)c * P) * inv;
+        if (prm.aux) {
+            float* a = prm.aux + (int64_t)t.f * (NT + 1) * P + t.pix;
+            #pragma unroll
+            for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = __ldcg(sums + (int64_t)j * P);
+        }
+        if (prm.mask) prm.mask[(int64_t)t.f * P + t.pix] = nrm > prm.eps ? 1.0f : 0.0f;
     }
 }
 
@@ -489,7 +520,7 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
-    prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count;
+    prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.n_frames = n_frames;
@@ -505,15 +536,19 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     const unsigned grid = (unsigned)n_tiles * (unsigned)n_frames;
     const unsigned heavy_grid = std::min<unsigned>(grid, 8u * (unsigned)slr_host::sm_count());
     expand_kernel<<<grid, TILE, 0, s>>>(prm);
+    heavy_prepare_kernel<<<heavy_grid, TILE, 0, s>>>(prm, n_tail + 1);
     if (n_tail == 0) {
         rowgather_kernel<0><<<grid, kCols, 0, s>>>(prm);
-        heavy_tile_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_scatter_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_finish_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
     } else if (n_tail == 1) {
         rowgather_kernel<1><<<grid, kCols, 0, s>>>(prm);
-        heavy_tile_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_scatter_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_finish_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
     } else {
         rowgather_kernel<2><<<grid, kCols, 0, s>>>(prm);
-        heavy_tile_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_scatter_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_finish_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
     }
     return SLR_LAUNCH_STATUS();
 }
