@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=60)
     ap.add_argument("--motion", default="A", choices=["A", "B", "C"])
     ap.add_argument("--batch", type=int, default=0, help="frames per gather launch (0 = library default)")
+    ap.add_argument("--no-pipeline", action="store_true", help="issue plan/expand/gather on one stream")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the CPU baseline sample")
@@ -261,10 +262,13 @@ def main():
         js = pkg.JointSplat(feat, Z, motion)
         if args.batch:
             js.batch = args.batch
+        js.pipeline = not args.no_pipeline
         return js
 
     n_mine = hi - lo
-    nbuf = min(n_mine, args.batch or pkg.JointSplat.batch)
+    # frames requested per frames() call: several batches, so that the library can overlap the
+    # index building of one batch with the gather of the previous one
+    nbuf = min(n_mine, 4 * (args.batch or pkg.JointSplat.batch))
     frame_buf = torch.empty(nbuf, C, H, W, dtype=torch.float32, device=dev) if algo == "gather" else None
 
     def synth_block(js, on_frames=None):

@@ -146,11 +146,18 @@ size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames);
  *   mask [n_frames, H, W] or NULL: norm > 1e-8                      (2layers...py:1039)
  * workspace: slr_clip_workspace_bytes(H, W, n_frames) bytes, 16-byte aligned.
  * slr_clip_frames = slr_clip_plan (Euler chains, landing table, destination-tile
- * bins; depends on the motion only) followed by slr_clip_gather (the gather
- * kernel) on the same workspace and the same motion (pixels whose motion is
- * exactly zero are not binned; the gather adds their self-contribution). */
+ * bins; depends on the motion only), slr_clip_expand (per-lane source lists of every
+ * destination row pair; depends on the motion and the blend weights) and
+ * slr_clip_gather (the gather itself) on the same workspace and the same motion
+ * (pixels whose motion is exactly zero are not binned; their self-contribution is
+ * added implicitly).  The three steps may be issued on different streams with the
+ * obvious dependencies, e.g. plan + expand of the next batch beside the gather of
+ * the current one (each batch needs its own workspace then). */
 int slr_clip_plan(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
                   int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream);
+int slr_clip_expand(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
+                    int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                    void* workspace, size_t workspace_bytes, slr_stream_t stream);
 int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
                     int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
                     float* out, float* aux, float* mask,

@@ -499,22 +499,21 @@ using namespace slr;
 using slr_host::carve;
 using slr_host::Workspace;
 
-extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
-                               int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
-                               float* out, float* aux, float* mask,
-                               const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+namespace {
+
+// Fills the kernel parameters shared by slr_clip_expand and slr_clip_gather.
+int make_params(GatherParams& prm, const void* scene, const float* motion, int64_t C, int n_tail,
+                int64_t H, int64_t W, int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                float* out, float* aux, float* mask, const void* workspace, size_t workspace_bytes)
 {
-    SLR_CHECK_ARGS(scene && motion && out && workspace && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
+    SLR_CHECK_ARGS(scene && motion && workspace && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
                    n_tail >= 0 && n_tail <= 2 && n_frames > 0 && n_frames <= kMaxFrames &&
                    t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)workspace & 15) == 0,
-                   "slr_clip_gather: bad arguments");
+                   "slr_clip_expand / slr_clip_gather: bad arguments");
     const int64_t P = H * W;
     const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
-    const int n_tiles = tiles_x * tiles_y;
     const Workspace ws = carve(const_cast<void*>(workspace), H, W, n_frames);
-    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_gather: workspace too small (see slr_clip_workspace_bytes)");
-
-    GatherParams prm;
+    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "workspace too small (see slr_clip_workspace_bytes)");
     const int groups = (int)((C + 3) / 4);
     prm.G = (const char*)scene;
     prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
@@ -523,7 +522,7 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
-    prm.tiles_x = tiles_x; prm.n_tiles = n_tiles; prm.n_frames = n_frames;
+    prm.tiles_x = tiles_x; prm.n_tiles = tiles_x * tiles_y; prm.n_frames = n_frames;
     prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
     for (int f = 0; f < n_frames; ++f) {
         // alpha = 1 - (t - start) / (end - start + 1) in fp32 (animating_softmax_splating.py:860),
@@ -532,10 +531,37 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
         a = fminf(fmaxf(a, alpha_lo), alpha_hi);
         prm.alphas.a[f] = a;
     }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
+                               int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                               void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    GatherParams prm;
+    const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                               nullptr, nullptr, nullptr, workspace, workspace_bytes);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
+    expand_kernel<<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
+                               int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                               float* out, float* aux, float* mask,
+                               const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(out, "slr_clip_gather: bad arguments");
+    GatherParams prm;
+    const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                               out, aux, mask, workspace, workspace_bytes);
+    if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream_;
-    const unsigned grid = (unsigned)n_tiles * (unsigned)n_frames;
+    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
     const unsigned heavy_grid = std::min<unsigned>(grid, 8u * (unsigned)slr_host::sm_count());
-    expand_kernel<<<grid, TILE, 0, s>>>(prm);
     heavy_prepare_kernel<<<heavy_grid, TILE, 0, s>>>(prm, n_tail + 1);
     if (n_tail == 0) {
         rowgather_kernel<0><<<grid, kCols, 0, s>>>(prm);
@@ -560,6 +586,9 @@ extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C
                                void* workspace, size_t workspace_bytes, slr_stream_t stream_)
 {
     int rc = slr_clip_plan(motion, H, W, start, end, t0, n_frames, workspace, workspace_bytes, stream_);
+    if (rc) return rc;
+    rc = slr_clip_expand(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                         workspace, workspace_bytes, stream_);
     if (rc) return rc;
     return slr_clip_gather(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                            out, aux, mask, workspace, workspace_bytes, stream_);

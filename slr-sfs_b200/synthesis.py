@@ -60,7 +60,9 @@ class JointSplat:
 
     #: frames per slr_clip_frames launch (bigger batches amortise the Euler chains,
     #: smaller ones keep the landing table and the bins inside the 126 MB L2)
-    batch = 12
+    batch = 8
+    #: overlap plan + expand of the next batch with the gather of the current one (two streams)
+    pipeline = True
 
     def __init__(self, features, Z, motion, z_mode="max", tail=None):
         assert features.dim() == 4 and features.shape[0] == 1
@@ -81,7 +83,8 @@ class JointSplat:
             else:
                 self.zsub = None
         self._scene = None
-        self._workspace = None
+        self._workspaces = {}
+        self._side = None
 
     # -- gather pipeline: scene_prep once, then bin + gather per batch of frames
     def _prepare(self):
@@ -94,15 +97,20 @@ class JointSplat:
                           _lib.current_stream(self.device))
         return self._scene
 
-    def _scratch(self, n):
+    def _scratch(self, n, slot=0):
         need = _lib.load().slr_clip_workspace_bytes(self.H, self.W, n)
-        if self._workspace is None or self._workspace.numel() * 4 < need:
-            self._workspace = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
-        return self._workspace, self._workspace.numel() * 4
+        ws = self._workspaces.get(slot)
+        if ws is None or ws.numel() * 4 < need:
+            ws = self._workspaces[slot] = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+        return ws, ws.numel() * 4
 
     def frames(self, start, end, t0, n, out=None, want_aux=False, want_mask=False, alpha_clamp=(0.0, 1.0)):
         """Frames t0..t0+n-1 of the clip [start, end]: gen_fs [n,C,H,W]
-        (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W])."""
+        (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W]).
+
+        Work is issued in batches of ``self.batch`` frames.  With ``self.pipeline`` the
+        latency-bound index building of batch i+1 (slr_clip_plan + slr_clip_expand, side
+        stream, second workspace) runs beside the bandwidth-bound gather of batch i."""
         scene = self._prepare()
         H, W, C = self.H, self.W, self.C
         if out is None:
@@ -110,17 +118,42 @@ class JointSplat:
         assert out.shape == (n, C, H, W) and out.is_contiguous() and out.device == self.device
         aux = torch.empty(n, self.n_tail + 1, H, W, dtype=torch.float32, device=self.device) if want_aux else None
         mask = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_mask else None
+        batches = [(b0, min(self.batch, n - b0)) for b0 in range(0, n, self.batch)]
         with torch.cuda.device(self.device):
-            s = _lib.current_stream(self.device)
-            for b0 in range(0, n, self.batch):
-                nb = min(self.batch, n - b0)
-                ws, ws_bytes = self._scratch(nb)
-                _lib.call("slr_clip_plan", _lib.ptr(self.motion), H, W, start, end, t0 + b0, nb,
-                          _lib.ptr(ws), ws_bytes, s)
-                _lib.call("slr_clip_gather", _lib.ptr(scene), _lib.ptr(self.motion), C, self.n_tail, H, W,
-                          start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1], _lib.ptr(out[b0:]),
+            main = torch.cuda.current_stream(self.device)
+            two_streams = self.pipeline and len(batches) > 1
+            if two_streams:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.device)
+                side = self._side
+                side.wait_stream(main)            # scene buffer, motion and anything the caller queued
+            else:
+                side = main
+            free = {}                             # workspace slot -> event: its last gather has finished
+            for i, (b0, nb) in enumerate(batches):
+                slot = i % 2 if two_streams else 0
+                ws, ws_bytes = self._scratch(self.batch if two_streams else nb, slot)
+                args = (C, self.n_tail, H, W, start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1])
+                with torch.cuda.stream(side):
+                    if slot in free:
+                        side.wait_event(free[slot])
+                    s = _lib.current_stream(self.device)
+                    _lib.call("slr_clip_plan", _lib.ptr(self.motion), H, W, start, end, t0 + b0, nb,
+                              _lib.ptr(ws), ws_bytes, s)
+                    _lib.call("slr_clip_expand", _lib.ptr(scene), _lib.ptr(self.motion), *args,
+                              _lib.ptr(ws), ws_bytes, s)
+                    if two_streams:
+                        ready = torch.cuda.Event()
+                        ready.record(side)
+                if two_streams:
+                    main.wait_event(ready)
+                _lib.call("slr_clip_gather", _lib.ptr(scene), _lib.ptr(self.motion), *args, _lib.ptr(out[b0:]),
                           None if aux is None else _lib.ptr(aux[b0:]),
-                          None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes, s)
+                          None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes,
+                          _lib.current_stream(self.device))
+                if two_streams:
+                    free[slot] = torch.cuda.Event()
+                    free[slot].record(main)
         res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
         return res if len(res) > 1 else out
 
