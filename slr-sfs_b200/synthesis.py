@@ -60,7 +60,7 @@ class JointSplat:
 
     #: frames per slr_clip_frames launch (bigger batches amortise the Euler chains,
     #: smaller ones keep the landing table and the bins inside the 126 MB L2)
-    batch = 8
+    batch = 12
     #: overlap plan + expand of the next batch with the gather of the current one (two streams)
     pipeline = True
 
