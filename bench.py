@@ -46,6 +46,21 @@ def parse():
     return ap.parse_args()
 
 
+def profiled_traffic(name, frames_per_call):
+    """DRAM bytes (read + write) per call of entry point `name`, from the committed ncu --set full
+    capture (profiles/*/traffic.json holds bytes per frame of its dominant kernel); None if absent."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "traffic.json")), reverse=True):
+        try:
+            with open(path) as fh:
+                entry = json.load(fh).get(name)
+            if entry:
+                return entry["dram_bytes_per_frame"] * frames_per_call
+        except Exception:
+            continue
+    return None
+
+
 def measured_peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -402,7 +417,8 @@ def main():
             achieved = alg_bytes / avg_s / 1e9
             share = tot_ms / (ms if world == 1 else ms)
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": profiled_traffic(name, frames_per_call),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_s * 1e6,
                     "share_of_step": share,
                     "all_kernels_ms_per_frame": {k: v[0] / max(1, (hi - lo) * world * args.steps) for k, v in ktimes.items()}}

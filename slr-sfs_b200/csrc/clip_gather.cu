@@ -401,7 +401,7 @@ heavy_prepare_kernel(const GatherParams prm, int n_sums)
 }
 
 template <int NT>
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(TILE, 4)
 heavy_scatter_kernel(const GatherParams prm)
 {
     const int tid = threadIdx.x;

@@ -230,3 +230,19 @@ def test_static_pixels_are_implicit_self_contributions(pkg):
         want = oracle.joint_splat_baseline(feat, Z, m, (0, t, N - 1))
         assert rel_err(js.frame((0, t, N - 1)).cpu().numpy(), want) <= TOL
         assert rel_err(js.frame_scatter((0, t, N - 1)).cpu().numpy(), want) <= TOL
+
+
+def test_pipelined_and_single_stream_frames_agree(pkg):
+    from slr_sfs_b200 import workloads
+    H, W, C, N = 72, 100, 8, 14
+    feat, Z, m = workloads.scene(H, W, C, "A", seed=8)
+    js = pkg.JointSplat(feat.cuda(), Z.cuda(), m.cuda())
+    js.batch = 3
+    js.pipeline = True
+    a = js.frames(0, N - 1, 0, N)
+    js.pipeline = False
+    b = js.frames(0, N - 1, 0, N)
+    torch.cuda.synchronize()
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+    want = oracle.joint_splat_baseline(feat.numpy(), Z.numpy(), m.numpy(), (0, 9, N - 1))
+    assert rel_err(a[9:10].cpu().numpy(), want) <= TOL
