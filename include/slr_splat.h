@@ -147,8 +147,10 @@ size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames);
  * workspace: slr_clip_workspace_bytes(H, W, n_frames) bytes, 16-byte aligned.
  * slr_clip_frames = slr_clip_plan (Euler chains, landing table, destination-tile
  * bins; depends on the motion only), slr_clip_expand (per-lane source lists of every
- * destination row pair; depends on the motion and the blend weights) and
- * slr_clip_gather (the gather itself) on the same workspace and the same motion
+ * destination row pair; depends on the motion and the blend weights),
+ * slr_clip_gather (the gather itself: every tile whose lists fit) and slr_clip_heavy
+ * (the few tiles in convergence zones of the flow whose lists do not fit, by fp32
+ * reductions at L2; touches only those tiles) on the same workspace and the same motion
  * (pixels whose motion is exactly zero are not binned; their self-contribution is
  * added implicitly).  The three steps may be issued on different streams with the
  * obvious dependencies, e.g. plan + expand of the next batch beside the gather of
@@ -162,6 +164,10 @@ int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tai
                     int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
                     float* out, float* aux, float* mask,
                     const void* workspace, size_t workspace_bytes, slr_stream_t stream);
+int slr_clip_heavy(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
+                   int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                   float* out, float* aux, float* mask,
+                   const void* workspace, size_t workspace_bytes, slr_stream_t stream);
 int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tail,
                     int64_t H, int64_t W, int start, int end, int t0, int n_frames,
                     float alpha_lo, float alpha_hi, float* out, float* aux, float* mask,

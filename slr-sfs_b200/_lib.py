@@ -37,6 +37,8 @@ SIGNATURES = {
                         _f32p, ctypes.c_size_t, _strm],
     "slr_clip_gather": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
                         _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
+    "slr_clip_heavy": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
+                       _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_frames": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
                         _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
 }
@@ -98,7 +100,7 @@ KERNELS_PER_CALL = {
     "slr_softsplat_sum_fwd": 1, "slr_softsplat_grad_input": 1, "slr_softsplat_grad_flow": 1,
     "slr_maxsplat_fwd": 2, "slr_maxwarpnorm": 3, "slr_euler": 1, "slr_reduce_max": 2,
     "slr_joint_scatter": 1, "slr_normalize": 1, "slr_scene_prep": 1, "slr_clip_frames": 8,
-    "slr_clip_plan": 3, "slr_clip_expand": 1, "slr_clip_gather": 4,
+    "slr_clip_plan": 3, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 3,
 }
 _launches = 0
 _timing = None          # None, or list of (name, start_event, end_event)

@@ -561,18 +561,33 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream_;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
+    if (n_tail == 0) rowgather_kernel<0><<<grid, kCols, 0, s>>>(prm);
+    else if (n_tail == 1) rowgather_kernel<1><<<grid, kCols, 0, s>>>(prm);
+    else rowgather_kernel<2><<<grid, kCols, 0, s>>>(prm);
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_clip_heavy(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
+                              int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
+                              float* out, float* aux, float* mask,
+                              const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(out, "slr_clip_heavy: bad arguments");
+    GatherParams prm;
+    const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                               out, aux, mask, workspace, workspace_bytes);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream_;
+    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
     const unsigned heavy_grid = std::min<unsigned>(grid, 8u * (unsigned)slr_host::sm_count());
     heavy_prepare_kernel<<<heavy_grid, TILE, 0, s>>>(prm, n_tail + 1);
     if (n_tail == 0) {
-        rowgather_kernel<0><<<grid, kCols, 0, s>>>(prm);
         heavy_scatter_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
         heavy_finish_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
     } else if (n_tail == 1) {
-        rowgather_kernel<1><<<grid, kCols, 0, s>>>(prm);
         heavy_scatter_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
         heavy_finish_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
     } else {
-        rowgather_kernel<2><<<grid, kCols, 0, s>>>(prm);
         heavy_scatter_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
         heavy_finish_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
     }
@@ -590,6 +605,9 @@ extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C
     rc = slr_clip_expand(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                          workspace, workspace_bytes, stream_);
     if (rc) return rc;
-    return slr_clip_gather(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
-                           out, aux, mask, workspace, workspace_bytes, stream_);
+    rc = slr_clip_gather(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                         out, aux, mask, workspace, workspace_bytes, stream_);
+    if (rc) return rc;
+    return slr_clip_heavy(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
+                          out, aux, mask, workspace, workspace_bytes, stream_);
 }

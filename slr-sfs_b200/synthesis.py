@@ -147,10 +147,11 @@ class JointSplat:
                         ready.record(side)
                 if two_streams:
                     main.wait_event(ready)
-                _lib.call("slr_clip_gather", _lib.ptr(scene), _lib.ptr(self.motion), *args, _lib.ptr(out[b0:]),
-                          None if aux is None else _lib.ptr(aux[b0:]),
-                          None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes,
-                          _lib.current_stream(self.device))
+                for entry in ("slr_clip_gather", "slr_clip_heavy"):
+                    _lib.call(entry, _lib.ptr(scene), _lib.ptr(self.motion), *args, _lib.ptr(out[b0:]),
+                              None if aux is None else _lib.ptr(aux[b0:]),
+                              None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes,
+                              _lib.current_stream(self.device))
                 if two_streams:
                     free[slot] = torch.cuda.Event()
                     free[slot].record(main)
