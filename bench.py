@@ -410,7 +410,10 @@ def main():
         # dominant kernel: the one with the largest total time in the timed region
         roof = None
         if ktimes:
-            name, (tot_ms, calls) = max(ktimes.items(), key=lambda kv: kv[1][0])
+            # entry points issued on the side stream are bracketed by events that include their
+            # waits; the dominant kernel is looked for among the ones with algorithmic traffic
+            cand = {k: v for k, v in ktimes.items() if _lib.algorithmic_bytes(k, C, P) > 0} or ktimes
+            name, (tot_ms, calls) = max(cand.items(), key=lambda kv: kv[1][0])
             frames_per_call = (hi - lo) * world * args.steps / calls if name.startswith("slr_clip") else 1
             alg_bytes = _lib.algorithmic_bytes(name, C, P) * frames_per_call
             avg_s = tot_ms / 1000.0 / calls
