@@ -129,17 +129,14 @@ class JointSplat:
                 side.wait_stream(main)            # scene buffer, motion and anything the caller queued
             else:
                 side = main
-            free = {}                             # workspace slot -> events: its last gather / heavy pass finished
-            heavy_done = []
+            free = {}                             # workspace slot -> event: its last gather has finished
             for i, (b0, nb) in enumerate(batches):
                 slot = i % 2 if two_streams else 0
                 ws, ws_bytes = self._scratch(self.batch if two_streams else nb, slot)
                 args = (C, self.n_tail, H, W, start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1])
-                outs = (_lib.ptr(out[b0:]), None if aux is None else _lib.ptr(aux[b0:]),
-                        None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes)
                 with torch.cuda.stream(side):
-                    for ev in free.get(slot, ()):
-                        side.wait_event(ev)
+                    if slot in free:
+                        side.wait_event(free[slot])
                     s = _lib.current_stream(self.device)
                     _lib.call("slr_clip_plan", _lib.ptr(self.motion), H, W, start, end, t0 + b0, nb,
                               _lib.ptr(ws), ws_bytes, s)
@@ -148,24 +145,16 @@ class JointSplat:
                     if two_streams:
                         ready = torch.cuda.Event()
                         ready.record(side)
-                        # the heavy tiles are disjoint from the ones the gather writes: beside it
-                        _lib.call("slr_clip_heavy", _lib.ptr(scene), _lib.ptr(self.motion), *args, *outs, s)
-                        done = torch.cuda.Event()
-                        done.record(side)
-                        heavy_done.append(done)
                 if two_streams:
                     main.wait_event(ready)
-                _lib.call("slr_clip_gather", _lib.ptr(scene), _lib.ptr(self.motion), *args, *outs,
-                          _lib.current_stream(self.device))
-                if two_streams:
-                    gathered = torch.cuda.Event()
-                    gathered.record(main)
-                    free[slot] = (gathered, heavy_done[-1])
-                else:
-                    _lib.call("slr_clip_heavy", _lib.ptr(scene), _lib.ptr(self.motion), *args, *outs,
+                for entry in ("slr_clip_gather", "slr_clip_heavy"):
+                    _lib.call(entry, _lib.ptr(scene), _lib.ptr(self.motion), *args, _lib.ptr(out[b0:]),
+                              None if aux is None else _lib.ptr(aux[b0:]),
+                              None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes,
                               _lib.current_stream(self.device))
-            for ev in heavy_done:
-                main.wait_event(ev)
+                if two_streams:
+                    free[slot] = torch.cuda.Event()
+                    free[slot].record(main)
         res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
         return res if len(res) > 1 else out
 
