@@ -75,3 +75,36 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), fn
                 assert "liboracle" not in text and "libref_softsplat" not in text, fn
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/softsplat.py"), reason="reference tree not mounted")
+def test_reference_models_import_our_operators_unchanged():
+    """Drop-in check at import level: with install_as_reference_modules() the reference's own
+    model files (unmodified, /root/reference) bind to this package's operators."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, warnings
+from unittest import mock
+warnings.simplefilter("ignore")
+sys.path.insert(0, %r)
+sys.path.insert(1, "/root/reference")
+for m in ["cv2", "av", "lz4framed", "lpips", "tensorboardX", "matplotlib", "matplotlib.pyplot"]:
+    try:
+        __import__(m)
+    except Exception:
+        sys.modules[m] = mock.MagicMock()
+import slr_sfs_b200
+slr_sfs_b200.install_as_reference_modules()
+import importlib
+base = importlib.import_module("models.animating_softmax_splating")
+two = importlib.import_module("models.animating_softmax_splating_2layers_alpha_seperate")
+assert "cupy" not in sys.modules
+assert base.softsplat is slr_sfs_b200.softsplat and two.softsplat is slr_sfs_b200.softsplat
+assert base.euler_integration is slr_sfs_b200.euler_integration
+assert base.EulerIntegration is slr_sfs_b200.EulerIntegration
+assert isinstance(base.softsplat.ModuleSoftsplat("summation"), slr_sfs_b200.ModuleSoftsplat)
+print("ok")
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
