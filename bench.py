@@ -258,6 +258,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     H, W, C, N = args.height, args.width, args.channels, args.frames
@@ -273,8 +274,9 @@ def main():
     own = tuple(t.pin_memory() for t in scenes_host[rank])
     lo, hi = frame_block(N, rank, world)
 
-    def make_joint(feat, Z, motion):
-        js = pkg.JointSplat(feat, Z, motion)
+    def make_joint(feat, Z, motion, resident=False):
+        # resident inputs are complete: the library may start on them while earlier frames still run
+        js = pkg.JointSplat(feat, Z, motion, inputs_event=False if resident else None)
         if args.batch:
             js.batch = args.batch
         js.pipeline = not args.no_pipeline
@@ -308,7 +310,7 @@ def main():
 
     def step_resident(record=None):
         for sc in resident:
-            out = synth_block(make_joint(*sc))
+            out = synth_block(make_joint(*sc, resident=True))
         return out
 
     def barrier():

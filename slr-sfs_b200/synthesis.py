@@ -64,7 +64,15 @@ class JointSplat:
     #: overlap plan + expand of the next batch with the gather of the current one (two streams)
     pipeline = True
 
-    def __init__(self, features, Z, motion, z_mode="max", tail=None):
+    # per device: the side stream, the two ping-pong workspaces and the events that say when a
+    # workspace may be overwritten.  Shared by all JointSplat objects so that the index building
+    # of the next scene overlaps the gather of the previous one.
+    _shared = {}
+
+    def __init__(self, features, Z, motion, z_mode="max", tail=None, inputs_event=None):
+        """``inputs_event``: a CUDA event after which the inputs are valid.  None (default): one is
+        recorded now on the current stream (whatever produced the inputs was queued there);
+        False: the inputs are already complete (lets the side stream start at once)."""
         assert features.dim() == 4 and features.shape[0] == 1
         self.feat = _req(features.detach(), "features")
         self.C, self.H, self.W = features.shape[1:]
@@ -73,45 +81,86 @@ class JointSplat:
         self.tail = None if tail is None else _req(tail.detach(), "tail")
         self.n_tail = 0 if tail is None else tail.shape[1]
         assert z_mode in ("max", "v1")
+        self.z_mode = z_mode
         self.device = features.device
-        with torch.cuda.device(self.device):
-            self.stream = None
-            if z_mode == "max":
-                self.zsub = torch.empty(1, dtype=torch.float32, device=self.device)
-                _lib.call("slr_reduce_max", _lib.ptr(self.Z), self.Z.numel(), _lib.ptr(self.zsub),
-                          _lib.current_stream(self.device))
-            else:
-                self.zsub = None
+        if inputs_event is None:
+            with torch.cuda.device(self.device):
+                inputs_event = torch.cuda.Event()
+                inputs_event.record(torch.cuda.current_stream(self.device))
+        self._inputs_ready = inputs_event or None
+        self._zsub = None
         self._scene = None
-        self._workspaces = {}
-        self._side = None
+        self._prepared = None          # event: zsub and the scene buffer are built
 
-    # -- gather pipeline: scene_prep once, then bin + gather per batch of frames
+    def _wait_inputs(self, stream):
+        if self._inputs_ready is not None:
+            stream.wait_event(self._inputs_ready)
+
     def _prepare(self):
-        if self._scene is None:
+        """Z.max() and the pre-weighted, channel-interleaved scene buffer: built once, on the
+        current stream; users on other streams are ordered behind the `_prepared` event.
+        Buffers are allocated by the caller's stream and marked as used by this one."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._prepared is None:
+            self._wait_inputs(cur)
+            for t in (self._zsub, self._scene):
+                if t is not None:
+                    t.record_stream(cur)
+            with torch.cuda.device(self.device):
+                s = _lib.current_stream(self.device)
+                if self._zsub is not None:
+                    _lib.call("slr_reduce_max", _lib.ptr(self.Z), self.Z.numel(), _lib.ptr(self._zsub), s)
+                if self._scene is not None:
+                    _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self._zsub),
+                              _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W, s)
+            self._prepared = torch.cuda.Event()
+            self._prepared.record(cur)
+        else:
+            cur.wait_event(self._prepared)
+
+    def _allocate(self, scene):
+        """Allocate (on the current stream's pool) what _prepare fills."""
+        if self.z_mode == "max" and self._zsub is None:
+            self._zsub = torch.empty(1, dtype=torch.float32, device=self.device)
+        if scene and self._scene is None:
             n = _lib.load().slr_scene_bytes(self.C, self.n_tail, self.H, self.W)
             self._scene = torch.empty(n // 4, dtype=torch.float32, device=self.device)
-            with torch.cuda.device(self.device):
-                _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self.zsub),
-                          _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W,
-                          _lib.current_stream(self.device))
-        return self._scene
+            self._prepared = None      # (re)build everything with the scene buffer
 
-    def _scratch(self, n, slot=0):
+    @property
+    def zsub(self):
+        """Device scalar Z.max() (or None for z_mode 'v1'), valid on the current stream."""
+        with torch.cuda.device(self.device):
+            self._allocate(scene=False)
+            self._prepare()
+        return self._zsub
+
+    def _shared_state(self):
+        st = JointSplat._shared.get(self.device)
+        if st is None:
+            st = JointSplat._shared[self.device] = {"side": torch.cuda.Stream(device=self.device),
+                                                    "ws": {}, "free": {}, "turn": 0}
+        return st
+
+    def _scratch(self, st, n, slot, side):
         need = _lib.load().slr_clip_workspace_bytes(self.H, self.W, n)
-        ws = self._workspaces.get(slot)
+        ws = st["ws"].get(slot)
         if ws is None or ws.numel() * 4 < need:
-            ws = self._workspaces[slot] = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+            # allocated by the current (main) stream and marked as used by the side stream, so the
+            # caching allocator does not hand the old block out while queued work still uses it
+            ws = st["ws"][slot] = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+            ws.record_stream(side)
         return ws, ws.numel() * 4
 
     def frames(self, start, end, t0, n, out=None, want_aux=False, want_mask=False, alpha_clamp=(0.0, 1.0)):
         """Frames t0..t0+n-1 of the clip [start, end]: gen_fs [n,C,H,W]
-        (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W]).
+        (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W]).  Asynchronous like any
+        torch op: results are ordered on the current stream.
 
         Work is issued in batches of ``self.batch`` frames.  With ``self.pipeline`` the
-        latency-bound index building of batch i+1 (slr_clip_plan + slr_clip_expand, side
-        stream, second workspace) runs beside the bandwidth-bound gather of batch i."""
-        scene = self._prepare()
+        latency-bound part (scene prep, slr_clip_plan, slr_clip_expand) goes to a side stream
+        with its own workspace and runs beside the bandwidth-bound gather of the previous
+        batch -- of this call or of an earlier one (the previous scene)."""
         H, W, C = self.H, self.W, self.C
         if out is None:
             out = torch.empty(n, C, H, W, dtype=torch.float32, device=self.device)
@@ -121,22 +170,19 @@ class JointSplat:
         batches = [(b0, min(self.batch, n - b0)) for b0 in range(0, n, self.batch)]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
-            two_streams = self.pipeline and len(batches) > 1
-            if two_streams:
-                if self._side is None:
-                    self._side = torch.cuda.Stream(device=self.device)
-                side = self._side
-                side.wait_stream(main)            # scene buffer, motion and anything the caller queued
-            else:
-                side = main
-            free = {}                             # workspace slot -> event: its last gather has finished
-            for i, (b0, nb) in enumerate(batches):
-                slot = i % 2 if two_streams else 0
-                ws, ws_bytes = self._scratch(self.batch if two_streams else nb, slot)
+            st = self._shared_state()
+            two_streams = bool(self.pipeline)
+            side = st["side"] if two_streams else main
+            self._allocate(scene=True)
+            scene = self._scene
+            for (b0, nb) in batches:
+                slot = st["turn"] = st["turn"] ^ 1
                 args = (C, self.n_tail, H, W, start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1])
+                ws, ws_bytes = self._scratch(st, self.batch, slot, side)
                 with torch.cuda.stream(side):
-                    if slot in free:
-                        side.wait_event(free[slot])
+                    for ev in st["free"].get(slot, ()):
+                        side.wait_event(ev)
+                    self._prepare()
                     s = _lib.current_stream(self.device)
                     _lib.call("slr_clip_plan", _lib.ptr(self.motion), H, W, start, end, t0 + b0, nb,
                               _lib.ptr(ws), ws_bytes, s)
@@ -152,9 +198,9 @@ class JointSplat:
                               None if aux is None else _lib.ptr(aux[b0:]),
                               None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes,
                               _lib.current_stream(self.device))
-                if two_streams:
-                    free[slot] = torch.cuda.Event()
-                    free[slot].record(main)
+                done = torch.cuda.Event()
+                done.record(main)
+                st["free"][slot] = (done,)
         res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
         return res if len(res) > 1 else out
 
