@@ -19,7 +19,10 @@ constexpr float kStaticLand = -1.0e30f;     // landing marker of pixels that are
 // its weights for the top and the bottom pixel.
 constexpr int kPairsPerTile = TH / 2;
 constexpr int kCanon = 12;             // canonical slots (direction x source-row offset x east/west)
-constexpr int kListDepth = 96;         // slots per lane in the global lists; deeper = heavy tile
+#ifndef SLR_LIST_DEPTH
+#define SLR_LIST_DEPTH 96
+#endif
+constexpr int kListDepth = SLR_LIST_DEPTH;   // slots per lane in the global lists; deeper = heavy tile
 
 struct FrameAlphas { float a[kMaxFrames]; };
 

@@ -35,7 +35,10 @@ namespace slr {
 constexpr int kRegSlots = 16;          // list slots a lane keeps in registers; deeper ones are re-read per group
 constexpr int kSmemSlots = 16;         // list slots expand_kernel stages in shared memory (>= kCanon)
 constexpr int kCols = TW * kPairsPerTile;   // 128 lanes (columns of row pairs) per tile
-constexpr int kHeavyGroups = 4;        // channel groups per work item of heavy_tile_kernel
+#ifndef SLR_HEAVY_GROUPS
+#define SLR_HEAVY_GROUPS 4
+#endif
+constexpr int kHeavyGroups = SLR_HEAVY_GROUPS;   // channel groups per work item of heavy_scatter_kernel
 constexpr unsigned kEmpty = 0xffffffffu;
 
 struct GatherParams {
