@@ -246,3 +246,34 @@ def test_pipelined_and_single_stream_frames_agree(pkg):
     assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
     want = oracle.joint_splat_baseline(feat.numpy(), Z.numpy(), m.numpy(), (0, 9, N - 1))
     assert rel_err(a[9:10].cpu().numpy(), want) <= TOL
+
+
+def test_c_abi_clip_frames_single_call(pkg):
+    """slr_clip_frames (plan + expand + gather + heavy in one C call) against the oracle."""
+    from slr_sfs_b200 import _lib, workloads
+    H, W, C, N = 56, 80, 12, 10
+    feat, Z, m = workloads.scene(H, W, C, "A", seed=12)
+    feat, Z, m = feat.cuda(), Z.cuda(), m.cuda()
+    lib = _lib.load()
+    s = _lib.current_stream(feat.device)
+    zmax = torch.empty(1, device="cuda")
+    scene = torch.empty(lib.slr_scene_bytes(C, 0, H, W) // 4, device="cuda")
+    ws_bytes = lib.slr_clip_workspace_bytes(H, W, 4)
+    ws = torch.empty((ws_bytes + 3) // 4, device="cuda")
+    out = torch.empty(4, C, H, W, device="cuda")
+    mask = torch.empty(4, 1, H, W, device="cuda")
+    _lib.call("slr_reduce_max", _lib.ptr(Z), Z.numel(), _lib.ptr(zmax), s)
+    _lib.call("slr_scene_prep", _lib.ptr(feat), _lib.ptr(Z), _lib.ptr(zmax), None, 0, _lib.ptr(scene), C, H, W, s)
+    _lib.call("slr_clip_frames", _lib.ptr(scene), _lib.ptr(m), C, 0, H, W, 0, N - 1, 3, 4, 0.0, 1.0,
+              _lib.ptr(out), None, _lib.ptr(mask), _lib.ptr(ws), ws_bytes, s)
+    torch.cuda.synchronize()
+    for i, t in enumerate(range(3, 7)):
+        want = oracle.joint_splat_baseline(feat.cpu().numpy(), Z.cpu().numpy(), m.cpu().numpy(), (0, t, N - 1))
+        got = out[i:i + 1].cpu().numpy()
+        assert rel_err(got, want) <= TOL
+        # the mask is exactly the decoder's hole test (networks/architectures.py:369) on the norm
+        covered = (np.abs(want).sum(1, keepdims=True) != 0)
+        assert np.mean(mask[i:i + 1].cpu().numpy().astype(bool) != covered) < 1e-3
+    with pytest.raises(_lib.SlrError):          # workspace too small is an argument error, not a crash
+        _lib.call("slr_clip_frames", _lib.ptr(scene), _lib.ptr(m), C, 0, H, W, 0, N - 1, 3, 4, 0.0, 1.0,
+                  _lib.ptr(out), None, None, _lib.ptr(ws), 1024, s)

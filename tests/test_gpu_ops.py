@@ -175,3 +175,14 @@ def test_euler_non_square_60_steps(pkg):
         d, v = pkg.euler_integration(cu(m), T)
         wd, wv = oracle.euler(m, T)
         assert np.array_equal(d.cpu().numpy(), wd) and np.array_equal(v.cpu().numpy(), wv)
+
+
+def test_euler_return_all_frames(pkg):
+    """Broken upstream (euler_integration_manipulator.py:31,:50); ours returns one entry per step count."""
+    rng = np.random.default_rng(4)
+    m = rng.uniform(-2, 2, (1, 2, 21, 34)).astype(np.float32)
+    d, v = pkg.euler_integration(cu(m), 5, return_all_frames=True)
+    assert d.shape == (6, 2, 21, 34) and v.shape == (6, 1, 21, 34)
+    for T in range(6):
+        wd, wv = oracle.euler(m, T)
+        assert np.array_equal(d[T:T + 1].cpu().numpy(), wd) and np.array_equal(v[T:T + 1].cpu().numpy(), wv)
