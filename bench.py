@@ -221,7 +221,7 @@ def run_reference_arm(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, algo):
@@ -236,8 +236,29 @@ def workload_config(args, algo):
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries chat on it (NCCL prints its version
+    banner with printf when NCCL_DEBUG=WARN/VERSION, torchrun children inherit it).  Point fd 1 at
+    stderr for the whole run and keep the original stdout for the final line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -258,7 +279,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     H, W, C, N = args.height, args.width, args.channels, args.frames
@@ -441,7 +461,7 @@ def main():
             "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
             "whole_path_roofline_frac": value / world / (peak * 1e9 / (4.0 * P * (4 * C + 5))),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
