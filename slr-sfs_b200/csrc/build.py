@@ -35,7 +35,7 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    # tuning knobs of the gather kernel (see clip_pipeline.cu); e.g. SLR_DEFINES="-DSLR_GATHER_DEPTH=12"
+    # tuning knobs (see clip_gather.cu / clip_common.cuh); e.g. SLR_DEFINES="-DSLR_LIST_DEPTH=128"
     extra = os.environ.get("SLR_DEFINES", "").split()
     cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

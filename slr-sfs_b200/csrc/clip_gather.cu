@@ -13,7 +13,7 @@
 //
 //   expand_kernel     one CTA per (destination tile 32x8, frame): turns the tile's bin into
 //                     per-lane (source, w_top, w_bottom) lists for its 4 row pairs.  Small
-//                     register footprint, 8 CTAs/SM: hides the latency of this pointer-chasing.
+//                     register footprint, 6 CTAs/SM: hides the latency of this pointer-chasing.
 //   rowgather_kernel  the hot kernel.  One warp per row pair (2 x 32 destination pixels), no
 //                     shared memory, no barriers.  A lane owns the pixels (x, y) and (x, y+1):
 //                     a source that feeds both (its north corners land on y, its south

@@ -159,9 +159,9 @@ def test_gather_ragged_shapes(pkg, shape, motion):
         assert np.all(out[t:t + 1][want == 0.0] == 0.0)
 
 
-def test_gather_sink_and_compression_use_multi_pass(pkg):
-    """Flows that pile many sources onto few destinations overflow the per-pixel register
-    lists and the per-pass bin chunk: the multi-pass path must give the same sums."""
+def test_gather_sink_and_compression_use_heavy_tiles(pkg):
+    """Flows that pile many sources onto few destinations overflow the per-lane lists: the
+    tail loop (deep lists) and the heavy-tile path (L2 reductions) must give the same sums."""
     H, W, C, N = 40, 72, 6, 3
     rng = np.random.default_rng(9)
     feat = rng.standard_normal((1, C, H, W)).astype(np.float32)
