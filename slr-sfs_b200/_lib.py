@@ -99,8 +99,8 @@ def current_stream(device):
 KERNELS_PER_CALL = {
     "slr_softsplat_sum_fwd": 1, "slr_softsplat_grad_input": 1, "slr_softsplat_grad_flow": 1,
     "slr_maxsplat_fwd": 2, "slr_maxwarpnorm": 3, "slr_euler": 1, "slr_reduce_max": 2,
-    "slr_joint_scatter": 1, "slr_normalize": 1, "slr_scene_prep": 1, "slr_clip_frames": 8,
-    "slr_clip_plan": 3, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 3,
+    "slr_joint_scatter": 1, "slr_normalize": 1, "slr_scene_prep": 1, "slr_clip_frames": 9,
+    "slr_clip_plan": 3, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 4,
 }
 _launches = 0
 _timing = None          # None, or list of (name, start_event, end_event)

@@ -89,7 +89,10 @@ struct Workspace {
     unsigned* tile_flag;  // [n][n_tiles]        1 = heavy tile
     unsigned* flag_list;  // [n * n_tiles]       compacted heavy tiles
     unsigned* flag_count; // [1]
-    float* heavy_sums;    // [n][3][P]           (tail..., norm) sums of heavy tiles
+    uint4* excess;        // [excess_cap]        pairs beyond kListDepth (dest pixel, source, weight, frame)
+    unsigned* excess_count; // [1]
+    unsigned excess_cap;
+    float* heavy_sums;    // [n][3][P]           (tail..., norm) sums of flagged tiles
     size_t bytes;
 };
 
@@ -113,6 +116,9 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
+    w.excess_cap = (unsigned)std::min<int64_t>(2 * P * n, 1ll << 30);
+    w.excess = (uint4*)(p + o);      o += align_up(sizeof(uint4) * (size_t)w.excess_cap);
+    w.excess_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.heavy_sums = (float*)(p + o);  o += align_up(sizeof(float) * 3 * P * n);
     w.bytes = o;
     return w;

@@ -49,10 +49,14 @@ struct GatherParams {
     const unsigned* offsets;   // [frames][n_tiles + 1]
     uint4* lists;              // [frames][n_tiles * 4][kListDepth][32]
     unsigned* row_k;           // [frames][n_tiles * 4]
-    unsigned* tile_flag;       // [frames][n_tiles]
-    unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the heavy tiles
+    unsigned* tile_flag;       // [frames][n_tiles]: 0 normal, 1 = some lane's list was cut at kListDepth (the
+                               // rest is in `excess`), 2 = excess list full: the whole tile goes the heavy way
+    unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
     unsigned* flag_count;      // [1], zeroed by slr_clip_plan
-    float* heavy_sums;         // [frames][3][P] (tail..., norm) sums of heavy tiles
+    uint4* excess;             // [excess_cap]: (destination pixel, source pixel, weight, frame) beyond kListDepth
+    unsigned* excess_count;    // [1], zeroed by slr_clip_plan
+    unsigned excess_cap;
+    float* heavy_sums;         // [frames][3][P] (tail..., norm) sums of flagged tiles
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -87,6 +91,7 @@ expand_kernel(const GatherParams prm)
     __shared__ uint4 tab[kSmemSlots * kCols];      // tab[slot * kCols + col] = (source, w_top, w_bottom, -)
     __shared__ unsigned occ[kCols];                // used canonical slots (bit mask)
     __shared__ unsigned ovf[kCols];                // overflow slots in use (kCanon, kCanon + 1, ...)
+    __shared__ unsigned excess_full;               // the global excess list ran out of room
 
     const int tid = threadIdx.x;
     const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
@@ -101,6 +106,7 @@ expand_kernel(const GatherParams prm)
 
     for (int i = tid; i < kCanon * kCols; i += TILE) tab[i] = make_uint4(kEmpty, 0u, 0u, 0u);
     if (tid < kCols) { occ[tid] = 0u; ovf[tid] = 0u; }
+    if (tid == 0) excess_full = 0u;
     __syncthreads();
 
     // one (destination pixel, source, weight) pair -> its lane's list
@@ -116,9 +122,18 @@ expand_kernel(const GatherParams prm)
         } else {
             const int so = kCanon + (int)atomicAdd(&ovf[col], 1u);
             const uint4 e = make_uint4(p, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, 0u);
-            if (so < kSmemSlots) tab[so * kCols + col] = e;
-            else if (so < kListDepth)     // deeper than the shared table: straight to its place in the global list
+            if (so < kSmemSlots) {
+                tab[so * kCols + col] = e;
+            } else if (so < kListDepth) {     // deeper than the shared table: straight to its place in the global list
                 __stcg(lists_tile + ((int64_t)(ly >> 1) * kListDepth + so) * 32 + lx, e);
+            } else {
+                // deeper than the lists (a convergence point): this one pair is added by an fp32
+                // reduction at L2 after the gather (heavy_scatter_kernel)
+                const unsigned i = atomicAdd(prm.excess_count, 1u);
+                const unsigned dpix = (unsigned)((ty * TH + ly) * prm.W + tx * TW + lx);
+                if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, p, __float_as_uint(w), (unsigned)f));
+                else excess_full = 1u;
+            }
         }
     };
 
@@ -148,16 +163,17 @@ expand_kernel(const GatherParams prm)
     }
     __syncthreads();
     const bool deep = tid < kCols && kCanon + (int)ovf[tid] > kListDepth;
-    const int over = __syncthreads_or(deep);
+    const int any_deep = __syncthreads_or(deep);
+    const unsigned flag = excess_full ? 2u : (any_deep ? 1u : 0u);
     if (tid == 0) {
-        prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = over ? 1u : 0u;
-        if (over) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
+        prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = flag;
+        if (flag) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
     }
-    if (over || tid >= kCols) return;
+    if (flag == 2u || tid >= kCols) return;
 
     // write the lists out, slot-major per row pair
     const unsigned my_occ = occ[tid];
-    const int n_ovf = (int)ovf[tid];
+    const int n_ovf = min((int)ovf[tid], kListDepth - kCanon);     // the rest is in the excess list
     const int my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz(my_occ);    // slots [0, my_hi) may be used
     const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
     const int64_t pair = pair0 + (tid >> 5);
@@ -189,6 +205,7 @@ struct RowCtx {
     int W, groups, C, kmax;
     float eps;
     bool in_top, in_bot;
+    bool raw;             // flagged tile: write un-normalised sums, heavy_finish_kernel divides
 };
 
 // K  = compile-time number of register-resident slots (the warp's list length rounded up);
@@ -228,7 +245,8 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
             }
         }
     }
-    const float inv_t = 1.0f / fmaxf(sum_t[NT], c.eps), inv_b = 1.0f / fmaxf(sum_b[NT], c.eps);
+    const float inv_t = c.raw ? 1.0f : 1.0f / fmaxf(sum_t[NT], c.eps);
+    const float inv_b = c.raw ? 1.0f : 1.0f / fmaxf(sum_b[NT], c.eps);
 
     const char* Gg = c.G;
     const size_t gstride = (size_t)(c.P + 1) * 16;
@@ -309,7 +327,8 @@ rowgather_kernel(const GatherParams prm)
 {
     const int tid = threadIdx.x;
     const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
-    if (__ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile) != 0u) return;    // heavy_tile_kernel's tile
+    const unsigned flag = __ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile);
+    if (flag == 2u) return;                                   // done entirely by the heavy kernels
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     const int X = tx * TW + (tid & 31), Y = ty * TH + 2 * (tid >> 5);
     const int64_t P = prm.P;
@@ -324,6 +343,7 @@ rowgather_kernel(const GatherParams prm)
     c.in_top = X < prm.W && Y < prm.H;
     c.in_bot = X < prm.W && Y + 1 < prm.H;
     c.kmax = kmax;
+    c.raw = flag == 1u;
 
     unsigned pk[kRegSlots];
     float wt[kRegSlots], wb[kRegSlots];
@@ -349,6 +369,12 @@ rowgather_kernel(const GatherParams prm)
         if (!(r ? c.in_bot : c.in_top)) continue;
         const float* sum = r ? sum_b : sum_t;
         const int64_t px = pix + (r ? prm.W : 0);
+        if (c.raw) {        // the excess pairs are still to come: leave the sums for heavy_finish_kernel
+            float* hs = prm.heavy_sums + (int64_t)f * 3 * P + px;
+            #pragma unroll
+            for (int j = 0; j <= NT; ++j) hs[(int64_t)j * P] = sum[j];
+            continue;
+        }
         if (prm.aux) {
             float* a = prm.aux + (int64_t)f * (NT + 1) * P + px;
             #pragma unroll
@@ -394,7 +420,10 @@ heavy_prepare_kernel(const GatherParams prm, int n_sums)
 {
     const unsigned n = *prm.flag_count;
     for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
-        const HeavyTile t = heavy_tile(prm, prm.flag_list[i], threadIdx.x);
+        const unsigned item = prm.flag_list[i];
+        const HeavyTile t = heavy_tile(prm, item, threadIdx.x);
+        const int tile = t.ty * prm.tiles_x + t.tx;
+        if (prm.tile_flag[(int64_t)t.f * prm.n_tiles + tile] != 2u) continue;    // flag 1: the gather wrote raw sums
         if (!t.inframe) continue;
         float* out = prm.out + (int64_t)t.f * prm.C * prm.P + t.pix;
         for (int c = 0; c < prm.C; ++c) out[(int64_t)c * prm.P] = 0.0f;
@@ -419,6 +448,7 @@ heavy_scatter_kernel(const GatherParams prm)
         const int chunk = (int)(wi % n_chunks);
         const HeavyTile t = heavy_tile(prm, item, tid);
         const int tile = t.ty * prm.tiles_x + t.tx;
+        if (prm.tile_flag[(int64_t)t.f * prm.n_tiles + tile] != 2u) continue;
         const float a_f = prm.alphas.a[t.f], a_b = 1.0f - a_f;
         const unsigned* off = prm.offsets + (int64_t)t.f * (prm.n_tiles + 1);
         const unsigned beg = off[tile], end = off[tile + 1];
@@ -466,6 +496,38 @@ heavy_scatter_kernel(const GatherParams prm)
                 if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
                     add_pair((int64_t)cy * prm.W + cx, pd & ~kDirBit, wa);
             }
+        }
+    }
+}
+
+// The pairs that did not fit the lists of flag-1 tiles: one thread per pair, fp32 reductions at
+// L2 onto the un-normalised sums the gather left in `out` / `heavy_sums`.
+template <int NT>
+__global__ void __launch_bounds__(TILE)
+heavy_excess_kernel(const GatherParams prm)
+{
+    const int64_t P = prm.P;
+    const int64_t sstride = P + 1;
+    const size_t gstride = (size_t)(P + 1) * 16;
+    const unsigned n = min(*prm.excess_count, prm.excess_cap);
+    for (unsigned i = blockIdx.x * TILE + threadIdx.x; i < n; i += gridDim.x * TILE) {
+        const uint4 e = __ldcg(prm.excess + i);
+        const int f = (int)e.w;
+        const int64_t dpix = e.x;
+        const int tile = (int)(dpix / prm.W) / TH * prm.tiles_x + (int)(dpix % prm.W) / TW;
+        if (prm.tile_flag[(int64_t)f * prm.n_tiles + tile] != 1u) continue;     // flag 2: done from the bin
+        const float w = __uint_as_float(e.z);
+        float* sums = prm.heavy_sums + (int64_t)f * 3 * P + dpix;
+        #pragma unroll
+        for (int j = 0; j <= NT; ++j) red_add(sums + (int64_t)j * P, __ldg(prm.S + (int64_t)j * sstride + e.y) * w);
+        float* out = prm.out + (int64_t)f * prm.C * P + dpix;
+        const char* Gg = prm.G;
+        for (int g = 0; g < prm.groups; ++g, Gg += gstride) {
+            const float4 v = __ldg(px16(Gg, e.y));
+            const float r[4] = {v.x * w, v.y * w, v.z * w, v.w * w};
+            #pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * g + j < prm.C) red_add(out + (int64_t)(4 * g + j) * P, r[j]);
         }
     }
 }
@@ -523,6 +585,7 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;
+    prm.excess = ws.excess; prm.excess_count = ws.excess_count; prm.excess_cap = ws.excess_cap;
     prm.out = out; prm.aux = aux; prm.mask = mask;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = tiles_x * tiles_y; prm.n_frames = n_frames;
@@ -586,12 +649,15 @@ extern "C" int slr_clip_heavy(const void* scene, const float* motion, int64_t C,
     heavy_prepare_kernel<<<heavy_grid, TILE, 0, s>>>(prm, n_tail + 1);
     if (n_tail == 0) {
         heavy_scatter_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_excess_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
         heavy_finish_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
     } else if (n_tail == 1) {
         heavy_scatter_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_excess_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
         heavy_finish_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
     } else {
         heavy_scatter_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
+        heavy_excess_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
         heavy_finish_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
     }
     return SLR_LAUNCH_STATUS();

@@ -278,6 +278,7 @@ extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int star
 
     SLR_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
     SLR_CUDA(cudaMemsetAsync(ws.flag_count, 0, sizeof(unsigned), s));
+    SLR_CUDA(cudaMemsetAsync(ws.excess_count, 0, sizeof(unsigned), s));
     const unsigned pblocks = (unsigned)((P + 255) / 256);
     euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
                                                ws.land, ws.counts, tiles_x, n_tiles);
