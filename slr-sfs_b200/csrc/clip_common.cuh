@@ -67,9 +67,13 @@ __device__ __forceinline__ unsigned warp_reserve(unsigned* counters, int key)
 // address of pixel `p` in a float4 plane: one IMAD.WIDE
 __device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
 {
+#if defined(SLR_CPU_EMULATION)      // tests/emu: the same sources compiled for the CPU
+    return reinterpret_cast<const float4*>(plane + (size_t)p * 16);
+#else
     unsigned long long a;
     asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(p), "l"(plane));
     return reinterpret_cast<const float4*>(a);
+#endif
 }
 
 }  // namespace slr

@@ -23,11 +23,17 @@
 //   heavy_*_kernel    tiles with a lane deeper than the lists hold (convergence zones of the
 //                     flow): per-pair fp32 reductions at L2, cost linear in pairs.
 #include "clip_common.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace slr {
 
 #ifndef SLR_GATHER_MINBLOCKS
 #define SLR_GATHER_MINBLOCKS 4         // resident 128-thread CTAs per SM the register budget is sized for
+#endif
+#ifndef SLR_GATHER_FRAMES
+#define SLR_GATHER_FRAMES 1            // default CTA shape of rowgather_kernel: frames x row pairs
+#define SLR_GATHER_PAIRS 4
 #endif
 #ifndef SLR_EXPAND_MINBLOCKS
 #define SLR_EXPAND_MINBLOCKS 6
@@ -321,19 +327,29 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
     else gather_rows<NT, K, 1>(c, pk, wt, wb, sum_t, sum_b);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kCols, SLR_GATHER_MINBLOCKS)
+// CTA shape: F frames x R row pairs (warps) of one destination tile, F * R * 32 threads.  Warps of
+// the SAME tile in consecutive frames read source regions that differ only by one frame's
+// displacement, so with F > 1 they share most of their lines in this SM's L1 as well (the
+// frame-fastest CTA order already shares them in L2).  R < 4 splits a tile's row pairs over CTAs.
+template <int NT, int F, int R>
+__global__ void __launch_bounds__(32 * F * R, (SLR_GATHER_MINBLOCKS * kCols) / (32 * F * R))
 rowgather_kernel(const GatherParams prm)
 {
+    constexpr int kParts = kPairsPerTile / R;           // CTAs per (tile, frame group)
     const int tid = threadIdx.x;
-    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    const int warp = tid >> 5;
+    const int n_fg = (prm.n_frames + F - 1) / F;
+    const int f = (int)(blockIdx.x % (unsigned)n_fg) * F + warp / R;
+    const int part = (int)(blockIdx.x / (unsigned)n_fg);
+    const int tile = part / kParts, pr = (part % kParts) * R + warp % R;      // row pair within the tile
+    if (f >= prm.n_frames) return;
     const unsigned flag = __ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile);
     if (flag == 2u) return;                                   // done entirely by the heavy kernels
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
-    const int X = tx * TW + (tid & 31), Y = ty * TH + 2 * (tid >> 5);
+    const int X = tx * TW + (tid & 31), Y = ty * TH + 2 * pr;
     const int64_t P = prm.P;
     const int64_t pix = (int64_t)Y * prm.W + X;
-    const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + (tid >> 5);
+    const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + pr;
     const int kmax = (int)__ldg(prm.row_k + pair);
 
     RowCtx c;
@@ -600,6 +616,28 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     return 0;
 }
 
+// CTA shape of rowgather_kernel: "<frames>x<row pairs>".  The default was chosen by measurement
+// (profiles/); the environment variable SLR_GATHER_SHAPE overrides it for sweeps.
+struct GatherShape { int frames, pairs; };
+
+GatherShape gather_shape()
+{
+    GatherShape g = {SLR_GATHER_FRAMES, SLR_GATHER_PAIRS};
+    const char* e = getenv("SLR_GATHER_SHAPE");
+    int f = 0, r = 0;
+    if (e && sscanf(e, "%dx%d", &f, &r) == 2) { g.frames = f; g.pairs = r; }
+    return g;
+}
+
+template <int F, int R>
+void launch_rowgather(const GatherParams& prm, int n_tail, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)(kPairsPerTile / R) * (unsigned)((prm.n_frames + F - 1) / F);
+    if (n_tail == 0) rowgather_kernel<0, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    else if (n_tail == 1) rowgather_kernel<1, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    else rowgather_kernel<2, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+}
+
 }  // namespace
 
 extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
@@ -625,11 +663,12 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                                out, aux, mask, workspace, workspace_bytes);
     if (rc) return rc;
-    cudaStream_t s = (cudaStream_t)stream_;
-    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
-    if (n_tail == 0) rowgather_kernel<0><<<grid, kCols, 0, s>>>(prm);
-    else if (n_tail == 1) rowgather_kernel<1><<<grid, kCols, 0, s>>>(prm);
-    else rowgather_kernel<2><<<grid, kCols, 0, s>>>(prm);
+    const GatherShape shape = gather_shape();
+    if (shape.frames == 2 && shape.pairs == 4) launch_rowgather<2, 4>(prm, n_tail, (cudaStream_t)stream_);
+    else if (shape.frames == 4 && shape.pairs == 4) launch_rowgather<4, 4>(prm, n_tail, (cudaStream_t)stream_);
+    else if (shape.frames == 2 && shape.pairs == 2) launch_rowgather<2, 2>(prm, n_tail, (cudaStream_t)stream_);
+    else if (shape.frames == 4 && shape.pairs == 1) launch_rowgather<4, 1>(prm, n_tail, (cudaStream_t)stream_);
+    else launch_rowgather<1, 4>(prm, n_tail, (cudaStream_t)stream_);
     return SLR_LAUNCH_STATUS();
 }
 

@@ -42,3 +42,9 @@ def rel_err(a, ref):
     s = float(np.sqrt(np.mean(ref * ref))) if ref.size else 0.0
     den = np.maximum(np.abs(ref), max(s, 1e-30))
     return float(np.max(np.abs(a - ref) / den)) if ref.size else 0.0
+
+
+# tests/emu (the CUDA sources compiled for the CPU) is importable as `emu`
+_TESTS = os.path.dirname(os.path.abspath(__file__))
+if _TESTS not in sys.path:
+    sys.path.insert(0, _TESTS)

@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE: the CUDA sources of slr-sfs_b200/csrc compiled for the CPU (see build.py
+and include/cuda_runtime.h) and driven through the same C ABI with numpy buffers."""
+import ctypes
+
+import numpy as np
+
+from . import build as _build
+
+_lib = None
+
+
+def lib():
+    """The emulation build of libslr_splat, bound with the argument types the product binding
+    (slr_sfs_b200/_lib.py: SIGNATURES) declares for the real one."""
+    global _lib
+    if _lib is None:
+        from slr_sfs_b200 import _lib as binding
+        L = ctypes.CDLL(_build.build())
+        for name, argtypes in binding.SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = binding._OTHER_RESTYPE.get(name, ctypes.c_int)
+        _lib = L
+    return _lib
+
+
+def call(name, *args):
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s -> %d: %s" % (name, rc, L.slr_last_error_string().decode()))
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def p(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def aligned(nbytes, align=256):
+    """Zero-initialised byte buffer whose data pointer is `align`-aligned (cudaMalloc gives 256)."""
+    raw = np.zeros(nbytes + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + nbytes]
+
+
+class Scene:
+    """What synthesis.JointSplat does on the device, on host buffers: Z.max(), scene buffer,
+    then batches of frames through the clip entry points."""
+
+    def __init__(self, feat, Z, motion, tail=None, z_mode="max"):
+        self.feat, self.Z, self.motion = f32(feat), f32(Z), f32(motion)
+        self.tail = None if tail is None else f32(tail)
+        self.n_tail = 0 if tail is None else self.tail.shape[1]
+        _, self.C, self.H, self.W = self.feat.shape
+        self.zsub = None
+        if z_mode == "max":
+            self.zsub = np.zeros(1, dtype=np.float32)
+            call("slr_reduce_max", p(self.Z), self.Z.size, p(self.zsub), None)
+        n = lib().slr_scene_bytes(self.C, self.n_tail, self.H, self.W)
+        self.scene = aligned(n)
+        call("slr_scene_prep", p(self.feat), p(self.Z), p(self.zsub), p(self.tail), self.n_tail,
+             p(self.scene), self.C, self.H, self.W, None)
+
+    def frames(self, start, end, t0, n, alpha_clamp=(0.0, 1.0), want_aux=False, want_mask=False, split=False):
+        C, H, W = self.C, self.H, self.W
+        out = np.full((n, C, H, W), np.nan, dtype=np.float32)
+        aux = np.full((n, self.n_tail + 1, H, W), np.nan, dtype=np.float32) if want_aux else None
+        mask = np.full((n, 1, H, W), np.nan, dtype=np.float32) if want_mask else None
+        nb = lib().slr_clip_workspace_bytes(H, W, n)
+        ws = aligned(nb)
+        ws[:] = 0xA5          # the library must not rely on a zeroed workspace
+        args = (C, self.n_tail, H, W, start, end, t0, n, alpha_clamp[0], alpha_clamp[1])
+        if split:
+            call("slr_clip_plan", p(self.motion), H, W, start, end, t0, n, p(ws), nb, None)
+            call("slr_clip_expand", p(self.scene), p(self.motion), *args, p(ws), nb, None)
+            for entry in ("slr_clip_gather", "slr_clip_heavy"):
+                call(entry, p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)
+        else:
+            call("slr_clip_frames", p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)
+        res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
+        return res if len(res) > 1 else out

@@ -1,0 +1,187 @@
+"""CPU: the CUDA kernel SOURCES (slr-sfs_b200/csrc/*.cu), compiled for the CPU by tests/emu
+and called through the same C ABI, against the oracle and the reference's golden vectors.
+
+This is not a product path (the package only ever loads csrc/libslr_splat.so and has no CPU
+mode); it lets the container without a GPU check the logic of the very kernel text the B200
+runs -- index arithmetic, list building, heavy-tile fallbacks, barriers -- before GPU time is
+spent.  What it cannot see: races (lanes run one after the other), device expf (1 ulp), speed.
+Same tolerances as tests/test_gpu_*.py."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err
+
+emu = pytest.importorskip("emu", reason="tests/emu")
+TOL = 1e-4
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def _case(seed, B, C, H, W, amp=3.0):
+    r = _rng(seed)
+    return (r.standard_normal((B, C, H, W)).astype(np.float32),
+            (r.uniform(-amp, amp, (B, 2, H, W))).astype(np.float32))
+
+
+# ---------------------------------------------------------------------------- operator level
+@pytest.mark.parametrize("shape", [(1, 3, 17, 23), (2, 5, 32, 32), (1, 9, 40, 70)])
+def test_emu_summation_splat_and_grads(shape):
+    B, C, H, W = shape
+    inp, flow = _case(1, B, C, H, W)
+    out = np.full_like(inp, np.nan)
+    emu.call("slr_softsplat_sum_fwd", emu.p(inp), emu.p(flow), emu.p(out), B, C, H, W, 1, None)
+    assert rel_err(out, oracle.softsplat_sum(inp, flow)) <= TOL
+    gout = _rng(2).standard_normal(inp.shape).astype(np.float32)
+    gin = np.full_like(inp, np.nan)
+    emu.call("slr_softsplat_grad_input", emu.p(flow), emu.p(gout), emu.p(gin), B, C, H, W, None)
+    assert rel_err(gin, oracle.softsplat_grad_input(flow, gout)) <= TOL
+    gflow = np.full_like(flow, np.nan)
+    emu.call("slr_softsplat_grad_flow", emu.p(inp), emu.p(flow), emu.p(gout), emu.p(gflow), B, C, H, W, None)
+    assert rel_err(gflow, oracle.softsplat_grad_flow(inp, flow, gout)) <= TOL
+
+
+def test_emu_golden_cases_from_the_reference_kernels(golden_softsplat):
+    g = golden_softsplat
+    for case in sorted({k.split("/")[0] for k in g.files if "/" in k}):
+        inp, flow, gout = g[case + "/inp"], g[case + "/flow"], g[case + "/gout"]
+        B, C, H, W = inp.shape
+        out, gin, gflow = np.empty_like(inp), np.empty_like(inp), np.empty_like(flow)
+        emu.call("slr_softsplat_sum_fwd", emu.p(inp), emu.p(flow), emu.p(out), B, C, H, W, 1, None)
+        emu.call("slr_softsplat_grad_input", emu.p(flow), emu.p(gout), emu.p(gin), B, C, H, W, None)
+        emu.call("slr_softsplat_grad_flow", emu.p(inp), emu.p(flow), emu.p(gout), emu.p(gflow), B, C, H, W, None)
+        assert rel_err(out, g[case + "/sum"]) <= TOL, case
+        assert rel_err(gin, g[case + "/gin"]) <= TOL, case
+        assert rel_err(gflow, g[case + "/gflow"]) <= TOL, case
+        z = g[case + "/z"]
+        scratch, mw = np.empty_like(z), np.empty_like(z)
+        emu.call("slr_maxwarpnorm", emu.p(z), emu.p(flow), emu.p(scratch), emu.p(mw), *z.shape, None)
+        assert np.array_equal(mw, g[case + "/maxwarpnorm"]), case
+
+
+def test_emu_max_warp_norm_bit_exact():
+    inp, flow = _case(3, 2, 1, 24, 40, amp=5.0)
+    scratch, out = np.empty_like(inp), np.empty_like(inp)
+    emu.call("slr_maxwarpnorm", emu.p(inp), emu.p(flow), emu.p(scratch), emu.p(out), 2, 1, 24, 40, None)
+    assert np.array_equal(out, oracle.max_warp_norm(inp, flow))
+
+
+@pytest.mark.parametrize("T", [0, 1, 7, 60])
+def test_emu_euler_bit_exact(T):
+    H, W = 33, 50
+    motion = (_rng(4).uniform(-2.5, 2.5, (1, 2, H, W))).astype(np.float32)
+    motion[:, :, 10:20, 5:30] = 0.0
+    for sign in (1.0, -1.0):
+        disp = np.empty((1, 2, H, W), dtype=np.float32)
+        vis = np.empty((1, 1, H, W), dtype=np.float32)
+        emu.call("slr_euler", emu.p(motion), sign, T, emu.p(disp), emu.p(vis), H, W, None)
+        want_d, want_v = oracle.euler(np.float32(sign) * motion, T)
+        assert np.array_equal(disp, want_d) and np.array_equal(vis, want_v)
+
+
+def test_emu_reduce_max_mixed_signs():
+    x = _rng(5).standard_normal(5000).astype(np.float32) - 3.0
+    out = np.zeros(1, dtype=np.float32)
+    emu.call("slr_reduce_max", emu.p(x), x.size, emu.p(out), None)
+    assert out[0] == x.max()
+    x = -np.abs(x) - 1.0
+    emu.call("slr_reduce_max", emu.p(x), x.size, emu.p(out), None)
+    assert out[0] == x.max()
+
+
+# ---------------------------------------------------------------------------- joint block
+def _scene(H, W, C, kind, seed):
+    from slr_sfs_b200 import workloads
+    feat, Z, m = workloads.scene(H, W, C, kind, seed=seed)
+    return feat.numpy(), Z.numpy(), m.numpy()
+
+
+def test_emu_scatter_joint_vs_oracle():
+    H, W, C, N, t = 24, 40, 6, 9, 4
+    feat, Z, motion = _scene(H, W, C, "A", 1)
+    zsub = np.array([Z.max()], dtype=np.float32)
+    disp = np.empty((2, 2, H, W), dtype=np.float32)
+    emu.call("slr_euler", emu.p(motion), 1.0, t, emu.p(disp[0]), None, H, W, None)
+    emu.call("slr_euler", emu.p(motion), -1.0, N - 1 - t + 1, emu.p(disp[1]), None, H, W, None)
+    acc = np.full((1, C + 1, H, W), np.nan, dtype=np.float32)
+    alpha = float(oracle.blend_alpha(t, 0, N - 1))
+    emu.call("slr_joint_scatter", emu.p(feat), emu.p(Z), emu.p(zsub), None, 0, emu.p(disp[0]), emu.p(disp[1]),
+             alpha, emu.p(acc), C, H, W, None)
+    out = np.empty((1, C, H, W), dtype=np.float32)
+    emu.call("slr_normalize", emu.p(acc), emu.p(out), None, C, C, C + 1, 1e-8, H, W, None)
+    assert rel_err(out, oracle.joint_splat_baseline(feat, Z, motion, (0, t, N - 1))) <= TOL
+
+
+@pytest.mark.parametrize("kind,shape", [("A", (40, 64)), ("B", (24, 40)), ("C", (17, 37)), ("A", (9, 33))])
+def test_emu_gather_clip_vs_oracle(kind, shape):
+    H, W = shape
+    C, N = 6, 8
+    feat, Z, motion = _scene(H, W, C, kind, 2)
+    sc = emu.Scene(feat, Z, motion)
+    got = sc.frames(0, N - 1, 0, N)
+    assert not np.isnan(got).any()
+    for t in range(N):
+        want = oracle.joint_splat_baseline(feat, Z, motion, (0, t, N - 1))
+        assert rel_err(got[t:t + 1], want) <= TOL, (kind, t)
+        assert np.all(got[t:t + 1][want == 0.0] == 0.0)
+
+
+@pytest.mark.parametrize("shape", ["1x4", "2x4", "4x4", "2x2", "4x1"])
+def test_emu_gather_cta_shapes_agree(shape, monkeypatch):
+    """rowgather_kernel's CTA shapes (frames x row pairs per CTA, SLR_GATHER_SHAPE) only regroup
+    the same warps: identical results, including a ragged frame count and ragged image edges."""
+    H, W, C, N = 21, 45, 5, 7
+    feat, Z, motion = _scene(H, W, C, "A", 6)
+    sc = emu.Scene(feat, Z, motion)
+    monkeypatch.delenv("SLR_GATHER_SHAPE", raising=False)
+    base = sc.frames(0, N - 1, 0, N)
+    monkeypatch.setenv("SLR_GATHER_SHAPE", shape)
+    got = sc.frames(0, N - 1, 0, N)
+    assert np.array_equal(got, base)
+    want = oracle.joint_splat_baseline(feat, Z, motion, (0, 3, N - 1))
+    assert rel_err(got[3:4], want) <= TOL
+
+
+def test_emu_gather_nonzero_start_split_calls_and_v1():
+    H, W, C = 24, 40, 5
+    feat, Z, motion = _scene(H, W, C, "A", 3)
+    sc = emu.Scene(feat, Z, motion, z_mode="v1")
+    got = sc.frames(2, 11, 5, 3, split=True)
+    for i, t in enumerate((5, 6, 7)):
+        want = oracle.joint_splat_baseline(feat, Z, motion, (2, t, 11), z_mode="v1")
+        assert rel_err(got[i:i + 1], want) <= TOL, t
+
+
+def test_emu_two_layer_aux_and_mask():
+    from slr_sfs_b200 import workloads
+    H, W, C, N = 24, 40, 4, 6
+    feat, Z, motion = _scene(H, W, C, "A", 4)
+    a_f, a_bg = [t.numpy() for t in workloads.two_layer_extras(H, W, seed=4)]
+    s = 1.0 / (1.0 + np.exp(-a_f))
+    A = (s / np.maximum(s + a_bg, 1e-8)).astype(np.float32)
+    tail = np.concatenate([a_f * np.exp(A), np.exp(A)], 1).astype(np.float32)
+    sc = emu.Scene(feat, Z, motion, tail=tail)
+    lo, hi = float(np.float32(1.0 / 600.0)), float(np.float32(599.0 / 600.0))
+    gen, aux, mask = sc.frames(0, N - 1, 0, N, alpha_clamp=(lo, hi), want_aux=True, want_mask=True)
+    for t in (0, 2, N - 1):
+        w_gen, w_alpha, w_mask = oracle.joint_splat_2layer(feat, Z, a_f, a_bg, motion, (0, t, N - 1), alpha0=True)
+        assert rel_err(gen[t:t + 1], w_gen) <= TOL
+        alpha_fluid = aux[t:t + 1, 0:1] / np.maximum(aux[t:t + 1, 1:2], np.float32(1e-8))
+        assert rel_err(alpha_fluid, w_alpha) <= TOL
+        assert np.array_equal(mask[t:t + 1], w_mask)
+
+
+def test_emu_sink_flow_takes_the_heavy_paths():
+    """Everything flows into one point: lists overflow (flag 1, excess pairs) and, with a tiny
+    excess capacity, whole tiles fall back to reductions from their bins (flag 2)."""
+    H, W, C, N = 32, 64, 4, 30
+    feat, Z, _ = _scene(H, W, C, "A", 5)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    motion = np.stack([(W / 2 - xs) * 0.2, (H / 2 - ys) * 0.2])[None].astype(np.float32)
+    sc = emu.Scene(feat, Z, motion)
+    got = sc.frames(0, N - 1, 20, 4)
+    for i, t in enumerate(range(20, 24)):
+        want = oracle.joint_splat_baseline(feat, Z, motion, (0, t, N - 1))
+        assert rel_err(got[i:i + 1], want) <= TOL, t
