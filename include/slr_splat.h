@@ -173,6 +173,14 @@ int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tai
                     float alpha_lo, float alpha_hi, float* out, float* aux, float* mask,
                     void* workspace, size_t workspace_bytes, slr_stream_t stream);
 
+/* Diagnostics (a `_host` call: copies four counters to the host and synchronises `stream`).
+ * After slr_clip_expand on `workspace`: stats[0] = flagged destination tiles of the batch (some
+ * lane's source list was cut at the list depth), stats[1] = of those, tiles done entirely by
+ * per-pair reductions from their bins, stats[2] = (destination, source) pairs beyond the list
+ * depth, stats[3] = capacity of that excess list. */
+int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,
+                        uint32_t stats[4], slr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

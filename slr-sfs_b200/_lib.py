@@ -41,6 +41,7 @@ SIGNATURES = {
                        _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_frames": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
                         _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
+    "slr_clip_stats_host": [_f32p, ctypes.c_size_t, _i64, _i64, _int, ctypes.POINTER(ctypes.c_uint32), _strm],
 }
 _OTHER_RESTYPE = {"slr_last_error_string": ctypes.c_char_p, "slr_scene_bytes": ctypes.c_size_t,
                   "slr_clip_workspace_bytes": ctypes.c_size_t}

@@ -25,6 +25,7 @@
 #include "clip_common.cuh"
 #include <stdio.h>
 #include <stdlib.h>
+#include <vector>
 
 namespace slr {
 
@@ -718,4 +719,28 @@ extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C
     if (rc) return rc;
     return slr_clip_heavy(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                           out, aux, mask, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,
+                                   uint32_t stats[4], slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(workspace && stats && H > 0 && W > 0 && n_frames > 0 && n_frames <= kMaxFrames,
+                   "slr_clip_stats_host: bad arguments");
+    const Workspace ws = carve(const_cast<void*>(workspace), H, W, n_frames);
+    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "workspace too small (see slr_clip_workspace_bytes)");
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int64_t tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * n_frames;
+    uint32_t n_flag = 0, n_excess = 0;
+    SLR_CUDA(cudaMemcpyAsync(&n_flag, ws.flag_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SLR_CUDA(cudaMemcpyAsync(&n_excess, ws.excess_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SLR_CUDA(cudaStreamSynchronize(s));
+    uint32_t n_full = 0;
+    if (n_flag) {
+        std::vector<uint32_t> flags((size_t)tiles);
+        SLR_CUDA(cudaMemcpyAsync(flags.data(), ws.tile_flag, sizeof(uint32_t) * (size_t)tiles, cudaMemcpyDeviceToHost, s));
+        SLR_CUDA(cudaStreamSynchronize(s));
+        for (uint32_t v : flags) n_full += v == 2u;
+    }
+    stats[0] = n_flag; stats[1] = n_full; stats[2] = n_excess; stats[3] = ws.excess_cap;
+    return 0;
 }

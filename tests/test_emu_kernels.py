@@ -173,15 +173,58 @@ def test_emu_two_layer_aux_and_mask():
         assert np.array_equal(mask[t:t + 1], w_mask)
 
 
-def test_emu_sink_flow_takes_the_heavy_paths():
-    """Everything flows into one point: lists overflow (flag 1, excess pairs) and, with a tiny
-    excess capacity, whole tiles fall back to reductions from their bins (flag 2)."""
-    H, W, C, N = 32, 64, 4, 30
-    feat, Z, _ = _scene(H, W, C, "A", 5)
+def _sink_scene(H, W, C, seed):
+    feat, Z, _ = _scene(H, W, C, "A", seed)
     ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
-    motion = np.stack([(W / 2 - xs) * 0.2, (H / 2 - ys) * 0.2])[None].astype(np.float32)
-    sc = emu.Scene(feat, Z, motion)
-    got = sc.frames(0, N - 1, 20, 4)
-    for i, t in enumerate(range(20, 24)):
-        want = oracle.joint_splat_baseline(feat, Z, motion, (0, t, N - 1))
-        assert rel_err(got[i:i + 1], want) <= TOL, t
+    sink = np.stack([(W / 2 + 0.3) - xs, (H / 3 + 0.6) - ys])[None].astype(np.float32)     # everything -> one point in 1 step
+    squeeze = np.stack([-(xs - W / 2) * 0.45, -(ys - H / 2) * 0.2])[None].astype(np.float32)  # strong compression
+    return feat, Z, sink, squeeze
+
+
+def test_emu_convergent_flows_take_the_heavy_paths():
+    """Flows that pile many sources onto few destinations: deep lists (tail loop of the gather),
+    lists cut at the list depth with the excess pairs added by reductions (flag 1)."""
+    H, W, C, N = 40, 72, 6, 3
+    feat, Z, sink, squeeze = _sink_scene(H, W, C, 9)
+    seen_flagged = 0
+    for m in (sink, squeeze):
+        sc = emu.Scene(feat, Z, m)
+        got = sc.frames(0, N - 1, 1, 2)
+        seen_flagged += sc.stats["flagged"]
+        for i, t in enumerate((1, 2)):
+            want = oracle.joint_splat_baseline(feat, Z, m, (0, t, N - 1))
+            assert rel_err(got[i:i + 1], want) <= TOL
+            assert np.all(got[i:i + 1][want == 0.0] == 0.0)
+    assert seen_flagged > 0
+
+
+def test_emu_excess_list_overflow_falls_back_to_whole_tile_reductions():
+    """A one-step sink puts 4*P pairs onto four pixels; with a single frame in the batch the excess
+    list (2*P*n entries) overflows and the tile goes the flag-2 way: zeroed, every pair of its
+    bin added by reductions, divided at the end."""
+    H, W, C, N = 40, 72, 6, 3
+    feat, Z, sink, _ = _sink_scene(H, W, C, 9)
+    sc = emu.Scene(feat, Z, sink)
+    got = sc.frames(0, N - 1, 1, 1)
+    assert sc.stats["full"] > 0 and sc.stats["excess"] > sc.stats["excess_cap"]
+    want = oracle.joint_splat_baseline(feat, Z, sink, (0, 1, N - 1))
+    assert rel_err(got, want) <= TOL
+    assert np.all(got[want == 0.0] == 0.0)
+
+
+def test_emu_static_pixels_and_negative_zero():
+    H, W, C, N = 24, 40, 4, 8
+    r = _rng(21)
+    feat = r.standard_normal((1, C, H, W)).astype(np.float32)
+    Z = r.standard_normal((1, 1, H, W)).astype(np.float32)
+    zero = np.zeros((1, 2, H, W), np.float32)
+    out = emu.Scene(feat, Z, zero).frames(0, N - 1, 0, N)
+    for t in (0, 5, N - 1):
+        assert rel_err(out[t:t + 1], feat) <= 1e-6
+    m = zero.copy()
+    m[0, 0, :, : W // 2] = 1.7
+    m[0, 1, : H // 2, : W // 2] = -0.6
+    m[0, 0, 3, 5] = -0.0
+    got = emu.Scene(feat, Z, m).frames(0, N - 1, 0, N)
+    for t in (1, 6, N - 1):
+        assert rel_err(got[t:t + 1], oracle.joint_splat_baseline(feat, Z, m, (0, t, N - 1))) <= TOL
