@@ -28,7 +28,7 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default=None, choices=[None, "scatter", "gather"],
@@ -71,59 +71,121 @@ def measured_peak_hbm():
 
 
 # --------------------------------------------------------------------------
-# clocks: sample nvidia-smi while the timed region runs
+# clocks: sampled (NVML) while the timed region runs
 # --------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU while the timed region runs.  NVML in a thread
+    (a sample every ~10 ms, so that even a 50 ms region is seen); `nvidia-smi -lms` as fallback.
+    Samples between mark_begin() and mark_end() are the ones reported; if the region was too short
+    to catch one, the samples of the whole bracket (warm-up included) are used and that is said."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, cuda_index):
+        self.cuda_index = cuda_index
+        self.samples = []            # (host time, sm MHz, set of reasons)
+        self.smax = None
+        self.t0 = self.t1 = None
+        self.how = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._proc = None
 
-    def start(self):
+    # ---- NVML
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            uuid = str(torch.cuda.get_device_properties(self.cuda_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except TypeError:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
         except Exception:
-            self.proc = None
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            idx = int(ids[self.cuda_index]) if ids and all(v.strip().isdigit() for v in ids) else self.cuda_index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _nvml_loop(self, pynvml, h):
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                bits = int(reasons_fn(h))
+                self.samples.append((time.perf_counter(), mhz, {n for b, n in self.REASONS.items() if bits & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
+    # ---- nvidia-smi fallback
+    def _smi_loop(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
+        for line in self._proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                smax = float(parts[2])
+                mhz = float(parts[1])
+                self.smax = float(parts[2])
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+            self.samples.append((time.perf_counter(), mhz,
+                                 {n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")}))
+
+    def start(self):
+        try:
+            pynvml, h = self._nvml_handle()
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._nvml_loop, args=(pynvml, h), daemon=True)
+            self.how = "nvml"
+        except Exception:
+            try:
+                self._proc = subprocess.Popen(
+                    ["nvidia-smi", "-i", str(self.cuda_index), "--query-gpu=" + self.Q,
+                     "--format=csv,noheader,nounits", "-lms", "20"],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self._thread = threading.Thread(target=self._smi_loop, daemon=True)
+                self.how = "nvidia-smi"
+            except Exception:
+                self._thread = None
+        if self._thread is not None:
+            self._thread.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
+                    "source": "unavailable (neither NVML nor nvidia-smi)"}
+        self._stop.set()
+        if self._proc is not None:
+            time.sleep(0.05)
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=2)
+            except Exception:
+                self._proc.kill()
+        self._thread.join(timeout=2)
+        inside = [s for s in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= s[0] <= self.t1]
+        window = "timed region"
+        if not inside:
+            inside, window = list(self.samples), "warm-up + timed region (timed region too short for a sample)"
+        sm = sorted(s[1] for s in inside)
+        reasons = sorted(set().union(*[s[2] for s in inside])) if inside else []
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                "samples": len(sm), "window": window, "source": self.how}
 
 
 # --------------------------------------------------------------------------
@@ -339,20 +401,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
     launches0 = _lib.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     _lib.kernel_timing(True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step_resident()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ktimes = _lib.kernel_timing(False)
     launches = _lib.launch_count() - launches0
