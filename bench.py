@@ -374,6 +374,7 @@ def main():
         """Synthesise this rank's frame block of one scene; on_frames(tensor [k,C,H,W]) consumes
         each finished group of frames (the decoder's place; the e2e leg copies them out)."""
         if algo == "gather":
+            js.prepare_clip(0, N - 1, lo, hi - lo)        # Euler chains once for this rank's frame block
             for b0 in range(lo, hi, nbuf):
                 nb = min(nbuf, hi - b0)
                 out = js.frames(0, N - 1, b0, nb, out=frame_buf[:nb])

@@ -173,6 +173,23 @@ int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tai
                     float alpha_lo, float alpha_hi, float* out, float* aux, float* mask,
                     void* workspace, size_t workspace_bytes, slr_stream_t stream);
 
+/* Clip table: slr_clip_plan split in two, so that the part that depends on the motion only --
+ * both Euler chains, the landing coordinates and the bin sizes of every frame -- is computed ONCE
+ * for a whole run of frames (one forward and one backward chain: t0+n-1-start and end-t0+1 steps
+ * for the run, where per-batch plans re-integrate from zero for every batch, as the reference
+ * does for every frame, euler_integration_manipulator.py:36) and the batches are cut from it:
+ *   slr_clip_table(motion, ..., t0, n_frames, table)              n_frames <= 4096, table of
+ *                                                                 slr_clip_table_bytes(H, W, n_frames)
+ *   slr_clip_bin(table, ..., table_frames, f0, n, workspace)      bins of frames f0 .. f0+n-1 of the
+ *                                                                 table (n <= 64) into a batch workspace
+ * after which slr_clip_expand / slr_clip_gather / slr_clip_heavy run on that workspace with
+ * t0 = (the table's t0) + f0 exactly as after slr_clip_plan. */
+size_t slr_clip_table_bytes(int64_t H, int64_t W, int n_frames);
+int slr_clip_table(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
+                   int n_frames, void* table, size_t table_bytes, slr_stream_t stream);
+int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, int64_t W, int table_frames,
+                 int f0, int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream);
+
 /* Diagnostics (a `_host` call: copies four counters to the host and synchronises `stream`).
  * After slr_clip_expand on `workspace`: stats[0] = flagged destination tiles of the batch (some
  * lane's source list was cut at the list depth), stats[1] = of those, tiles done entirely by

@@ -102,6 +102,31 @@ struct Workspace {
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Clip table: everything that depends on the motion only, for a run of consecutive frames
+// (slr_clip_table).  The batch workspace below embeds one for its own frames (slr_clip_plan).
+constexpr int kMaxTableFrames = 4096;
+struct ClipTable {
+    float* land;          // [n][2 dirs][2][P]   landing coordinates
+    unsigned* counts;     // [n][n_tiles]        entries per destination tile (zero again after the scan)
+    unsigned* offsets;    // [n][n_tiles + 1]    bin offsets
+    size_t bytes;
+};
+
+inline ClipTable carve_table(void* base, int64_t H, int64_t W, int n)
+{
+    using namespace slr;
+    const int64_t P = H * W;
+    const int64_t tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+    char* p = (char*)base;
+    size_t o = 0;
+    ClipTable t;
+    t.land = (float*)(p + o);        o += align_up(sizeof(float) * 4 * P * n);
+    t.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
+    t.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
+    t.bytes = o;
+    return t;
+}
+
 inline Workspace carve(void* base, int64_t H, int64_t W, int n)
 {
     using namespace slr;

@@ -262,6 +262,80 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
     return SLR_LAUNCH_STATUS();
 }
 
+namespace {
+
+// Euler chains, landing table, per-tile counts and bin offsets of frames t0 .. t0+n-1 into `tab`.
+int build_table(const float* motion, int64_t H, int64_t W, int start, int end, int t0, int n_frames,
+                const slr_host::ClipTable& tab, cudaStream_t s)
+{
+    const int64_t P = H * W;
+    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
+    const int n_tiles = tiles_x * tiles_y;
+    SLR_CUDA(cudaMemsetAsync(tab.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
+    const unsigned pblocks = (unsigned)((P + 255) / 256);
+    euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
+                                               tab.land, tab.counts, tiles_x, n_tiles);
+    bin_scan_kernel<<<n_frames, 1024, 0, s>>>(tab.counts, tab.offsets, n_tiles);
+    return SLR_LAUNCH_STATUS();
+}
+
+// Bins of frames f0 .. f0+n-1 of a table into the batch workspace `ws` (whose offsets are already in place).
+int fill_bins(const float* land, int64_t H, int64_t W, int n_frames, const Workspace& ws, cudaStream_t s)
+{
+    const int64_t P = H * W;
+    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
+    const int n_tiles = tiles_x * tiles_y;
+    SLR_CUDA(cudaMemsetAsync(ws.flag_count, 0, sizeof(unsigned), s));
+    SLR_CUDA(cudaMemsetAsync(ws.excess_count, 0, sizeof(unsigned), s));
+    const unsigned pblocks = (unsigned)((P + 255) / 256);
+    bin_fill_kernel<<<dim3(pblocks, n_frames), 256, 0, s>>>(land, ws.offsets, ws.counts, ws.ent,
+                                                            (int)H, (int)W, tiles_x, n_tiles, 8 * P);
+    return SLR_LAUNCH_STATUS();
+}
+
+}  // namespace
+
+extern "C" size_t slr_clip_table_bytes(int64_t H, int64_t W, int n_frames)
+{
+    if (H <= 0 || W <= 0 || n_frames <= 0 || n_frames > slr_host::kMaxTableFrames) return 0;
+    return slr_host::carve_table(nullptr, H, W, n_frames).bytes;
+}
+
+extern "C" int slr_clip_table(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
+                              int n_frames, void* table, size_t table_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(motion && table && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   n_frames > 0 && n_frames <= slr_host::kMaxTableFrames &&
+                   t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)table & 15) == 0,
+                   "slr_clip_table: bad arguments");
+    const slr_host::ClipTable tab = slr_host::carve_table(table, H, W, n_frames);
+    SLR_CHECK_ARGS(tab.bytes <= table_bytes, "slr_clip_table: table too small (see slr_clip_table_bytes)");
+    return build_table(motion, H, W, start, end, t0, n_frames, tab, (cudaStream_t)stream_);
+}
+
+extern "C" int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, int64_t W, int table_frames,
+                            int f0, int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(table && workspace && H > 0 && W > 0 && H * W < (1ll << 27) &&
+                   table_frames > 0 && table_frames <= slr_host::kMaxTableFrames &&
+                   n_frames > 0 && n_frames <= kMaxFrames && f0 >= 0 && f0 + n_frames <= table_frames &&
+                   ((uintptr_t)table & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+                   "slr_clip_bin: bad arguments");
+    const int64_t P = H * W;
+    const int n_tiles = (int)(((W + TW - 1) / TW) * ((H + TH - 1) / TH));
+    const slr_host::ClipTable tab = slr_host::carve_table(const_cast<void*>(table), H, W, table_frames);
+    SLR_CHECK_ARGS(tab.bytes <= table_bytes, "slr_clip_bin: table too small (see slr_clip_table_bytes)");
+    const Workspace ws = carve(workspace, H, W, n_frames);
+    SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_bin: workspace too small (see slr_clip_workspace_bytes)");
+    cudaStream_t s = (cudaStream_t)stream_;
+    // the batch's own copy of its bin offsets (expand / gather / heavy read them from the workspace);
+    // the fill cursors start at zero
+    SLR_CUDA(cudaMemcpyAsync(ws.offsets, tab.offsets + (size_t)f0 * (n_tiles + 1),
+                             sizeof(unsigned) * (size_t)(n_tiles + 1) * n_frames, cudaMemcpyDeviceToDevice, s));
+    SLR_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
+    return fill_bins(tab.land + (size_t)f0 * 4 * P, H, W, n_frames, ws, s);
+}
+
 extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
                              int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream_)
 {
@@ -269,22 +343,13 @@ extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int star
                    n_frames > 0 && n_frames <= kMaxFrames &&
                    t0 >= start && t0 + n_frames - 1 <= end + 1 && ((uintptr_t)workspace & 15) == 0,
                    "slr_clip_plan: bad arguments");
-    const int64_t P = H * W;
-    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
-    const int n_tiles = tiles_x * tiles_y;
     const Workspace ws = carve(workspace, H, W, n_frames);
     SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_plan: workspace too small (see slr_clip_workspace_bytes)");
     cudaStream_t s = (cudaStream_t)stream_;
-
-    SLR_CUDA(cudaMemsetAsync(ws.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
-    SLR_CUDA(cudaMemsetAsync(ws.flag_count, 0, sizeof(unsigned), s));
-    SLR_CUDA(cudaMemsetAsync(ws.excess_count, 0, sizeof(unsigned), s));
-    const unsigned pblocks = (unsigned)((P + 255) / 256);
-    euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
-                                               ws.land, ws.counts, tiles_x, n_tiles);
-    bin_scan_kernel<<<n_frames, 1024, 0, s>>>(ws.counts, ws.offsets, n_tiles);
-    bin_fill_kernel<<<dim3(pblocks, n_frames), 256, 0, s>>>(ws.land, ws.offsets, ws.counts, ws.ent,
-                                                            (int)H, (int)W, tiles_x, n_tiles, 8 * P);
-    return SLR_LAUNCH_STATUS();
+    // the table of exactly this batch lives in the workspace itself
+    slr_host::ClipTable tab;
+    tab.land = ws.land; tab.counts = ws.counts; tab.offsets = ws.offsets; tab.bytes = 0;
+    const int rc = build_table(motion, H, W, start, end, t0, n_frames, tab, s);
+    if (rc) return rc;
+    return fill_bins(ws.land, H, W, n_frames, ws, s);       // bin_scan left the counts at zero: they are the cursors
 }
-

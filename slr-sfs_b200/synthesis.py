@@ -91,6 +91,7 @@ class JointSplat:
         self._zsub = None
         self._scene = None
         self._prepared = None          # event: zsub and the scene buffer are built
+        self._table = None             # cached clip table (see _clip_table)
 
     def _wait_inputs(self, stream):
         if self._inputs_ready is not None:
@@ -152,15 +153,48 @@ class JointSplat:
             ws.record_stream(side)
         return ws, ws.numel() * 4
 
+    def _clip_table(self, start, end, t0, n, side):
+        """The motion-only part of the plan (slr_clip_table: both Euler chains, landing coordinates,
+        bin sizes) for frames t0 .. t0+n-1 of the clip [start, end], built once on `side` and cached:
+        later calls for any sub-range of it only cut their batches from it (slr_clip_bin)."""
+        tb = self._table
+        if tb is not None and tb["clip"] == (start, end) and tb["t0"] <= t0 and t0 + n <= tb["t0"] + tb["n"]:
+            return tb
+        nbytes = _lib.load().slr_clip_table_bytes(self.H, self.W, n)
+        buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        buf.record_stream(side)
+        with torch.cuda.stream(side):
+            self._wait_inputs(side)
+            _lib.call("slr_clip_table", _lib.ptr(self.motion), self.H, self.W, start, end, t0, n,
+                      _lib.ptr(buf), nbytes, _lib.current_stream(self.device))
+            ready = torch.cuda.Event()
+            ready.record(side)
+        tb = self._table = {"clip": (start, end), "t0": t0, "n": n, "buf": buf, "bytes": nbytes,
+                            "ready": ready, "stream": side}
+        return tb
+
+    def prepare_clip(self, start, end, t0=None, n=None):
+        """Optional hint: the caller is going to ask for frames t0 .. t0+n-1 (default: the whole
+        clip) of [start, end], in any number of frames() / frame() calls.  Builds the clip table
+        for that range now, so that every Euler chain is integrated once for the range instead of
+        once per call."""
+        t0 = start if t0 is None else t0
+        n = end - t0 + 1 if n is None else n
+        with torch.cuda.device(self.device):
+            st = self._shared_state()
+            side = st["side"] if self.pipeline else torch.cuda.current_stream(self.device)
+            self._clip_table(start, end, t0, n, side)
+
     def frames(self, start, end, t0, n, out=None, want_aux=False, want_mask=False, alpha_clamp=(0.0, 1.0)):
         """Frames t0..t0+n-1 of the clip [start, end]: gen_fs [n,C,H,W]
         (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W]).  Asynchronous like any
         torch op: results are ordered on the current stream.
 
-        Work is issued in batches of ``self.batch`` frames.  With ``self.pipeline`` the
-        latency-bound part (scene prep, slr_clip_plan, slr_clip_expand) goes to a side stream
-        with its own workspace and runs beside the bandwidth-bound gather of the previous
-        batch -- of this call or of an earlier one (the previous scene)."""
+        The Euler chains of the requested range are integrated once (slr_clip_table, cached: see
+        prepare_clip); the rest is issued in batches of ``self.batch`` frames.  With
+        ``self.pipeline`` the latency-bound part (scene prep, table, slr_clip_bin, slr_clip_expand)
+        goes to a side stream with its own workspace and runs beside the bandwidth-bound gather of
+        the previous batch -- of this call or of an earlier one (the previous scene)."""
         H, W, C = self.H, self.W, self.C
         if out is None:
             out = torch.empty(n, C, H, W, dtype=torch.float32, device=self.device)
@@ -175,6 +209,9 @@ class JointSplat:
             side = st["side"] if two_streams else main
             self._allocate(scene=True)
             scene = self._scene
+            tb = self._clip_table(start, end, t0, n, side)
+            if tb["stream"] != side:
+                tb["buf"].record_stream(side)
             for (b0, nb) in batches:
                 slot = st["turn"] = st["turn"] ^ 1
                 args = (C, self.n_tail, H, W, start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1])
@@ -182,9 +219,10 @@ class JointSplat:
                 with torch.cuda.stream(side):
                     for ev in st["free"].get(slot, ()):
                         side.wait_event(ev)
+                    side.wait_event(tb["ready"])
                     self._prepare()
                     s = _lib.current_stream(self.device)
-                    _lib.call("slr_clip_plan", _lib.ptr(self.motion), H, W, start, end, t0 + b0, nb,
+                    _lib.call("slr_clip_bin", _lib.ptr(tb["buf"]), tb["bytes"], H, W, tb["n"], t0 + b0 - tb["t0"], nb,
                               _lib.ptr(ws), ws_bytes, s)
                     _lib.call("slr_clip_expand", _lib.ptr(scene), _lib.ptr(self.motion), *args,
                               _lib.ptr(ws), ws_bytes, s)
@@ -208,6 +246,11 @@ class JointSplat:
         """gen_fs [1,C,H,W] for index = (start, t, end) -- the per-frame call of the
         reference's loop (test_v1_4eval_rawsize.py:233-239)."""
         start, mid, end = _index_triplet(index)
+        tb = self._table
+        if start <= mid <= end and (tb is None or tb["clip"] != (start, end)):
+            # the reference's loop asks for every t of the clip, one call each: integrate the
+            # chains for the whole clip on the first call instead of restarting them per frame
+            self.prepare_clip(start, end)
         return self.frames(start, end, mid, 1, **kw)
 
     # -- scatter variant: Euler x2 -> atomic scatter of both directions -> normalise

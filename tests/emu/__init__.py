@@ -64,7 +64,16 @@ class Scene:
         call("slr_scene_prep", p(self.feat), p(self.Z), p(self.zsub), p(self.tail), self.n_tail,
              p(self.scene), self.C, self.H, self.W, None)
 
-    def frames(self, start, end, t0, n, alpha_clamp=(0.0, 1.0), want_aux=False, want_mask=False, split=False):
+    def table(self, start, end, t0, n):
+        """slr_clip_table for frames t0 .. t0+n-1; returns the handle frames(..., table=) takes."""
+        nb = lib().slr_clip_table_bytes(self.H, self.W, n)
+        buf = aligned(nb)
+        buf[:] = 0x5A
+        call("slr_clip_table", p(self.motion), self.H, self.W, start, end, t0, n, p(buf), nb, None)
+        return dict(buf=buf, bytes=nb, t0=t0, n=n, start=start, end=end)
+
+    def frames(self, start, end, t0, n, alpha_clamp=(0.0, 1.0), want_aux=False, want_mask=False, split=False,
+               table=None):
         C, H, W = self.C, self.H, self.W
         out = np.full((n, C, H, W), np.nan, dtype=np.float32)
         aux = np.full((n, self.n_tail + 1, H, W), np.nan, dtype=np.float32) if want_aux else None
@@ -73,8 +82,12 @@ class Scene:
         ws = aligned(nb)
         ws[:] = 0xA5          # the library must not rely on a zeroed workspace
         args = (C, self.n_tail, H, W, start, end, t0, n, alpha_clamp[0], alpha_clamp[1])
-        if split:
-            call("slr_clip_plan", p(self.motion), H, W, start, end, t0, n, p(ws), nb, None)
+        if table is not None:
+            assert (table["start"], table["end"]) == (start, end)
+            call("slr_clip_bin", p(table["buf"]), table["bytes"], H, W, table["n"], t0 - table["t0"], n, p(ws), nb, None)
+        if split or table is not None:
+            if table is None:
+                call("slr_clip_plan", p(self.motion), H, W, start, end, t0, n, p(ws), nb, None)
             call("slr_clip_expand", p(self.scene), p(self.motion), *args, p(ws), nb, None)
             for entry in ("slr_clip_gather", "slr_clip_heavy"):
                 call(entry, p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)

@@ -154,6 +154,26 @@ def test_emu_gather_nonzero_start_split_calls_and_v1():
         assert rel_err(got[i:i + 1], want) <= TOL, t
 
 
+def test_emu_clip_table_batches_equal_per_batch_plans():
+    """slr_clip_table once for the clip + slr_clip_bin per batch == slr_clip_plan per batch
+    (same chains, continued instead of restarted)."""
+    H, W, C = 24, 72, 4
+    feat, Z, motion = _scene(H, W, C, "A", 7)
+    sc = emu.Scene(feat, Z, motion)
+    start, end = 1, 14
+    tab = sc.table(start, end, 3, 11)                       # frames 3..13 of the clip [1, 14]
+    for t0, n in ((3, 4), (7, 5), (12, 2), (5, 1)):
+        a = sc.frames(start, end, t0, n, table=tab)
+        b = sc.frames(start, end, t0, n, split=True)
+        assert np.array_equal(a, b), (t0, n)
+    want = oracle.joint_splat_baseline(feat, Z, motion, (start, 9, end))
+    assert rel_err(sc.frames(start, end, 9, 1, table=tab), want) <= TOL
+    # the last frame index the reference loop ever asks for (t = end) and a whole-clip table
+    tab = sc.table(start, end, start, end - start + 1)
+    want = oracle.joint_splat_baseline(feat, Z, motion, (start, end, end))
+    assert rel_err(sc.frames(start, end, end, 1, table=tab), want) <= TOL
+
+
 def test_emu_two_layer_aux_and_mask():
     from slr_sfs_b200 import workloads
     H, W, C, N = 24, 40, 4, 6
