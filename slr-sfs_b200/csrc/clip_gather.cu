@@ -25,6 +25,7 @@
 #include "clip_common.cuh"
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 namespace slr {
@@ -35,6 +36,9 @@ namespace slr {
 #ifndef SLR_GATHER_FRAMES
 #define SLR_GATHER_FRAMES 1            // default CTA shape of rowgather_kernel: frames x row pairs
 #define SLR_GATHER_PAIRS 4
+#endif
+#ifndef SLR_EXPAND_ATOMIC_CLAIM
+#define SLR_EXPAND_ATOMIC_CLAIM 1      // default claim mode of expand_kernel (1: atomicCAS, 0: store + re-read)
 #endif
 #ifndef SLR_EXPAND_MINBLOCKS
 #define SLR_EXPAND_MINBLOCKS 6
@@ -91,12 +95,23 @@ __host__ __device__ constexpr SlotRole slot_role(int k)
 
 // ---------------------------------------------------------------------------
 // expand_kernel
+// A canonical slot of a lane is claimed by the first source that asks for it; a second source
+// with the same (direction, row offset, east/west) -- the flow compresses there -- goes to the
+// lane's overflow slots.  Two ways to decide who is first:
+//   kAtomicClaim = true   atomicCAS on the slot's source field (one shared-memory atomic per pair
+//                         plus an atomicOr into the lane's occupancy mask);
+//   kAtomicClaim = false  the bin is walked in chunks of one entry per thread: every thread
+//                         writes its source into the slots it wants IF they are empty (plain
+//                         stores, some writer wins), barrier, then re-reads them: "mine" -> store
+//                         the weight, "someone else's" -> overflow.  No shared-memory atomics in
+//                         regular flow; slots claimed in earlier chunks are simply not empty.
 // ---------------------------------------------------------------------------
+template <bool kAtomicClaim>
 __global__ void __launch_bounds__(TILE, SLR_EXPAND_MINBLOCKS)
 expand_kernel(const GatherParams prm)
 {
     __shared__ uint4 tab[kSmemSlots * kCols];      // tab[slot * kCols + col] = (source, w_top, w_bottom, -)
-    __shared__ unsigned occ[kCols];                // used canonical slots (bit mask)
+    __shared__ unsigned occ[kCols];                // used canonical slots (bit mask; atomic claims only)
     __shared__ unsigned ovf[kCols];                // overflow slots in use (kCanon, kCanon + 1, ...)
     __shared__ unsigned excess_full;               // the global excess list ran out of room
 
@@ -116,32 +131,35 @@ expand_kernel(const GatherParams prm)
     if (tid == 0) excess_full = 0u;
     __syncthreads();
 
-    // one (destination pixel, source, weight) pair -> its lane's list
-    auto insert = [&](int lx, int ly, unsigned p, float w, unsigned dir, int dx, int dy) {
+    // a pair whose canonical slot belongs to another source: the lane's next overflow slot
+    auto spill = [&](int lx, int ly, unsigned p, float w) {
         const int col = (ly >> 1) * TW + lx, r = ly & 1;
-        const int s = canon_slot(dir, r - dy, dx);
-        uint4* cell = tab + s * kCols + col;
-        const unsigned old = atomicCAS(&cell->x, kEmpty, p);
-        if (old == kEmpty) atomicOr(&occ[col], 1u << s);
-        if (old == kEmpty || old == p) {
-            // the slot is this source's: the other row's corner of the same source shares it
-            (r ? cell->z : cell->y) = __float_as_uint(w);
+        const int so = kCanon + (int)atomicAdd(&ovf[col], 1u);
+        const uint4 e = make_uint4(p, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, 0u);
+        if (so < kSmemSlots) {
+            tab[so * kCols + col] = e;
+        } else if (so < kListDepth) {     // deeper than the shared table: straight to its place in the global list
+            __stcg(lists_tile + ((int64_t)(ly >> 1) * kListDepth + so) * 32 + lx, e);
         } else {
-            const int so = kCanon + (int)atomicAdd(&ovf[col], 1u);
-            const uint4 e = make_uint4(p, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, 0u);
-            if (so < kSmemSlots) {
-                tab[so * kCols + col] = e;
-            } else if (so < kListDepth) {     // deeper than the shared table: straight to its place in the global list
-                __stcg(lists_tile + ((int64_t)(ly >> 1) * kListDepth + so) * 32 + lx, e);
-            } else {
-                // deeper than the lists (a convergence point): this one pair is added by an fp32
-                // reduction at L2 after the gather (heavy_scatter_kernel)
-                const unsigned i = atomicAdd(prm.excess_count, 1u);
-                const unsigned dpix = (unsigned)((ty * TH + ly) * prm.W + tx * TW + lx);
-                if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, p, __float_as_uint(w), (unsigned)f));
-                else excess_full = 1u;
-            }
+            // deeper than the lists (a convergence point): this one pair is added by an fp32
+            // reduction at L2 after the gather (heavy_excess_kernel)
+            const unsigned i = atomicAdd(prm.excess_count, 1u);
+            const unsigned dpix = (unsigned)((ty * TH + ly) * prm.W + tx * TW + lx);
+            if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, p, __float_as_uint(w), (unsigned)f));
+            else excess_full = 1u;
         }
+    };
+    auto cell_of = [&](int lx, int ly, unsigned dir, int dx, int dy) {
+        return tab + canon_slot(dir, (ly & 1) - dy, dx) * kCols + (ly >> 1) * TW + lx;
+    };
+    // one (destination pixel, source, weight) pair -> its lane's list, claim by atomicCAS
+    auto insert = [&](int lx, int ly, unsigned p, float w, unsigned dir, int dx, int dy) {
+        uint4* cell = cell_of(lx, ly, dir, dx, dy);
+        const unsigned old = atomicCAS(&cell->x, kEmpty, p);
+        if (old == kEmpty) atomicOr(&occ[(ly >> 1) * TW + lx], 1u << canon_slot(dir, (ly & 1) - dy, dx));
+        // the slot is this source's: the other row's corner of the same source shares it
+        if (old == kEmpty || old == p) ((ly & 1) ? cell->z : cell->y) = __float_as_uint(w);
+        else spill(lx, ly, p, w);
     };
 
     {   // a destination pixel with exactly zero motion receives itself with weight a + (1 - a)
@@ -150,25 +168,73 @@ expand_kernel(const GatherParams prm)
         const int X = tx * TW + lx, Y = ty * TH + ly;
         if (X < prm.W && Y < prm.H) {
             const int64_t pix = (int64_t)Y * prm.W + X;
-            if (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f)
-                insert(lx, ly, (unsigned)pix, a_f + a_b, 0u, 0, 0);
+            if (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f) {
+                if (kAtomicClaim) {
+                    insert(lx, ly, (unsigned)pix, a_f + a_b, 0u, 0, 0);
+                } else {    // nothing else has been inserted yet, and no two pixels share a slot: it is theirs
+                    uint4* cell = cell_of(lx, ly, 0u, 0, 0);
+                    cell->x = (unsigned)pix;
+                    ((ly & 1) ? cell->z : cell->y) = __float_as_uint(a_f + a_b);
+                }
+            }
         }
     }
-    for (unsigned e = beg + tid; e < end; e += TILE) {
-        const float4 en = __ldcs(ent + e);
-        const unsigned pd = __float_as_uint(en.x);
-        const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
-        const unsigned dir = pd >> 31;
-        const float a = dir ? a_b : a_f;
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-            const float wa = fp.w[k] * a;
-            if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
-                insert(lx, ly, pd & ~kDirBit, wa, dir, k & 1, k >> 1);
+    if (kAtomicClaim) {
+        for (unsigned e = beg + tid; e < end; e += TILE) {
+            const float4 en = __ldcs(ent + e);
+            const unsigned pd = __float_as_uint(en.x);
+            const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+            const unsigned dir = pd >> 31;
+            const float a = dir ? a_b : a_f;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                const float wa = fp.w[k] * a;
+                if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                    insert(lx, ly, pd & ~kDirBit, wa, dir, k & 1, k >> 1);
+            }
         }
+        __syncthreads();
+    } else {
+        __syncthreads();                 // the static pixels' slots are in place
+        for (unsigned base = beg; base < end; base += TILE) {       // block-uniform trip count
+            const unsigned e = base + tid;
+            const bool have = e < end;
+            Footprint fp;
+            unsigned p = 0u, dir = 0u, valid = 0u;
+            float a = 0.0f;
+            if (have) {
+                const float4 en = __ldcs(ent + e);
+                const unsigned pd = __float_as_uint(en.x);
+                fp = footprint_at(en.y, en.z, prm.H, prm.W);
+                p = pd & ~kDirBit;
+                dir = pd >> 31;
+                a = dir ? a_b : a_f;
+                #pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && fp.w[k] * a != 0.0f) {
+                        valid |= 1u << k;
+                        uint4* cell = cell_of(lx, ly, dir, k & 1, k >> 1);
+                        if (cell->x == kEmpty) cell->x = p;          // plain store: one of the askers wins
+                    }
+                }
+            }
+            __syncthreads();
+            // Slots this chunk asked for are no longer empty, so the next chunk's claims (no barrier
+            // in between) cannot disturb the re-reads below.
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!(valid >> k & 1u)) continue;
+                const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                const float wa = fp.w[k] * a;
+                uint4* cell = cell_of(lx, ly, dir, k & 1, k >> 1);
+                if (cell->x == p) ((ly & 1) ? cell->z : cell->y) = __float_as_uint(wa);
+                else spill(lx, ly, p, wa);
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const bool deep = tid < kCols && kCanon + (int)ovf[tid] > kListDepth;
     const int any_deep = __syncthreads_or(deep);
     const unsigned flag = excess_full ? 2u : (any_deep ? 1u : 0u);
@@ -179,7 +245,13 @@ expand_kernel(const GatherParams prm)
     if (flag == 2u || tid >= kCols) return;
 
     // write the lists out, slot-major per row pair
-    const unsigned my_occ = occ[tid];
+    unsigned my_occ = 0u;
+    if (kAtomicClaim) {
+        my_occ = occ[tid];
+    } else {
+        #pragma unroll
+        for (int k = 0; k < kCanon; ++k) my_occ |= (tab[k * kCols + tid].x != kEmpty ? 1u : 0u) << k;
+    }
     const int n_ovf = min((int)ovf[tid], kListDepth - kCanon);     // the rest is in the excess list
     const int my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz(my_occ);    // slots [0, my_hi) may be used
     const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
@@ -630,6 +702,15 @@ GatherShape gather_shape()
     return g;
 }
 
+// How expand_kernel claims canonical slots: SLR_EXPAND_CLAIM = "atomic" | "store" (see the kernel).
+bool expand_claims_atomically()
+{
+    const char* e = getenv("SLR_EXPAND_CLAIM");
+    if (e && strcmp(e, "store") == 0) return false;
+    if (e && strcmp(e, "atomic") == 0) return true;
+    return SLR_EXPAND_ATOMIC_CLAIM != 0;
+}
+
 template <int F, int R>
 void launch_rowgather(const GatherParams& prm, int n_tail, cudaStream_t s)
 {
@@ -650,7 +731,8 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
                                nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
-    expand_kernel<<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    if (expand_claims_atomically()) expand_kernel<true><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    else expand_kernel<false><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
     return SLR_LAUNCH_STATUS();
 }
 

@@ -16,6 +16,13 @@ emu = pytest.importorskip("emu", reason="tests/emu")
 TOL = 1e-4
 
 
+@pytest.fixture(params=["atomic", "store"], autouse=True)
+def expand_claim_mode(request, monkeypatch):
+    """Every test runs with both ways expand_kernel claims list slots (SLR_EXPAND_CLAIM)."""
+    monkeypatch.setenv("SLR_EXPAND_CLAIM", request.param)
+    return request.param
+
+
 def _rng(seed):
     return np.random.default_rng(seed)
 
