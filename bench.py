@@ -367,19 +367,29 @@ def main():
     n_mine = hi - lo
     # frames requested per frames() call: several batches, so that the library can overlap the
     # index building of one batch with the gather of the previous one
-    nbuf = min(n_mine, 4 * (args.batch or pkg.JointSplat.batch))
-    frame_buf = torch.empty(nbuf, C, H, W, dtype=torch.float32, device=dev) if algo == "gather" else None
+    batch = args.batch or pkg.JointSplat.batch
+    nbuf = min(n_mine, 4 * batch)
+    # two output buffers: the consumer of one group of frames (the e2e leg's D2H copy) runs beside
+    # the synthesis of the next group
+    frame_bufs = [torch.empty(nbuf, C, H, W, dtype=torch.float32, device=dev) for _ in range(2)] if algo == "gather" else None
+    buf_free = [None, None]          # events after which a buffer may be overwritten
 
-    def synth_block(js, on_frames=None):
-        """Synthesise this rank's frame block of one scene; on_frames(tensor [k,C,H,W]) consumes
-        each finished group of frames (the decoder's place; the e2e leg copies them out)."""
+    def synth_block(js, on_frames=None, chunk=None):
+        """Synthesise this rank's frame block of one scene in groups of `chunk` frames;
+        on_frames(tensor [k,C,H,W]) consumes each finished group (the decoder's place; the e2e leg
+        copies them out) and may return an event that says when the group's buffer is free again."""
         if algo == "gather":
+            chunk = min(chunk or nbuf, nbuf)
             js.prepare_clip(0, N - 1, lo, hi - lo)        # Euler chains once for this rank's frame block
-            for b0 in range(lo, hi, nbuf):
-                nb = min(nbuf, hi - b0)
-                out = js.frames(0, N - 1, b0, nb, out=frame_buf[:nb])
+            for i, b0 in enumerate(range(lo, hi, chunk)):
+                nb = min(chunk, hi - b0)
+                slot = i & 1
+                if buf_free[slot] is not None:
+                    torch.cuda.current_stream().wait_event(buf_free[slot])
+                    buf_free[slot] = None
+                out = js.frames(0, N - 1, b0, nb, out=frame_bufs[slot][:nb])
                 if on_frames is not None:
-                    on_frames(out)
+                    buf_free[slot] = on_frames(out)
         else:
             for t in range(lo, hi):
                 out = js.frame_scatter((0, t, N - 1))
@@ -457,8 +467,7 @@ def main():
                         state["k"] += 1
                     copied = torch.cuda.Event()
                     copied.record()
-                # the frame buffer is reused by the next batch: do not overwrite before it is copied out
-                torch.cuda.current_stream().wait_event(copied)
+                return copied         # the group's buffer must not be overwritten before this
 
             for s in range(world):
                 if world > 1:
@@ -467,7 +476,7 @@ def main():
                         dist.broadcast(t, src=s)
                 else:
                     sc = mine
-                synth_block(make_joint(*sc), copy_out)
+                synth_block(make_joint(*sc), copy_out, chunk=batch)
             copy_stream.synchronize()
 
         for _ in range(min(args.warmup, 1)):
@@ -490,7 +499,8 @@ def main():
                "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
                "steps": steps_e2e,
                "note": "per step: pinned-host features+Z+motion -> device (+ NCCL broadcast when N>1), every "
-                       "synthesised [C,H,W] fp32 frame -> pinned host ring (3 slots) on a copy stream"}
+                       "synthesised [C,H,W] fp32 frame -> pinned host ring (3 slots) on a copy stream, beside the synthesis "
+                       "of the next group of frames (two device buffers)"}
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()

@@ -715,9 +715,16 @@ template <int F, int R>
 void launch_rowgather(const GatherParams& prm, int n_tail, cudaStream_t s)
 {
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)(kPairsPerTile / R) * (unsigned)((prm.n_frames + F - 1) / F);
-    if (n_tail == 0) rowgather_kernel<0, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
-    else if (n_tail == 1) rowgather_kernel<1, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
-    else rowgather_kernel<2, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    if (n_tail == 0) {
+        slr_host::prefer_carveout(rowgather_kernel<0, F, R>);
+        rowgather_kernel<0, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    } else if (n_tail == 1) {
+        slr_host::prefer_carveout(rowgather_kernel<1, F, R>);
+        rowgather_kernel<1, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    } else {
+        slr_host::prefer_carveout(rowgather_kernel<2, F, R>);
+        rowgather_kernel<2, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    }
 }
 
 }  // namespace
@@ -731,8 +738,13 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
                                nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
-    if (expand_claims_atomically()) expand_kernel<true><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
-    else expand_kernel<false><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    if (expand_claims_atomically()) {
+        slr_host::prefer_carveout(expand_kernel<true>);
+        expand_kernel<true><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    } else {
+        slr_host::prefer_carveout(expand_kernel<false>);
+        expand_kernel<false><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    }
     return SLR_LAUNCH_STATUS();
 }
 

@@ -19,6 +19,8 @@ Two algorithms, same results up to fp32 summation order:
   * ``frame_scatter``        -- atomic scatter + normalise (csrc/splat_ops.cu), the
                                 design BASELINE.json sketches, kept as measured baseline.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -60,7 +62,7 @@ class JointSplat:
 
     #: frames per slr_clip_frames launch (bigger batches amortise the Euler chains,
     #: smaller ones keep the landing table and the bins inside the 126 MB L2)
-    batch = 12
+    batch = int(os.environ.get("SLR_BATCH", "12"))
     #: overlap plan + expand of the next batch with the gather of the current one (two streams)
     pipeline = True
 
@@ -139,7 +141,9 @@ class JointSplat:
     def _shared_state(self):
         st = JointSplat._shared.get(self.device)
         if st is None:
-            st = JointSplat._shared[self.device] = {"side": torch.cuda.Stream(device=self.device),
+            # SLR_SIDE_PRIORITY=-1: the side stream's CTAs are scheduled ahead of the gather's
+            prio = int(os.environ.get("SLR_SIDE_PRIORITY", "0"))
+            st = JointSplat._shared[self.device] = {"side": torch.cuda.Stream(device=self.device, priority=prio),
                                                     "ws": {}, "free": {}, "turn": 0}
         return st
 

@@ -54,7 +54,7 @@ def host_pkg(monkeypatch):
     monkeypatch.setattr(synthesis, "_req", lambda t, name: t.contiguous())
     main = _Stream()
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: main)
-    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None, priority=0: _Stream())
     monkeypatch.setattr(torch.cuda, "Event", _Event)
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
