@@ -35,6 +35,7 @@ def run(H, W, C=64, N=60, two_layer=False, batch=12, reps=3):
     def clip():
         js = pkg.JointSplat(feat, Z, m, tail=tail)
         js.batch = batch
+        js.prepare_clip(0, N - 1)
         for b0 in range(0, N, nbuf):
             nb = min(nbuf, N - b0)
             js.frames(0, N - 1, b0, nb, out=out[:nb], want_aux=two_layer, want_mask=two_layer, alpha_clamp=clamp)
