@@ -10,7 +10,7 @@ t0=$(date +%s)
 stamp() { echo "$1 rc=$2 t=$(( $(date +%s) - t0 ))s" >> $S; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 
-timeout 240 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/pytest_gpu.log 2>&1; stamp pytest_gpu $?
+timeout 300 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/pytest_gpu.log 2>&1; stamp pytest_gpu $?
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; stamp smoke $?
 timeout 150 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; stamp bench_default $?
 timeout 150 python profiles/sweep_variants.py > gpurun_out/sweep_variants.jsonl 2> gpurun_out/sweep_variants.err; stamp sweep $?
@@ -27,8 +27,8 @@ try:
 except Exception:
     pass
 if best:
-    print("export SLR_GATHER_SHAPE=%s SLR_EXPAND_CLAIM=%s SLR_SMEM_CARVEOUT=%s SLR_SIDE_PRIORITY=%s SLR_BATCH=%s"
-          % (best["shape"], best["claim"], best["carveout"], best["priority"], best["batch"]))
+    print("export SLR_GATHER_SHAPE=%s SLR_EXPAND_CLAIM=%s SLR_SMEM_CARVEOUT=%s SLR_SIDE_PRIORITY=%s SLR_BATCH=%s SLR_GATHER_PAD_SMEM=%s"
+          % (best["shape"], best["claim"], best["carveout"], best["priority"], best["batch"], best["pad"]))
 PY
 cat gpurun_out/best_env.sh >> $S
 source gpurun_out/best_env.sh

@@ -5,6 +5,7 @@ reads SLR_GATHER_SHAPE / SLR_EXPAND_CLAIM per call, the batch is a JointSplat at
     SLR_GATHER_SHAPE   CTA shape of rowgather_kernel, frames x row pairs   (1x4, 2x4, 4x4, 2x2, 4x1)
     SLR_EXPAND_CLAIM   how expand_kernel claims list slots                 (atomic, store)
     SLR_SMEM_CARVEOUT  shared-memory carve-out all clip kernels ask for, %  (-1 = driver default)
+    SLR_GATHER_PAD_SMEM unused dynamic shared memory per gather CTA (caps its CTAs per SM under a carve-out)
     SLR_SIDE_PRIORITY  priority of the side stream (table / bins / expand)  (0, -1 = high)
     batch              frames per expand / gather launch
 
@@ -29,6 +30,7 @@ from slr_sfs_b200 import _lib, workloads
 H, W, C, N = 768, 1024, 64, 60
 DEFAULT = {"shape": os.environ.get("SLR_GATHER_SHAPE", "1x4"), "claim": os.environ.get("SLR_EXPAND_CLAIM", "atomic"),
            "carveout": int(os.environ.get("SLR_SMEM_CARVEOUT", "-1")), "priority": int(os.environ.get("SLR_SIDE_PRIORITY", "0")),
+           "pad": int(os.environ.get("SLR_GATHER_PAD_SMEM", "0")),
            "batch": pkg.JointSplat.batch}
 
 
@@ -36,6 +38,7 @@ def apply(v):
     os.environ["SLR_GATHER_SHAPE"] = v["shape"]
     os.environ["SLR_EXPAND_CLAIM"] = v["claim"]
     os.environ["SLR_SMEM_CARVEOUT"] = str(v["carveout"])
+    os.environ["SLR_GATHER_PAD_SMEM"] = str(v["pad"])
     if os.environ.get("SLR_SIDE_PRIORITY") != str(v["priority"]):
         os.environ["SLR_SIDE_PRIORITY"] = str(v["priority"])
         torch.cuda.synchronize()
@@ -106,6 +109,14 @@ def main():
                 continue
             fps = measure(v)
             emit(dict(v, frames_per_s=fps, what="overlap"))
+            if fps > top * 1.005:
+                top, best = fps, v
+    # cap the gather at 3 CTAs per SM so that a side-stream CTA fits beside it
+    for carve, pad in ((50, 33 << 10), (50, 28 << 10), (75, 40 << 10), (75, 33 << 10)):
+        for prio in (0, -1):
+            v = dict(best, carveout=carve, pad=pad, priority=prio)
+            fps = measure(v)
+            emit(dict(v, frames_per_s=fps, what="room for the side stream"))
             if fps > top * 1.005:
                 top, best = fps, v
     fps = measure(best, steps=20)

@@ -37,6 +37,9 @@ namespace slr {
 #define SLR_GATHER_FRAMES 1            // default CTA shape of rowgather_kernel: frames x row pairs
 #define SLR_GATHER_PAIRS 4
 #endif
+#ifndef SLR_GATHER_PAD_SMEM
+#define SLR_GATHER_PAD_SMEM 0          // see launch_rowgather()
+#endif
 #ifndef SLR_EXPAND_ATOMIC_CLAIM
 #define SLR_EXPAND_ATOMIC_CLAIM 1      // default claim mode of expand_kernel (1: atomicCAS, 0: store + re-read)
 #endif
@@ -715,15 +718,20 @@ template <int F, int R>
 void launch_rowgather(const GatherParams& prm, int n_tail, cudaStream_t s)
 {
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)(kPairsPerTile / R) * (unsigned)((prm.n_frames + F - 1) / F);
+    // SLR_GATHER_PAD_SMEM: unused dynamic shared memory per CTA (<= 48 KB).  With a non-zero carve-out
+    // it caps how many gather CTAs an SM takes, which leaves registers and shared memory for the
+    // side stream's CTAs (the gather alone fills the register file).
+    const char* e = getenv("SLR_GATHER_PAD_SMEM");
+    const size_t pad = e ? (size_t)std::min(std::max(atoi(e), 0), 48 << 10) : (size_t)SLR_GATHER_PAD_SMEM;
     if (n_tail == 0) {
         slr_host::prefer_carveout(rowgather_kernel<0, F, R>);
-        rowgather_kernel<0, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+        rowgather_kernel<0, F, R><<<grid, 32 * F * R, pad, s>>>(prm);
     } else if (n_tail == 1) {
         slr_host::prefer_carveout(rowgather_kernel<1, F, R>);
-        rowgather_kernel<1, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+        rowgather_kernel<1, F, R><<<grid, 32 * F * R, pad, s>>>(prm);
     } else {
         slr_host::prefer_carveout(rowgather_kernel<2, F, R>);
-        rowgather_kernel<2, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+        rowgather_kernel<2, F, R><<<grid, 32 * F * R, pad, s>>>(prm);
     }
 }
 
