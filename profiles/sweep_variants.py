@@ -30,7 +30,7 @@ from slr_sfs_b200 import _lib, workloads
 H, W, C, N = 768, 1024, 64, 60
 DEFAULT = {"shape": os.environ.get("SLR_GATHER_SHAPE", "1x4"), "claim": os.environ.get("SLR_EXPAND_CLAIM", "atomic"),
            "carveout": int(os.environ.get("SLR_SMEM_CARVEOUT", "-1")), "priority": int(os.environ.get("SLR_SIDE_PRIORITY", "0")),
-           "pad": int(os.environ.get("SLR_GATHER_PAD_SMEM", "0")),
+           "pad": int(os.environ.get("SLR_GATHER_PAD_SMEM", "0")), "main_priority": 0,
            "batch": pkg.JointSplat.batch}
 
 
@@ -50,6 +50,13 @@ def main():
     feat, Z, m = feat.cuda(), Z.cuda(), m.cuda()
     bufs = [torch.empty(48, C, H, W, device="cuda") for _ in range(2)]
 
+    high = torch.cuda.Stream(priority=-1)
+
+    def main_stream(v):
+        # main_priority -1: the caller's stream (the gather) is a high-priority one, so that the side
+        # stream's CTAs only fill what the gather leaves free
+        return torch.cuda.stream(high if v.get("main_priority") else torch.cuda.current_stream())
+
     def clip(v, pipeline=True):
         js = pkg.JointSplat(feat, Z, m, inputs_event=False)
         js.batch, js.pipeline = v["batch"], pipeline
@@ -60,19 +67,20 @@ def main():
 
     def measure(v, steps=10, reps=2, pipeline=True):
         apply(v)
-        for _ in range(2):
-            clip(v, pipeline)
         best = None
-        for _ in range(reps):
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(steps):
+        with main_stream(v):
+            for _ in range(2):
                 clip(v, pipeline)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / (steps * N)
-            best = ms if best is None else min(best, ms)
+            for _ in range(reps):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    clip(v, pipeline)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / (steps * N)
+                best = ms if best is None else min(best, ms)
         return 1000.0 / best
 
     def kernels(v):
@@ -87,38 +95,49 @@ def main():
     def emit(row):
         print(json.dumps(row), flush=True)
 
+    stages = os.environ.get("SWEEP_STAGES", "knobs,overlap,room,main").split(",")
     base = measure(DEFAULT)
     emit(dict(DEFAULT, frames_per_s=base, what="default", kernels_ms_per_frame=kernels(DEFAULT)))
-    best = dict(DEFAULT)
-    for knob, values in (("shape", ["2x4", "4x4", "2x2", "4x1"]), ("claim", ["store"]), ("batch", [6, 8, 10, 16, 20]),
-                         ("carveout", [25, 50, 75]), ("priority", [-1])):
-        top = base
-        for val in values:
-            v = dict(DEFAULT, **{knob: val})
-            fps = measure(v)
-            emit(dict(v, frames_per_s=fps, what=knob))
-            if fps > top * 1.005:
-                top, best[knob] = fps, val
-    # the overlap knobs interact: carve-out x priority on top of the best shape / claim / batch
-    top = measure(best)
-    emit(dict(best, frames_per_s=top, what="best of each"))
-    for carve in (-1, 25, 50, 75):
-        for prio in (0, -1):
-            v = dict(best, carveout=carve, priority=prio)
-            if v == best:
-                continue
-            fps = measure(v)
-            emit(dict(v, frames_per_s=fps, what="overlap"))
-            if fps > top * 1.005:
-                top, best = fps, v
-    # cap the gather at 3 CTAs per SM so that a side-stream CTA fits beside it
-    for carve, pad in ((50, 33 << 10), (50, 28 << 10), (75, 40 << 10), (75, 33 << 10)):
-        for prio in (0, -1):
-            v = dict(best, carveout=carve, pad=pad, priority=prio)
-            fps = measure(v)
-            emit(dict(v, frames_per_s=fps, what="room for the side stream"))
-            if fps > top * 1.005:
-                top, best = fps, v
+    best, top = dict(DEFAULT), base
+    if "knobs" in stages:
+        for knob, values in (("shape", ["2x4", "4x4", "2x2", "4x1"]), ("claim", ["store"]), ("batch", [6, 8, 10, 16, 20]),
+                             ("carveout", [25, 50, 75]), ("priority", [-1])):
+            knob_top = base
+            for val in values:
+                v = dict(DEFAULT, **{knob: val})
+                fps = measure(v)
+                emit(dict(v, frames_per_s=fps, what=knob))
+                if fps > knob_top * 1.005:
+                    knob_top, best[knob] = fps, val
+        top = measure(best)
+        emit(dict(best, frames_per_s=top, what="best of each"))
+    if "overlap" in stages:      # the overlap knobs interact: carve-out x priority on top of the best shape / claim / batch
+        for carve in (-1, 25, 50, 75):
+            for prio in (0, -1):
+                v = dict(best, carveout=carve, priority=prio)
+                if v == best:
+                    continue
+                fps = measure(v)
+                emit(dict(v, frames_per_s=fps, what="overlap"))
+                if fps > top * 1.005:
+                    top, best = fps, v
+    if "room" in stages:         # cap the gather at 3 CTAs per SM so that a side-stream CTA fits beside it
+        for carve, pad in ((50, 33 << 10), (50, 28 << 10), (75, 40 << 10), (75, 33 << 10)):
+            for prio in (0, -1):
+                v = dict(best, carveout=carve, pad=pad, priority=prio)
+                fps = measure(v)
+                emit(dict(v, frames_per_s=fps, what="room for the side stream"))
+                if fps > top * 1.005:
+                    top, best = fps, v
+    if "main" in stages:         # the gather's stream at high priority, for the default and the multi-frame CTA shapes
+        for shape in ("1x4", "2x2", "4x1"):
+            for mp in (0, -1):
+                for batch in (12, 16):
+                    v = dict(DEFAULT, shape=shape, main_priority=mp, batch=batch)
+                    fps = measure(v)
+                    emit(dict(v, frames_per_s=fps, what="main stream priority"))
+                    if fps > top * 1.005:
+                        top, best = fps, v
     fps = measure(best, steps=20)
     again = measure(DEFAULT, steps=20)
     emit(dict(best, frames_per_s=fps, what="combined", kernels_ms_per_frame=kernels(best)))

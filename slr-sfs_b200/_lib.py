@@ -108,19 +108,21 @@ KERNELS_PER_CALL = {
 }
 _launches = 0
 _timing = None          # None, or list of (name, start_event, end_event)
+_timing_only = None     # None = every entry point, else the set of names to bracket
 
 
 def launch_count():
     return _launches
 
 
-def kernel_timing(enable):
-    """enable=True: start bracketing every entry-point call with CUDA events on the
-    current stream.  enable=False: stop, synchronise and return
+def kernel_timing(enable, only=None):
+    """enable=True: start bracketing every entry-point call (or just the ones named in `only`)
+    with CUDA events on the current stream.  enable=False: stop, synchronise and return
     {entry point: (total ms, calls)}."""
-    global _timing
+    global _timing, _timing_only
     if enable:
         _timing = []
+        _timing_only = None if only is None else set(only)
         return None
     import torch
     recs, _timing = _timing or [], None
@@ -151,7 +153,7 @@ _plain_call = call
 
 def call(name, *args):  # noqa: F811  (instrumented wrapper around the plain call)
     global _launches
-    if _timing is not None:
+    if _timing is not None and (_timing_only is None or name in _timing_only):
         import torch
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
