@@ -19,7 +19,9 @@
 //                     a source that feeds both (its north corners land on y, its south
 //                     corners on y+1) is loaded ONCE -- 12 loads instead of 16 per pixel pair
 //                     in regular flow.  Per channel group: <=12 independent LDG.128 in flight,
-//                     then the FMAs, then streaming stores.
+//                     then the FMAs, then streaming stores.  A CTA is 4 such warps: 2 row pairs of
+//                     one tile in 2 consecutive frames (their sources differ by one frame's
+//                     displacement, so they share lines in L1).
 //   heavy_*_kernel    tiles with a lane deeper than the lists hold (convergence zones of the
 //                     flow): per-pair fp32 reductions at L2, cost linear in pairs.
 #include "clip_common.cuh"
@@ -34,8 +36,8 @@ namespace slr {
 #define SLR_GATHER_MINBLOCKS 4         // resident 128-thread CTAs per SM the register budget is sized for
 #endif
 #ifndef SLR_GATHER_FRAMES
-#define SLR_GATHER_FRAMES 1            // default CTA shape of rowgather_kernel: frames x row pairs
-#define SLR_GATHER_PAIRS 4
+#define SLR_GATHER_FRAMES 2            // default CTA shape of rowgather_kernel: frames x row pairs
+#define SLR_GATHER_PAIRS 2             // (measured: 2x2 = 4x1 > 1x4 > 2x4 > 4x4, profiles/r01/sweep_variants.jsonl)
 #endif
 #ifndef SLR_GATHER_PAD_SMEM
 #define SLR_GATHER_PAD_SMEM 0          // see launch_rowgather()
@@ -272,11 +274,12 @@ expand_kernel(const GatherParams prm)
 
 // ---------------------------------------------------------------------------
 // rowgather_kernel
-// CTA = 4 warps = the 4 row pairs of one destination tile (vertically shared sources stay in
-// this SM's L1).  CTA order is frame-fastest: the CTAs resident at any moment work on the
-// SAME destination tiles of all frames of the batch; their source regions differ only by the
-// frame-to-frame displacement, so a source line is fetched from HBM once per batch and the
-// other frames hit it in L2 (one frame's features alone, 204 MB, exceed the 126 MB L2).
+// One warp per row pair; a CTA is F frames x R row pairs of one destination tile (template
+// parameters, default 2 x 2: vertically shared sources and the sources of the same rows in the
+// next frame stay in this SM's L1).  CTA order is frame-fastest: the CTAs resident at any moment
+// work on the SAME destination tiles of all frames of the batch; their source regions differ
+// only by the frame-to-frame displacement, so a source line is fetched from HBM once per batch
+// and the other frames hit it in L2 (one frame's features alone, 204 MB, exceed the 126 MB L2).
 // ---------------------------------------------------------------------------
 struct RowCtx {
     const char* G;        // group plane 0

@@ -78,7 +78,15 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False):
+def build(force=False, asan=False):
+    """asan=True: a second library instrumented with AddressSanitizer (load it in a process started
+    with LD_PRELOAD=libasan): the CPU stand-in for compute-sanitizer's memcheck."""
+    if asan:
+        build(force)
+        lib = LIB[:-3] + "_asan.so"
+        if force or not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(LIB):
+            _compile(lib, ["-fsanitize=address", "-fno-omit-frame-pointer"])
+        return lib
     if not force and not stale():
         return LIB
     os.makedirs(OUT, exist_ok=True)
@@ -91,13 +99,27 @@ def build(force=False):
         with open(dst, "w") as fh:
             fh.write('#line 1 "%s"\n' % cu + text)
         srcs.append(dst)
+    _compile(LIB, [])
+    return LIB
+
+
+def _compile(lib, extra):
+    srcs = [os.path.join(HERE, "emu_runtime.cpp")] + sorted(glob.glob(os.path.join(OUT, "*.emu.cpp")))
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing",
-           "-Wno-attributes", "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "include"), "-I", CSRC,
-           "-o", LIB] + srcs
+           "-Wno-attributes", "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "include"), "-I", CSRC] + extra + \
+          ["-o", lib] + srcs
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("emulation build failed:\n" + proc.stdout[-6000:])
-    return LIB
+
+
+def libasan():
+    """Path of the ASan runtime to LD_PRELOAD, or None."""
+    try:
+        path = subprocess.run(["gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    except OSError:
+        return None
+    return path if os.path.isabs(path) and os.path.exists(path) else None
 
 
 if __name__ == "__main__":
