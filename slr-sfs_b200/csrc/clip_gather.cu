@@ -617,12 +617,18 @@ heavy_excess_kernel(const GatherParams prm)
         for (int j = 0; j <= NT; ++j) red_add(sums + (int64_t)j * P, __ldg(prm.S + (int64_t)j * sstride + e.y) * w);
         float* out = prm.out + (int64_t)f * prm.C * P + dpix;
         const char* Gg = prm.G;
-        for (int g = 0; g < prm.groups; ++g, Gg += gstride) {
-            const float4 v = __ldg(px16(Gg, e.y));
-            const float r[4] = {v.x * w, v.y * w, v.z * w, v.w * w};
+        for (int g0 = 0; g0 < prm.groups; g0 += 4, Gg += 4 * gstride) {     // four loads in flight per thread
+            float4 v[4];
             #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (4 * g + j < prm.C) red_add(out + (int64_t)(4 * g + j) * P, r[j]);
+            for (int gi = 0; gi < 4; ++gi)
+                v[gi] = g0 + gi < prm.groups ? __ldg(px16(Gg + gi * gstride, e.y)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            #pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+                const float r[4] = {v[gi].x * w, v[gi].y * w, v[gi].z * w, v[gi].w * w};
+                #pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * (g0 + gi) + j < prm.C) red_add(out + (int64_t)(4 * (g0 + gi) + j) * P, r[j]);
+            }
         }
     }
 }
@@ -640,7 +646,16 @@ heavy_finish_kernel(const GatherParams prm)
         const float nrm = __ldcg(sums + (int64_t)NT * P);
         const float inv = 1.0f / fmaxf(nrm, prm.eps);
         float* out = prm.out + (int64_t)t.f * prm.C * P + t.pix;
-        for (int c = 0; c < prm.C; ++c) out[(int64_t)c * P] = __ldcg(out + (int64_t)c * P) * inv;
+        // eight independent loads in flight per thread (one load -> store chain per channel is a
+        // full memory latency each: 64 of them made this kernel 33 us whatever the tile count)
+        for (int c0 = 0; c0 < prm.C; c0 += 8) {
+            float v[8];
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = c0 + j < prm.C ? __ldcg(out + (int64_t)(c0 + j) * P) : 0.0f;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < prm.C) out[(int64_t)(c0 + j) * P] = v[j] * inv;
+        }
         if (prm.aux) {
             float* a = prm.aux + (int64_t)t.f * (NT + 1) * P + t.pix;
             #pragma unroll
