@@ -17,5 +17,5 @@ timeout 120 ncu --set full --clock-control none --import-source on -k regex:rowg
 timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 45 --csv --log-file gpurun_out/launches_final.csv \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-pipeline > gpurun_out/ncu_list.log 2>&1; stamp ncu_list $?
 timeout 100 python profiles/sweep_configs.py > gpurun_out/sweep_configs_final.json 2> gpurun_out/sweep_configs.err; stamp sweep_configs $?
-timeout 150 compute-sanitizer --tool memcheck python profiles/debug/small_case.py > gpurun_out/memcheck.log 2>&1; stamp memcheck $?
+for i in 1 2 3; do timeout 60 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_repeat_$i.json 2>> gpurun_out/bench_final.err; stamp repeat_$i $?; done
 cat $S

@@ -39,6 +39,9 @@ namespace slr {
 #define SLR_GATHER_FRAMES 2            // default CTA shape of rowgather_kernel: frames x row pairs
 #define SLR_GATHER_PAIRS 2             // (measured: 2x2 = 4x1 > 1x4 > 2x4 > 4x4, profiles/r01/sweep_variants.jsonl)
 #endif
+#ifndef SLR_GATHER_FINE_BUCKETS
+#define SLR_GATHER_FINE_BUCKETS 0      // 1: unrolled variants for list lengths 10 and 14 as well
+#endif
 #ifndef SLR_GATHER_PAD_SMEM
 #define SLR_GATHER_PAD_SMEM 0          // see launch_rowgather()
 #endif
@@ -49,7 +52,11 @@ namespace slr {
 #define SLR_EXPAND_MINBLOCKS 6
 #endif
 constexpr int kRegSlots = 16;          // list slots a lane keeps in registers; deeper ones are re-read per group
-constexpr int kSmemSlots = 16;         // list slots expand_kernel stages in shared memory (>= kCanon)
+#ifndef SLR_EXPAND_SMEM_SLOTS
+#define SLR_EXPAND_SMEM_SLOTS 16
+#endif
+constexpr int kSmemSlots = SLR_EXPAND_SMEM_SLOTS;   // list slots expand_kernel stages in shared memory (>= kCanon)
+static_assert(kSmemSlots >= kCanon && kSmemSlots <= kRegSlots, "shared list table: kCanon <= slots <= kRegSlots");
 constexpr int kCols = TW * kPairsPerTile;   // 128 lanes (columns of row pairs) per tile
 #ifndef SLR_HEAVY_GROUPS
 #define SLR_HEAVY_GROUPS 4
@@ -456,7 +463,13 @@ rowgather_kernel(const GatherParams prm)
     else if (kmax <= 4) gather_rows_dispatch<NT, 4>(c, pk, wt, wb, sum_t, sum_b);
     else if (kmax <= 6) gather_rows_dispatch<NT, 6>(c, pk, wt, wb, sum_t, sum_b);
     else if (kmax <= 8) gather_rows_dispatch<NT, 8>(c, pk, wt, wb, sum_t, sum_b);
+#if SLR_GATHER_FINE_BUCKETS
+    else if (kmax <= 10) gather_rows_dispatch<NT, 10>(c, pk, wt, wb, sum_t, sum_b);
     else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b);
+    else if (kmax <= 14) gather_rows_dispatch<NT, 14>(c, pk, wt, wb, sum_t, sum_b);
+#else
+    else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b);
+#endif
     else gather_rows_dispatch<NT, 16>(c, pk, wt, wb, sum_t, sum_b);
 
     #pragma unroll

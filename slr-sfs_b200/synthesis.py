@@ -20,6 +20,7 @@ Two algorithms, same results up to fp32 summation order:
                                 design BASELINE.json sketches, kept as measured baseline.
 """
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -46,6 +47,55 @@ def _req(t, name):
     assert t.is_cuda, "%s must be a CUDA tensor (no CPU path)" % name
     assert t.dtype == torch.float32 and t.is_contiguous(), "%s must be contiguous fp32" % name
     return t
+
+
+class _BufferPool:
+    """Per device: the big buffers that one stream writes and another reads (scene buffer, clip
+    table), recycled between JointSplat objects WITHOUT going through the caching allocator.  A
+    block freed there after record_stream() is not handed out again until the recorded streams
+    have drained, so a host that runs ahead of the GPU keeps getting fresh cudaMallocs -- each a
+    device-wide synchronisation -- in the middle of the pipeline (measured: occasional bench runs
+    35 % slower).  An entry remembers, per stream, the last event after which its contents are no
+    longer needed; whoever takes it over makes its writing stream wait for those on the device."""
+    KEEP = 4          # free entries kept per kind; more are handed back to the allocator
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+
+    def acquire(self, kind, nbytes):
+        entries = self.free.setdefault(kind, [])
+        for i, e in enumerate(entries):
+            if e["buf"].numel() * 4 >= nbytes:
+                return entries.pop(i)
+        return {"kind": kind, "last": {},
+                "buf": torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)}
+
+    def release(self, entry):
+        entries = self.free.setdefault(entry["kind"], [])
+        if len(entries) >= self.KEEP:
+            for stream in entry["last"]:          # back to the allocator, with the streams that used it
+                entry["buf"].record_stream(stream)
+        else:
+            entries.append(entry)
+
+    @staticmethod
+    def take_over(entry, writer):
+        """`writer` is about to overwrite the entry: order it behind the previous contents' users."""
+        for ev in entry["last"].values():
+            writer.wait_event(ev)
+        entry["last"] = {}
+
+    @staticmethod
+    def used(entry, stream, event):
+        """The entry's contents are needed until `event` (recorded on `stream`)."""
+        entry["last"][stream] = event
+
+
+def _release_all(pool, entries):
+    for e in entries:
+        pool.release(e)
+    del entries[:]
 
 
 class JointSplat:
@@ -94,6 +144,9 @@ class JointSplat:
         self._scene = None
         self._prepared = None          # event: zsub and the scene buffer are built
         self._table = None             # cached clip table (see _clip_table)
+        self._scene_entry = None       # pool entries behind _scene / _table["buf"]
+        self._pooled = []              # everything to give back when this object dies
+        self._finalizer = None
 
     def _wait_inputs(self, stream):
         if self._inputs_ready is not None:
@@ -101,14 +154,14 @@ class JointSplat:
 
     def _prepare(self):
         """Z.max() and the pre-weighted, channel-interleaved scene buffer: built once, on the
-        current stream; users on other streams are ordered behind the `_prepared` event.
-        Buffers are allocated by the caller's stream and marked as used by this one."""
+        current stream; users on other streams are ordered behind the `_prepared` event."""
         cur = torch.cuda.current_stream(self.device)
         if self._prepared is None:
             self._wait_inputs(cur)
-            for t in (self._zsub, self._scene):
-                if t is not None:
-                    t.record_stream(cur)
+            if self._zsub is not None:
+                self._zsub.record_stream(cur)
+            if self._scene_entry is not None:
+                _BufferPool.take_over(self._scene_entry, cur)
             with torch.cuda.device(self.device):
                 s = _lib.current_stream(self.device)
                 if self._zsub is not None:
@@ -118,17 +171,28 @@ class JointSplat:
                               _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W, s)
             self._prepared = torch.cuda.Event()
             self._prepared.record(cur)
+            if self._scene_entry is not None:
+                _BufferPool.used(self._scene_entry, cur, self._prepared)
         else:
             cur.wait_event(self._prepared)
 
     def _allocate(self, scene):
-        """Allocate (on the current stream's pool) what _prepare fills."""
+        """Allocate what _prepare fills."""
         if self.z_mode == "max" and self._zsub is None:
             self._zsub = torch.empty(1, dtype=torch.float32, device=self.device)
         if scene and self._scene is None:
             n = _lib.load().slr_scene_bytes(self.C, self.n_tail, self.H, self.W)
-            self._scene = torch.empty(n // 4, dtype=torch.float32, device=self.device)
+            self._scene_entry = self._from_pool("scene", n)
+            self._scene = self._scene_entry["buf"]
             self._prepared = None      # (re)build everything with the scene buffer
+
+    def _from_pool(self, kind, nbytes):
+        pool = self._shared_state()["pool"]
+        entry = pool.acquire(kind, nbytes)
+        self._pooled.append(entry)
+        if self._finalizer is None:
+            self._finalizer = weakref.finalize(self, _release_all, pool, self._pooled)
+        return entry
 
     @property
     def zsub(self):
@@ -144,7 +208,8 @@ class JointSplat:
             # SLR_SIDE_PRIORITY=-1: the side stream's CTAs are scheduled ahead of the gather's
             prio = int(os.environ.get("SLR_SIDE_PRIORITY", "0"))
             st = JointSplat._shared[self.device] = {"side": torch.cuda.Stream(device=self.device, priority=prio),
-                                                    "ws": {}, "free": {}, "turn": 0}
+                                                    "ws": {}, "free": {}, "turn": 0,
+                                                    "pool": _BufferPool(self.device)}
         return st
 
     def _scratch(self, st, n, slot, side):
@@ -165,16 +230,22 @@ class JointSplat:
         if tb is not None and tb["clip"] == (start, end) and tb["t0"] <= t0 and t0 + n <= tb["t0"] + tb["n"]:
             return tb
         nbytes = _lib.load().slr_clip_table_bytes(self.H, self.W, n)
-        buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
-        buf.record_stream(side)
+        if tb is not None:                      # the old table goes back to the pool right away
+            self._pooled.remove(tb["entry"])
+            self._shared_state()["pool"].release(tb["entry"])
+            self._table = None
+        entry = self._from_pool("table", nbytes)
+        buf = entry["buf"]
         with torch.cuda.stream(side):
             self._wait_inputs(side)
+            _BufferPool.take_over(entry, side)
             _lib.call("slr_clip_table", _lib.ptr(self.motion), self.H, self.W, start, end, t0, n,
                       _lib.ptr(buf), nbytes, _lib.current_stream(self.device))
             ready = torch.cuda.Event()
             ready.record(side)
+        _BufferPool.used(entry, side, ready)
         tb = self._table = {"clip": (start, end), "t0": t0, "n": n, "buf": buf, "bytes": nbytes,
-                            "ready": ready, "stream": side}
+                            "ready": ready, "entry": entry}
         return tb
 
     def prepare_clip(self, start, end, t0=None, n=None):
@@ -214,8 +285,6 @@ class JointSplat:
             self._allocate(scene=True)
             scene = self._scene
             tb = self._clip_table(start, end, t0, n, side)
-            if tb["stream"] != side:
-                tb["buf"].record_stream(side)
             for (b0, nb) in batches:
                 slot = st["turn"] = st["turn"] ^ 1
                 args = (C, self.n_tail, H, W, start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1])
@@ -243,6 +312,9 @@ class JointSplat:
                 done = torch.cuda.Event()
                 done.record(main)
                 st["free"][slot] = (done,)
+                # the batch's side-stream work precedes `ready`, which main waited for: `done` covers both
+                _BufferPool.used(self._scene_entry, main, done)
+                _BufferPool.used(tb["entry"], main, done)
         res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
         return res if len(res) > 1 else out
 

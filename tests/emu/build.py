@@ -107,6 +107,7 @@ def _compile(lib, extra):
     srcs = [os.path.join(HERE, "emu_runtime.cpp")] + sorted(glob.glob(os.path.join(OUT, "*.emu.cpp")))
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing",
            "-Wno-attributes", "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "include"), "-I", CSRC] + extra + \
+          os.environ.get("SLR_DEFINES", "").split() + \
           ["-o", lib] + srcs
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:

@@ -130,3 +130,29 @@ def test_scatter_variant_through_the_python_layer(host_pkg):
     for t in (0, 3, N - 1):
         want = oracle.joint_splat_baseline(feat.numpy(), Z.numpy(), m.numpy(), (0, t, N - 1))
         assert rel_err(js.frame_scatter((0, t, N - 1)).numpy(), want) <= TOL
+
+
+def test_scene_and_table_buffers_are_recycled_between_scenes(host_pkg):
+    """A new JointSplat per scene (what bench.py and a per-scene loop do) must not allocate: the
+    big cross-stream buffers come back from the per-device pool, ordered by events."""
+    import gc
+    H, W, C, N = 17, 37, 3, 6
+    feat, Z, m = _scene(H, W, C, 9)
+    seen = []
+    for _ in range(3):
+        js = host_pkg.JointSplat(feat, Z, m)
+        out = js.frames(0, N - 1, 0, N).numpy()
+        seen.append((js._scene.data_ptr(), js._table["buf"].data_ptr()))
+        pool = js._shared_state()["pool"]
+        del js
+        gc.collect()
+        assert len(pool.free["scene"]) == 1 and len(pool.free["table"]) == 1
+    assert seen[0] == seen[1] == seen[2]
+    want = oracle.joint_splat_baseline(feat.numpy(), Z.numpy(), m.numpy(), (0, 2, N - 1))
+    assert rel_err(out[2:3], want) <= TOL
+    # a second clip on the same object: the old table returns to the pool and is taken again
+    js = host_pkg.JointSplat(feat, Z, m)
+    js.frames(0, N - 1, 0, 2)
+    first = js._table["buf"].data_ptr()
+    js.frames(0, N, 0, 2)
+    assert js._table["buf"].data_ptr() == first and len(js._pooled) == 2
