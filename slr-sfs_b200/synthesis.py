@@ -61,23 +61,31 @@ class _BufferPool:
 
     def __init__(self, device):
         self.device = device
-        self.free = {}
+        self.free = {}          # kind -> free entries, oldest first
 
     def acquire(self, kind, nbytes):
+        """An entry whose previous users have finished if there is one (the side stream can then
+        run ahead into the next scene), else a new one while fewer than KEEP are waiting, else the
+        one released longest ago."""
         entries = self.free.setdefault(kind, [])
-        for i, e in enumerate(entries):
-            if e["buf"].numel() * 4 >= nbytes:
-                return entries.pop(i)
+        fits = [e for e in entries if e["buf"].numel() * 4 >= nbytes]
+        pick = next((e for e in fits if all(ev.query() for ev in e["last"].values())), None)
+        if pick is None and fits and len(entries) >= self.KEEP:
+            pick = fits[0]
+        if pick is not None:
+            entries.remove(pick)
+            return pick
         return {"kind": kind, "last": {},
                 "buf": torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)}
 
     def release(self, entry):
         entries = self.free.setdefault(entry["kind"], [])
-        if len(entries) >= self.KEEP:
-            for stream in entry["last"]:          # back to the allocator, with the streams that used it
-                entry["buf"].record_stream(stream)
-        else:
-            entries.append(entry)
+        entries.append(entry)
+        if len(entries) > self.KEEP:
+            drop = min(entries, key=lambda e: e["buf"].numel())     # the smallest (the oldest among equals)
+            entries.remove(drop)
+            for stream in drop["last"]:           # back to the allocator, with the streams that used it
+                drop["buf"].record_stream(stream)
 
     @staticmethod
     def take_over(entry, writer):

@@ -36,6 +36,9 @@ class _Event:
     def record(self, stream=None):
         pass
 
+    def query(self):
+        return True
+
 
 @pytest.fixture()
 def host_pkg(monkeypatch):
