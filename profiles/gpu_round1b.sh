@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical record: run at commit "gather pad-smem knob; sweep stage for side-stream room")
 # ONE gpurun call (round 1, second session): parity suite, bench, knob sweep, parity + bench under the
 # winning knobs, ncu launch list + one full capture of the hot kernel.  Ordered by priority; every step has
 # its own timeout and writes to gpurun_out/ as it goes.

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical record: run at commit "bench: live timing brackets the dominant kernel only ...")
 # Second GPU call of this session: A/B of the rowgather CTA shape through bench.py itself (alternating runs),
 # and the main-stream-priority stage of the knob sweep.
 mkdir -p gpurun_out

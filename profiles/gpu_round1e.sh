@@ -1,4 +1,6 @@
 #!/bin/bash
+# (historical record: the variant libraries were built locally into gpurun_variants/ with
+#  SLR_EXPAND_SMEM_SLOTS / SLR_EXPAND_MINBLOCKS / SLR_GATHER_FINE_BUCKETS defines that have since been removed)
 # A/B of compile-time variants prebuilt into gpurun_variants/ (no nvcc on the GPU box), alternating runs.
 mkdir -p gpurun_out
 B="--no-cpu-baseline --no-e2e --steps 30"

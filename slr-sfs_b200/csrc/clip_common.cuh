@@ -82,30 +82,7 @@ __device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
 // ---------------------------------------------------------------------------
 // host side: layout of the caller-provided workspace
 // ---------------------------------------------------------------------------
-#ifndef SLR_SMEM_CARVEOUT
-#define SLR_SMEM_CARVEOUT -1           // see slr_host::smem_carveout()
-#endif
-
 namespace slr_host {
-
-// Shared-memory carve-out the clip kernels ask for, in per cent of the SM's L1/shared array (-1:
-// the driver's choice per kernel, which is "all shared" for expand_kernel -- 6 CTAs x 33 KB -- and
-// "all L1" for the others).  When kernels run side by side on two streams (table / bins / expand
-// of the next batch beside the gather of the current one) an SM can only host CTAs of both if
-// their carve-outs agree; SLR_SMEM_CARVEOUT overrides the compiled-in default for sweeps.
-inline int smem_carveout()
-{
-    const char* e = getenv("SLR_SMEM_CARVEOUT");
-    return e ? atoi(e) : SLR_SMEM_CARVEOUT;
-}
-
-template <class Kernel>
-inline void prefer_carveout(Kernel kernel)
-{
-    const int pct = smem_carveout();
-    if (pct >= -1 && pct <= 100)
-        cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-}
 
 struct Workspace {
     float* land;          // [n][2 dirs][2][P]   landing coordinates

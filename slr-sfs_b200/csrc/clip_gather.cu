@@ -37,25 +37,13 @@ namespace slr {
 #endif
 #ifndef SLR_GATHER_FRAMES
 #define SLR_GATHER_FRAMES 2            // default CTA shape of rowgather_kernel: frames x row pairs
-#define SLR_GATHER_PAIRS 2             // (measured: 2x2 = 4x1 > 1x4 > 2x4 > 4x4, profiles/r01/sweep_variants.jsonl)
-#endif
-#ifndef SLR_GATHER_FINE_BUCKETS
-#define SLR_GATHER_FINE_BUCKETS 0      // 1: unrolled variants for list lengths 10 and 14 as well
-#endif
-#ifndef SLR_GATHER_PAD_SMEM
-#define SLR_GATHER_PAD_SMEM 0          // see launch_rowgather()
-#endif
-#ifndef SLR_EXPAND_ATOMIC_CLAIM
-#define SLR_EXPAND_ATOMIC_CLAIM 1      // default claim mode of expand_kernel (1: atomicCAS, 0: store + re-read)
+#define SLR_GATHER_PAIRS 2             // (measured: 2x2 = 4x1 > 1x4 > 2x4 > 4x4, profiles/r01/sweep_variants.jsonl; 1x4 kept for A/B)
 #endif
 #ifndef SLR_EXPAND_MINBLOCKS
 #define SLR_EXPAND_MINBLOCKS 6
 #endif
 constexpr int kRegSlots = 16;          // list slots a lane keeps in registers; deeper ones are re-read per group
-#ifndef SLR_EXPAND_SMEM_SLOTS
-#define SLR_EXPAND_SMEM_SLOTS 16
-#endif
-constexpr int kSmemSlots = SLR_EXPAND_SMEM_SLOTS;   // list slots expand_kernel stages in shared memory (>= kCanon)
+constexpr int kSmemSlots = 16;         // list slots expand_kernel stages in shared memory (>= kCanon)
 static_assert(kSmemSlots >= kCanon && kSmemSlots <= kRegSlots, "shared list table: kCanon <= slots <= kRegSlots");
 constexpr int kCols = TW * kPairsPerTile;   // 128 lanes (columns of row pairs) per tile
 #ifndef SLR_HEAVY_GROUPS
@@ -107,23 +95,17 @@ __host__ __device__ constexpr SlotRole slot_role(int k)
 
 // ---------------------------------------------------------------------------
 // expand_kernel
-// A canonical slot of a lane is claimed by the first source that asks for it; a second source
-// with the same (direction, row offset, east/west) -- the flow compresses there -- goes to the
-// lane's overflow slots.  Two ways to decide who is first:
-//   kAtomicClaim = true   atomicCAS on the slot's source field (one shared-memory atomic per pair
-//                         plus an atomicOr into the lane's occupancy mask);
-//   kAtomicClaim = false  the bin is walked in chunks of one entry per thread: every thread
-//                         writes its source into the slots it wants IF they are empty (plain
-//                         stores, some writer wins), barrier, then re-reads them: "mine" -> store
-//                         the weight, "someone else's" -> overflow.  No shared-memory atomics in
-//                         regular flow; slots claimed in earlier chunks are simply not empty.
+// A canonical slot of a lane is claimed (atomicCAS on its source field) by the first source that
+// asks for it; a second source with the same (direction, row offset, east/west) -- the flow
+// compresses there -- goes to the lane's overflow slots.  (A variant that claims with plain stores
+// and re-reads after a barrier, no shared-memory atomics, measured the same: the claims are not
+// what bounds this kernel, profiles/README.md.)
 // ---------------------------------------------------------------------------
-template <bool kAtomicClaim>
 __global__ void __launch_bounds__(TILE, SLR_EXPAND_MINBLOCKS)
 expand_kernel(const GatherParams prm)
 {
     __shared__ uint4 tab[kSmemSlots * kCols];      // tab[slot * kCols + col] = (source, w_top, w_bottom, -)
-    __shared__ unsigned occ[kCols];                // used canonical slots (bit mask; atomic claims only)
+    __shared__ unsigned occ[kCols];                // used canonical slots (bit mask)
     __shared__ unsigned ovf[kCols];                // overflow slots in use (kCanon, kCanon + 1, ...)
     __shared__ unsigned excess_full;               // the global excess list ran out of room
 
@@ -164,7 +146,7 @@ expand_kernel(const GatherParams prm)
     auto cell_of = [&](int lx, int ly, unsigned dir, int dx, int dy) {
         return tab + canon_slot(dir, (ly & 1) - dy, dx) * kCols + (ly >> 1) * TW + lx;
     };
-    // one (destination pixel, source, weight) pair -> its lane's list, claim by atomicCAS
+    // one (destination pixel, source, weight) pair -> its lane's list
     auto insert = [&](int lx, int ly, unsigned p, float w, unsigned dir, int dx, int dy) {
         uint4* cell = cell_of(lx, ly, dir, dx, dy);
         const unsigned old = atomicCAS(&cell->x, kEmpty, p);
@@ -180,73 +162,25 @@ expand_kernel(const GatherParams prm)
         const int X = tx * TW + lx, Y = ty * TH + ly;
         if (X < prm.W && Y < prm.H) {
             const int64_t pix = (int64_t)Y * prm.W + X;
-            if (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f) {
-                if (kAtomicClaim) {
-                    insert(lx, ly, (unsigned)pix, a_f + a_b, 0u, 0, 0);
-                } else {    // nothing else has been inserted yet, and no two pixels share a slot: it is theirs
-                    uint4* cell = cell_of(lx, ly, 0u, 0, 0);
-                    cell->x = (unsigned)pix;
-                    ((ly & 1) ? cell->z : cell->y) = __float_as_uint(a_f + a_b);
-                }
-            }
+            if (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f)
+                insert(lx, ly, (unsigned)pix, a_f + a_b, 0u, 0, 0);
         }
     }
-    if (kAtomicClaim) {
-        for (unsigned e = beg + tid; e < end; e += TILE) {
-            const float4 en = __ldcs(ent + e);
-            const unsigned pd = __float_as_uint(en.x);
-            const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
-            const unsigned dir = pd >> 31;
-            const float a = dir ? a_b : a_f;
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-                const float wa = fp.w[k] * a;
-                if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
-                    insert(lx, ly, pd & ~kDirBit, wa, dir, k & 1, k >> 1);
-            }
+    for (unsigned e = beg + tid; e < end; e += TILE) {
+        const float4 en = __ldcs(ent + e);
+        const unsigned pd = __float_as_uint(en.x);
+        const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+        const unsigned dir = pd >> 31;
+        const float a = dir ? a_b : a_f;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+            const float wa = fp.w[k] * a;
+            if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                insert(lx, ly, pd & ~kDirBit, wa, dir, k & 1, k >> 1);
         }
-        __syncthreads();
-    } else {
-        __syncthreads();                 // the static pixels' slots are in place
-        for (unsigned base = beg; base < end; base += TILE) {       // block-uniform trip count
-            const unsigned e = base + tid;
-            const bool have = e < end;
-            Footprint fp;
-            unsigned p = 0u, dir = 0u, valid = 0u;
-            float a = 0.0f;
-            if (have) {
-                const float4 en = __ldcs(ent + e);
-                const unsigned pd = __float_as_uint(en.x);
-                fp = footprint_at(en.y, en.z, prm.H, prm.W);
-                p = pd & ~kDirBit;
-                dir = pd >> 31;
-                a = dir ? a_b : a_f;
-                #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-                    if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && fp.w[k] * a != 0.0f) {
-                        valid |= 1u << k;
-                        uint4* cell = cell_of(lx, ly, dir, k & 1, k >> 1);
-                        if (cell->x == kEmpty) cell->x = p;          // plain store: one of the askers wins
-                    }
-                }
-            }
-            __syncthreads();
-            // Slots this chunk asked for are no longer empty, so the next chunk's claims (no barrier
-            // in between) cannot disturb the re-reads below.
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!(valid >> k & 1u)) continue;
-                const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-                const float wa = fp.w[k] * a;
-                uint4* cell = cell_of(lx, ly, dir, k & 1, k >> 1);
-                if (cell->x == p) ((ly & 1) ? cell->z : cell->y) = __float_as_uint(wa);
-                else spill(lx, ly, p, wa);
-            }
-        }
-        __syncthreads();
     }
+    __syncthreads();
     const bool deep = tid < kCols && kCanon + (int)ovf[tid] > kListDepth;
     const int any_deep = __syncthreads_or(deep);
     const unsigned flag = excess_full ? 2u : (any_deep ? 1u : 0u);
@@ -257,13 +191,7 @@ expand_kernel(const GatherParams prm)
     if (flag == 2u || tid >= kCols) return;
 
     // write the lists out, slot-major per row pair
-    unsigned my_occ = 0u;
-    if (kAtomicClaim) {
-        my_occ = occ[tid];
-    } else {
-        #pragma unroll
-        for (int k = 0; k < kCanon; ++k) my_occ |= (tab[k * kCols + tid].x != kEmpty ? 1u : 0u) << k;
-    }
+    const unsigned my_occ = occ[tid];
     const int n_ovf = min((int)ovf[tid], kListDepth - kCanon);     // the rest is in the excess list
     const int my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz(my_occ);    // slots [0, my_hi) may be used
     const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
@@ -463,13 +391,7 @@ rowgather_kernel(const GatherParams prm)
     else if (kmax <= 4) gather_rows_dispatch<NT, 4>(c, pk, wt, wb, sum_t, sum_b);
     else if (kmax <= 6) gather_rows_dispatch<NT, 6>(c, pk, wt, wb, sum_t, sum_b);
     else if (kmax <= 8) gather_rows_dispatch<NT, 8>(c, pk, wt, wb, sum_t, sum_b);
-#if SLR_GATHER_FINE_BUCKETS
-    else if (kmax <= 10) gather_rows_dispatch<NT, 10>(c, pk, wt, wb, sum_t, sum_b);
     else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b);
-    else if (kmax <= 14) gather_rows_dispatch<NT, 14>(c, pk, wt, wb, sum_t, sum_b);
-#else
-    else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b);
-#endif
     else gather_rows_dispatch<NT, 16>(c, pk, wt, wb, sum_t, sum_b);
 
     #pragma unroll
@@ -723,8 +645,8 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     return 0;
 }
 
-// CTA shape of rowgather_kernel: "<frames>x<row pairs>".  The default was chosen by measurement
-// (profiles/); the environment variable SLR_GATHER_SHAPE overrides it for sweeps.
+// CTA shape of rowgather_kernel: "<frames>x<row pairs>", 2x2 (default, chosen by measurement:
+// profiles/README.md) or 1x4; the environment variable SLR_GATHER_SHAPE overrides the default for A/B runs.
 struct GatherShape { int frames, pairs; };
 
 GatherShape gather_shape()
@@ -736,34 +658,13 @@ GatherShape gather_shape()
     return g;
 }
 
-// How expand_kernel claims canonical slots: SLR_EXPAND_CLAIM = "atomic" | "store" (see the kernel).
-bool expand_claims_atomically()
-{
-    const char* e = getenv("SLR_EXPAND_CLAIM");
-    if (e && strcmp(e, "store") == 0) return false;
-    if (e && strcmp(e, "atomic") == 0) return true;
-    return SLR_EXPAND_ATOMIC_CLAIM != 0;
-}
-
 template <int F, int R>
 void launch_rowgather(const GatherParams& prm, int n_tail, cudaStream_t s)
 {
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)(kPairsPerTile / R) * (unsigned)((prm.n_frames + F - 1) / F);
-    // SLR_GATHER_PAD_SMEM: unused dynamic shared memory per CTA (<= 48 KB).  With a non-zero carve-out
-    // it caps how many gather CTAs an SM takes, which leaves registers and shared memory for the
-    // side stream's CTAs (the gather alone fills the register file).
-    const char* e = getenv("SLR_GATHER_PAD_SMEM");
-    const size_t pad = e ? (size_t)std::min(std::max(atoi(e), 0), 48 << 10) : (size_t)SLR_GATHER_PAD_SMEM;
-    if (n_tail == 0) {
-        slr_host::prefer_carveout(rowgather_kernel<0, F, R>);
-        rowgather_kernel<0, F, R><<<grid, 32 * F * R, pad, s>>>(prm);
-    } else if (n_tail == 1) {
-        slr_host::prefer_carveout(rowgather_kernel<1, F, R>);
-        rowgather_kernel<1, F, R><<<grid, 32 * F * R, pad, s>>>(prm);
-    } else {
-        slr_host::prefer_carveout(rowgather_kernel<2, F, R>);
-        rowgather_kernel<2, F, R><<<grid, 32 * F * R, pad, s>>>(prm);
-    }
+    if (n_tail == 0) rowgather_kernel<0, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    else if (n_tail == 1) rowgather_kernel<1, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    else rowgather_kernel<2, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
 }
 
 }  // namespace
@@ -777,13 +678,7 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
                                nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
-    if (expand_claims_atomically()) {
-        slr_host::prefer_carveout(expand_kernel<true>);
-        expand_kernel<true><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
-    } else {
-        slr_host::prefer_carveout(expand_kernel<false>);
-        expand_kernel<false><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
-    }
+    expand_kernel<<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
     return SLR_LAUNCH_STATUS();
 }
 
@@ -798,11 +693,8 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
                                out, aux, mask, workspace, workspace_bytes);
     if (rc) return rc;
     const GatherShape shape = gather_shape();
-    if (shape.frames == 2 && shape.pairs == 4) launch_rowgather<2, 4>(prm, n_tail, (cudaStream_t)stream_);
-    else if (shape.frames == 4 && shape.pairs == 4) launch_rowgather<4, 4>(prm, n_tail, (cudaStream_t)stream_);
-    else if (shape.frames == 2 && shape.pairs == 2) launch_rowgather<2, 2>(prm, n_tail, (cudaStream_t)stream_);
-    else if (shape.frames == 4 && shape.pairs == 1) launch_rowgather<4, 1>(prm, n_tail, (cudaStream_t)stream_);
-    else launch_rowgather<1, 4>(prm, n_tail, (cudaStream_t)stream_);
+    if (shape.frames == 1 && shape.pairs == 4) launch_rowgather<1, 4>(prm, n_tail, (cudaStream_t)stream_);
+    else launch_rowgather<2, 2>(prm, n_tail, (cudaStream_t)stream_);
     return SLR_LAUNCH_STATUS();
 }
 

@@ -273,8 +273,6 @@ int build_table(const float* motion, int64_t H, int64_t W, int start, int end, i
     const int n_tiles = tiles_x * tiles_y;
     SLR_CUDA(cudaMemsetAsync(tab.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
     const unsigned pblocks = (unsigned)((P + 255) / 256);
-    slr_host::prefer_carveout(euler_table_kernel);
-    slr_host::prefer_carveout(bin_scan_kernel);
     euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
                                                tab.land, tab.counts, tiles_x, n_tiles);
     bin_scan_kernel<<<n_frames, 1024, 0, s>>>(tab.counts, tab.offsets, n_tiles);
@@ -290,7 +288,6 @@ int fill_bins(const float* land, int64_t H, int64_t W, int n_frames, const Works
     SLR_CUDA(cudaMemsetAsync(ws.flag_count, 0, sizeof(unsigned), s));
     SLR_CUDA(cudaMemsetAsync(ws.excess_count, 0, sizeof(unsigned), s));
     const unsigned pblocks = (unsigned)((P + 255) / 256);
-    slr_host::prefer_carveout(bin_fill_kernel);
     bin_fill_kernel<<<dim3(pblocks, n_frames), 256, 0, s>>>(land, ws.offsets, ws.counts, ws.ent,
                                                             (int)H, (int)W, tiles_x, n_tiles, 8 * P);
     return SLR_LAUNCH_STATUS();

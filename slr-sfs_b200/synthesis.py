@@ -213,9 +213,7 @@ class JointSplat:
     def _shared_state(self):
         st = JointSplat._shared.get(self.device)
         if st is None:
-            # SLR_SIDE_PRIORITY=-1: the side stream's CTAs are scheduled ahead of the gather's
-            prio = int(os.environ.get("SLR_SIDE_PRIORITY", "0"))
-            st = JointSplat._shared[self.device] = {"side": torch.cuda.Stream(device=self.device, priority=prio),
+            st = JointSplat._shared[self.device] = {"side": torch.cuda.Stream(device=self.device),
                                                     "ws": {}, "free": {}, "turn": 0,
                                                     "pool": _BufferPool(self.device)}
         return st

@@ -16,13 +16,6 @@ emu = pytest.importorskip("emu", reason="tests/emu")
 TOL = 1e-4
 
 
-@pytest.fixture(params=["atomic", "store"], autouse=True)
-def expand_claim_mode(request, monkeypatch):
-    """Every test runs with both ways expand_kernel claims list slots (SLR_EXPAND_CLAIM)."""
-    monkeypatch.setenv("SLR_EXPAND_CLAIM", request.param)
-    return request.param
-
-
 def _rng(seed):
     return np.random.default_rng(seed)
 
@@ -135,7 +128,7 @@ def test_emu_gather_clip_vs_oracle(kind, shape):
         assert np.all(got[t:t + 1][want == 0.0] == 0.0)
 
 
-@pytest.mark.parametrize("shape", ["1x4", "2x4", "4x4", "2x2", "4x1"])
+@pytest.mark.parametrize("shape", ["1x4", "2x2"])
 def test_emu_gather_cta_shapes_agree(shape, monkeypatch):
     """rowgather_kernel's CTA shapes (frames x row pairs per CTA, SLR_GATHER_SHAPE) only regroup
     the same warps: identical results, including a ragged frame count and ragged image edges."""

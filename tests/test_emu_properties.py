@@ -69,10 +69,9 @@ def test_euler_kernel_is_bit_exact(H, W, T, kind, amp, seed, sign):
 @given(H=st.integers(1, 26), W=st.integers(1, 70), C=st.integers(1, 9), N=st.integers(1, 12),
        kind=st.sampled_from(["random", "smooth", "constant", "integer", "half", "patchy"]),
        amp=st.sampled_from([0.0, 0.75, 3.0, 9.0]), seed=st.integers(0, 2 ** 16), data=st.data(),
-       shape=st.sampled_from(["1x4", "2x2", "4x1", "2x4", "4x4"]), claim=st.sampled_from(["atomic", "store"]))
-def test_clip_pipeline_matches_the_oracle(H, W, C, N, kind, amp, seed, data, shape, claim, monkeypatch):
+       shape=st.sampled_from(["1x4", "2x2"]))
+def test_clip_pipeline_matches_the_oracle(H, W, C, N, kind, amp, seed, data, shape, monkeypatch):
     monkeypatch.setenv("SLR_GATHER_SHAPE", shape)
-    monkeypatch.setenv("SLR_EXPAND_CLAIM", claim)
     rng = np.random.default_rng(seed)
     feat = rng.standard_normal((1, C, H, W)).astype(np.float32)
     Z = rng.standard_normal((1, 1, H, W)).astype(np.float32)
