@@ -248,3 +248,8 @@ def test_emu_static_pixels_and_negative_zero():
     got = emu.Scene(feat, Z, m).frames(0, N - 1, 0, N)
     for t in (1, 6, N - 1):
         assert rel_err(got[t:t + 1], oracle.joint_splat_baseline(feat, Z, m, (0, t, N - 1))) <= TOL
+
+
+def test_emu_clip_table_bin_stats_case_shared_with_the_gpu_suite():
+    import clip_abi_cases
+    clip_abi_cases.clip_table_bin_stats(clip_abi_cases.EmuBackend())
