@@ -190,13 +190,15 @@ int slr_clip_table(const float* motion, int64_t H, int64_t W, int start, int end
 int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, int64_t W, int table_frames,
                  int f0, int n_frames, void* workspace, size_t workspace_bytes, slr_stream_t stream);
 
-/* Diagnostics (a `_host` call: copies four counters to the host and synchronises `stream`).
- * After slr_clip_expand on `workspace`: stats[0] = flagged destination tiles of the batch (some
- * lane's source list was cut at the list depth), stats[1] = of those, tiles done entirely by
+/* Diagnostics (a `_host` call: copies counters and the tile flags to the host and synchronises
+ * `stream`).  After slr_clip_expand on `workspace`: stats[0] = flagged destination tiles of the batch
+ * (some lane's source list was cut at the list depth), stats[1] = of those, tiles done entirely by
  * per-pair reductions from their bins, stats[2] = (destination, source) pairs beyond the list
- * depth, stats[3] = capacity of that excess list. */
+ * depth, stats[3] = capacity of that excess list, stats[4] = tiles served without lists (all pixels
+ * static, nothing lands there; 0 unless the library was built with that fast path), stats[5] = tiles
+ * x frames of the batch. */
 int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,
-                        uint32_t stats[4], slr_stream_t stream);
+                        uint32_t stats[6], slr_stream_t stream);
 
 #ifdef __cplusplus
 }

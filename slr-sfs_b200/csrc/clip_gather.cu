@@ -39,6 +39,14 @@ namespace slr {
 #define SLR_GATHER_FRAMES 2            // default CTA shape of rowgather_kernel: frames x row pairs
 #define SLR_GATHER_PAIRS 2             // (measured: 2x2 = 4x1 > 1x4 > 2x4 > 4x4, profiles/r01/sweep_variants.jsonl; 1x4 kept for A/B)
 #endif
+#ifndef SLR_STATIC_TILE_FASTPATH
+// 1: destination tiles whose 256 pixels all have zero motion and whose bin is empty (44 % of the
+// tiles of the benchmark scene) get no lists at all: expand_kernel only flags them (3) and
+// rowgather_kernel reads each pixel's own source directly.  Prepared and checked on the CPU
+// emulation (tests/test_emu_kernels.py builds it with -DSLR_STATIC_TILE_FASTPATH=1); compiled out
+// until it has been measured and parity-tested on a B200.
+#define SLR_STATIC_TILE_FASTPATH 0
+#endif
 #ifndef SLR_EXPAND_MINBLOCKS
 #define SLR_EXPAND_MINBLOCKS 6
 #endif
@@ -60,7 +68,7 @@ struct GatherParams {
     const unsigned* offsets;   // [frames][n_tiles + 1]
     uint4* lists;              // [frames][n_tiles * 4][kListDepth][32]
     unsigned* row_k;           // [frames][n_tiles * 4]
-    unsigned* tile_flag;       // [frames][n_tiles]: 0 normal, 1 = some lane's list was cut at kListDepth (the
+    unsigned* tile_flag;       // [frames][n_tiles]: 0 normal, 3 = static tile without lists (fast path), 1 = some lane's list was cut at kListDepth (the
                                // rest is in `excess`), 2 = excess list full: the whole tile goes the heavy way
     unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
     unsigned* flag_count;      // [1], zeroed by slr_clip_plan
@@ -120,6 +128,18 @@ expand_kernel(const GatherParams prm)
     const int64_t pair0 = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile;
     uint4* lists_tile = prm.lists + pair0 * (kListDepth * 32);
 
+#if SLR_STATIC_TILE_FASTPATH
+    {   // nothing lands here and nothing moves here: every pixel receives exactly itself
+        const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
+        const bool inside = X < prm.W && Y < prm.H;
+        const int64_t pix = inside ? (int64_t)Y * prm.W + X : 0;
+        const bool still = !inside || (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f);
+        if (__syncthreads_and(still && beg == end)) {
+            if (tid == 0) prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = 3u;
+            return;
+        }
+    }
+#endif
     for (int i = tid; i < kCanon * kCols; i += TILE) tab[i] = make_uint4(kEmpty, 0u, 0u, 0u);
     if (tid < kCols) { occ[tid] = 0u; ovf[tid] = 0u; }
     if (tid == 0) excess_full = 0u;
@@ -341,6 +361,67 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
     else gather_rows<NT, K, 1>(c, pk, wt, wb, sum_t, sum_b);
 }
 
+#if SLR_STATIC_TILE_FASTPATH
+// A row pair of a static tile (flag 3): each pixel receives exactly its own source with weight
+// a + (1 - a), as expand_kernel's static insert + the general gather would compute it.
+template <int NT>
+__device__ __forceinline__ void gather_static_rows(const GatherParams& prm, int f, int64_t pix, bool in_top, bool in_bot)
+{
+    const int64_t P = prm.P;
+    const float a_f = prm.alphas.a[f];
+    const float w = a_f + (1.0f - a_f);
+    const unsigned p_t = in_top ? (unsigned)pix : (unsigned)P;            // P = the all-zero pixel
+    const unsigned p_b = in_bot ? (unsigned)(pix + prm.W) : (unsigned)P;
+    const int64_t sstride = P + 1;
+    float sum_t[NT + 1], sum_b[NT + 1];
+    #pragma unroll
+    for (int t = 0; t <= NT; ++t) {
+        sum_t[t] = fmaf(__ldg(prm.S + (int64_t)t * sstride + p_t), w, 0.0f);
+        sum_b[t] = fmaf(__ldg(prm.S + (int64_t)t * sstride + p_b), w, 0.0f);
+    }
+    const float inv_t = 1.0f / fmaxf(sum_t[NT], prm.eps), inv_b = 1.0f / fmaxf(sum_b[NT], prm.eps);
+    const size_t gstride = (size_t)(P + 1) * 16;
+    float* o = prm.out + (int64_t)f * prm.C * P + pix;
+    const char* Gg = prm.G;
+    for (int g = 0; g < prm.groups; g += 2, Gg += 2 * gstride, o += 8 * P) {
+        float4 vt[2], vb[2];
+        #pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+            const bool has = g + gi < prm.groups;
+            vt[gi] = has ? __ldg(px16(Gg + gi * gstride, p_t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[gi] = has ? __ldg(px16(Gg + gi * gstride, p_b)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        #pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+            const float rt[4] = {fmaf(vt[gi].x, w, 0.0f) * inv_t, fmaf(vt[gi].y, w, 0.0f) * inv_t,
+                                 fmaf(vt[gi].z, w, 0.0f) * inv_t, fmaf(vt[gi].w, w, 0.0f) * inv_t};
+            const float rb[4] = {fmaf(vb[gi].x, w, 0.0f) * inv_b, fmaf(vb[gi].y, w, 0.0f) * inv_b,
+                                 fmaf(vb[gi].z, w, 0.0f) * inv_b, fmaf(vb[gi].w, w, 0.0f) * inv_b};
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = 4 * (g + gi) + j;
+                if (c < prm.C) {
+                    if (in_top) __stcs(o + (int64_t)(4 * gi + j) * P, rt[j]);
+                    if (in_bot) __stcs(o + (int64_t)(4 * gi + j) * P + prm.W, rb[j]);
+                }
+            }
+        }
+    }
+    #pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (!(r ? in_bot : in_top)) continue;
+        const float* sum = r ? sum_b : sum_t;
+        const int64_t px = pix + (r ? prm.W : 0);
+        if (prm.aux) {
+            float* a = prm.aux + (int64_t)f * (NT + 1) * P + px;
+            #pragma unroll
+            for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sum[j];
+        }
+        if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
+    }
+}
+#endif
+
 // CTA shape: F frames x R row pairs (warps) of one destination tile, F * R * 32 threads.  Warps of
 // the SAME tile in consecutive frames read source regions that differ only by one frame's
 // displacement, so with F > 1 they share most of their lines in this SM's L1 as well (the
@@ -363,6 +444,12 @@ rowgather_kernel(const GatherParams prm)
     const int X = tx * TW + (tid & 31), Y = ty * TH + 2 * pr;
     const int64_t P = prm.P;
     const int64_t pix = (int64_t)Y * prm.W + X;
+#if SLR_STATIC_TILE_FASTPATH
+    if (flag == 3u) {
+        gather_static_rows<NT>(prm, f, pix, X < prm.W && Y < prm.H, X < prm.W && Y + 1 < prm.H);
+        return;
+    }
+#endif
     const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + pr;
     const int kmax = (int)__ldg(prm.row_k + pair);
 
@@ -747,7 +834,7 @@ extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C
 }
 
 extern "C" int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,
-                                   uint32_t stats[4], slr_stream_t stream_)
+                                   uint32_t stats[6], slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(workspace && stats && H > 0 && W > 0 && n_frames > 0 && n_frames <= kMaxFrames,
                    "slr_clip_stats_host: bad arguments");
@@ -756,16 +843,14 @@ extern "C" int slr_clip_stats_host(const void* workspace, size_t workspace_bytes
     cudaStream_t s = (cudaStream_t)stream_;
     const int64_t tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * n_frames;
     uint32_t n_flag = 0, n_excess = 0;
+    std::vector<uint32_t> flags((size_t)tiles);
     SLR_CUDA(cudaMemcpyAsync(&n_flag, ws.flag_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     SLR_CUDA(cudaMemcpyAsync(&n_excess, ws.excess_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    SLR_CUDA(cudaMemcpyAsync(flags.data(), ws.tile_flag, sizeof(uint32_t) * (size_t)tiles, cudaMemcpyDeviceToHost, s));
     SLR_CUDA(cudaStreamSynchronize(s));
-    uint32_t n_full = 0;
-    if (n_flag) {
-        std::vector<uint32_t> flags((size_t)tiles);
-        SLR_CUDA(cudaMemcpyAsync(flags.data(), ws.tile_flag, sizeof(uint32_t) * (size_t)tiles, cudaMemcpyDeviceToHost, s));
-        SLR_CUDA(cudaStreamSynchronize(s));
-        for (uint32_t v : flags) n_full += v == 2u;
-    }
+    uint32_t n_full = 0, n_static = 0;
+    for (uint32_t v : flags) { n_full += v == 2u; n_static += v == 3u; }
     stats[0] = n_flag; stats[1] = n_full; stats[2] = n_excess; stats[3] = ws.excess_cap;
+    stats[4] = n_static; stats[5] = (uint32_t)tiles;
     return 0;
 }

@@ -124,8 +124,8 @@ def clip_table_bin_stats(be, H=40, W=72, C=6, start=1, end=12, t0=2, n_table=9, 
     out = be.empty(1, C, H, W)
     be.call("slr_clip_frames", be.ptr(scene), be.ptr(d_sink), C, 0, H, W, 0, 2, 1, 1, 0.0, 1.0,
             be.ptr(out), None, None, be.ptr(ws), ws_bytes, s)
-    stats = (ctypes.c_uint32 * 4)()
+    stats = (ctypes.c_uint32 * 6)()
     be.call("slr_clip_stats_host", be.ptr(ws), ws_bytes, H, W, 1, stats, s)
-    assert stats[0] >= 1 and stats[1] >= 1 and stats[2] > stats[3] == 2 * H * W
+    assert stats[0] >= 1 and stats[1] >= 1 and stats[2] > stats[3] == 2 * H * W and stats[5] == 5 * 3
     want = oracle.joint_splat_baseline(feat, Z, sink, (0, 1, 2))
     assert rel_err(be.host(out), want) <= TOL

@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE: the CUDA sources of slr-sfs_b200/csrc compiled for the CPU (see build.py
 and include/cuda_runtime.h) and driven through the same C ABI with numpy buffers."""
+import contextlib
 import ctypes
 
 import numpy as np
@@ -22,6 +23,28 @@ def lib():
             fn.restype = binding._OTHER_RESTYPE.get(name, ctypes.c_int)
         _lib = L
     return _lib
+
+
+def _bind(path):
+    from slr_sfs_b200 import _lib as binding
+    L = ctypes.CDLL(path)
+    for name, argtypes in binding.SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = binding._OTHER_RESTYPE.get(name, ctypes.c_int)
+    return L
+
+
+@contextlib.contextmanager
+def variant(tag, defines):
+    """Run the enclosed calls against a compile-time variant of the library (build.build_variant)."""
+    global _lib
+    lib()
+    saved, _lib = _lib, _bind(_build.build_variant(tag, defines))
+    try:
+        yield
+    finally:
+        _lib = saved
 
 
 def call(name, *args):
@@ -93,8 +116,8 @@ class Scene:
                 call(entry, p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)
         else:
             call("slr_clip_frames", p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)
-        st = (ctypes.c_uint32 * 4)()
+        st = (ctypes.c_uint32 * 6)()
         call("slr_clip_stats_host", p(ws), nb, H, W, n, st, None)
-        self.stats = dict(flagged=st[0], full=st[1], excess=st[2], excess_cap=st[3])
+        self.stats = dict(flagged=st[0], full=st[1], excess=st[2], excess_cap=st[3], static=st[4], tiles=st[5])
         res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
         return res if len(res) > 1 else out

@@ -103,6 +103,16 @@ def build(force=False, asan=False):
     return LIB
 
 
+def build_variant(tag, defines):
+    """The same sources with extra -D defines (compile-time variants that are prepared but not yet
+    enabled in the product build), as _build/libslr_splat_emu_<tag>.so."""
+    build()
+    lib = LIB[:-3] + "_" + tag + ".so"
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(LIB):
+        _compile(lib, list(defines))
+    return lib
+
+
 def _compile(lib, extra):
     srcs = [os.path.join(HERE, "emu_runtime.cpp")] + sorted(glob.glob(os.path.join(OUT, "*.emu.cpp")))
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing",

@@ -253,3 +253,26 @@ def test_emu_static_pixels_and_negative_zero():
 def test_emu_clip_table_bin_stats_case_shared_with_the_gpu_suite():
     import clip_abi_cases
     clip_abi_cases.clip_table_bin_stats(clip_abi_cases.EmuBackend())
+
+
+def test_emu_static_tile_fast_path_variant_is_bit_identical():
+    """-DSLR_STATIC_TILE_FASTPATH=1 (prepared, compiled out of the product build until measured on
+    a B200): fully static tiles with empty bins get no lists; same bits as the general path."""
+    H, W, C, N = 40, 96, 5, 7
+    feat, Z, _ = _scene(H, W, C, "A", 11)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    motion = np.zeros((1, 2, H, W), dtype=np.float32)
+    motion[0, 0, 8:24, 32:64] = 1.3 * np.sin(xs[8:24, 32:64] / 7.0)       # one moving island, static elsewhere
+    motion[0, 1, 8:24, 32:64] = -0.7
+    tail = np.abs(feat[:, :2]) + 0.5
+    sc = emu.Scene(feat, Z, motion, tail=tail)
+    base = sc.frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
+    assert sc.stats["static"] == 0
+    with emu.variant("static", ["-DSLR_STATIC_TILE_FASTPATH=1"]):
+        sc = emu.Scene(feat, Z, motion, tail=tail)
+        fast = sc.frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
+    assert 0 < sc.stats["static"] < sc.stats["tiles"]           # the island's tiles (and what it reaches) keep their lists
+    for a, b in zip(base, fast):
+        assert np.array_equal(a, b)
+    want = oracle.joint_splat_baseline(feat, Z, motion, (0, 3, N - 1))
+    assert rel_err(fast[0][3:4], want) <= TOL
