@@ -47,6 +47,17 @@ namespace slr {
 // until it has been measured and parity-tested on a B200.
 #define SLR_STATIC_TILE_FASTPATH 0
 #endif
+#ifndef SLR_GATHER_SHIFT_SHARE
+// 1: where the flow is locally one-to-one, the source in a lane's EAST slot (its north-east /
+// south-east corner lands on the lane's pixel) is the source in the WEST slot of the lane to its
+// left.  expand_kernel records, per lane, for which of the six (west, east) slot pairs that holds;
+// rowgather_kernel then takes the east slot's data from the neighbouring lane with four SHFL.UP
+// and issues the east slot's LDG.128 only for the lanes where it does not hold (lane 0, collisions)
+// -- up to half of the loads of the hot loop.  A pair is treated this way only in row pairs where
+// at least kShareMinLanes lanes benefit.  Prepared and checked on the CPU emulation (bit-identical
+// results); compiled out until it has been measured and parity-tested on a B200.
+#define SLR_GATHER_SHIFT_SHARE 0
+#endif
 #ifndef SLR_EXPAND_MINBLOCKS
 #define SLR_EXPAND_MINBLOCKS 6
 #endif
@@ -67,7 +78,7 @@ struct GatherParams {
     const float* motion;       // [2][P]: a destination pixel with zero motion contributes to itself
     const unsigned* offsets;   // [frames][n_tiles + 1]
     uint4* lists;              // [frames][n_tiles * 4][kListDepth][32]
-    unsigned* row_k;           // [frames][n_tiles * 4]
+    unsigned* row_k;           // [frames][n_tiles * 4]    slots in use per row pair
     unsigned* tile_flag;       // [frames][n_tiles]: 0 normal, 3 = static tile without lists (fast path), 1 = some lane's list was cut at kListDepth (the
                                // rest is in `excess`), 2 = excess list full: the whole tile goes the heavy way
     unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
@@ -100,6 +111,16 @@ __host__ __device__ constexpr SlotRole slot_role(int k)
 {
     return k < 8 ? ((k & 1) ? kBottomOnly : kBoth) : (k < kCanon ? kTopOnly : kBoth);
 }
+
+#if SLR_GATHER_SHIFT_SHARE
+// (west, east) canonical slot pairs: same direction and row offset, dx = 0 / 1.
+constexpr int kSlotPairs = 6;
+constexpr int kShareMinLanes = 16;
+__host__ __device__ constexpr int pair_west(int pi) { return pi < 4 ? pi : 8 + 2 * (pi - 4); }
+__host__ __device__ constexpr int pair_east(int pi) { return pi < 4 ? 4 + pi : 9 + 2 * (pi - 4); }
+// pair index of an east slot, -1 for every other slot
+__host__ __device__ constexpr int east_pair(int k) { return (k >= 4 && k < 8) ? k - 4 : k == 9 ? 4 : k == 11 ? 5 : -1; }
+#endif
 
 // ---------------------------------------------------------------------------
 // expand_kernel
@@ -217,11 +238,25 @@ expand_kernel(const GatherParams prm)
     const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
     const int64_t pair = pair0 + (tid >> 5);
     if ((tid & 31) == 0) prm.row_k[pair] = (unsigned)kmax;
+#if SLR_GATHER_SHIFT_SHARE
+    unsigned lane_share = 0u;        // bit pi: this lane's east slot of pair pi holds the left lane's west source
+    if ((tid & 31) != 0) {
+        #pragma unroll
+        for (int pi = 0; pi < kSlotPairs; ++pi)     // unclaimed slots compare as equal: both read the all-zero pixel
+            lane_share |= (tab[pair_east(pi) * kCols + tid].x == tab[pair_west(pi) * kCols + tid - 1].x ? 1u : 0u) << pi;
+    }
+#endif
     uint4* dst = prm.lists + pair * (kListDepth * 32) + (tid & 31);
     const uint4 none = make_uint4((unsigned)P, 0u, 0u, 0u);     // the zero pixel, weights 0
     for (int k = 0; k < min(kmax, kSmemSlots); ++k) {
         const bool used = k < kCanon ? (my_occ >> k & 1u) : (k - kCanon < n_ovf);
+#if SLR_GATHER_SHIFT_SHARE
+        uint4 e = used ? tab[k * kCols + tid] : none;
+        if (k == 0) e.w = lane_share;           // the spare word of the lane's first list entry
+        __stcg(dst + k * 32, e);
+#else
         __stcg(dst + k * 32, used ? tab[k * kCols + tid] : none);
+#endif
     }
     // slots past the shared table were written in place; pad this lane's unused ones
     for (int k = max(my_hi, kSmemSlots); k < kmax; ++k) __stcg(dst + k * 32, none);
@@ -246,6 +281,10 @@ struct RowCtx {
     float eps;
     bool in_top, in_bot;
     bool raw;             // flagged tile: write un-normalised sums, heavy_finish_kernel divides
+#if SLR_GATHER_SHIFT_SHARE
+    unsigned share;       // warp-uniform: slot pairs handled by SHFL.UP in this row pair
+    unsigned mine;        // of those, the pairs for which THIS lane takes the neighbour's data
+#endif
 };
 
 // K  = compile-time number of register-resident slots (the warp's list length rounded up);
@@ -300,11 +339,36 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
         #pragma unroll
         for (int kb = 0; kb < K; kb += B) {
             float4 v[GI][B];
+#if SLR_GATHER_SHIFT_SHARE
+            #pragma unroll
+            for (int gi = 0; gi < GI; ++gi) {
+                #pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    const int pi = east_pair(kb + k);
+                    const bool take = pi >= 0 && pair_west(pi) >= kb && (c.mine >> pi & 1u);
+                    if (!take) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
+                }
+            }
+            #pragma unroll
+            for (int gi = 0; gi < GI; ++gi) {
+                #pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    const int pi = east_pair(kb + k);
+                    if (pi >= 0 && pair_west(pi) >= kb && (c.share >> pi & 1u)) {          // warp-uniform
+                        const float4 w = v[gi][pair_west(pi) - kb];
+                        const float4 t = make_float4(__shfl_up_sync(0xffffffffu, w.x, 1), __shfl_up_sync(0xffffffffu, w.y, 1),
+                                                     __shfl_up_sync(0xffffffffu, w.z, 1), __shfl_up_sync(0xffffffffu, w.w, 1));
+                        if (c.mine >> pi & 1u) v[gi][k] = t;
+                    }
+                }
+            }
+#else
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
                 for (int k = 0; k < B; ++k) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
             }
+#endif
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
@@ -471,6 +535,15 @@ rowgather_kernel(const GatherParams prm)
         pk[k] = e.x;
         wt[k] = __uint_as_float(e.y);
         wb[k] = __uint_as_float(e.z);
+#if SLR_GATHER_SHIFT_SHARE
+        if (k == 0) {
+            c.share = 0u;
+            #pragma unroll
+            for (int pi = 0; pi < kSlotPairs; ++pi)
+                if (__popc(__ballot_sync(0xffffffffu, e.w >> pi & 1u)) >= kShareMinLanes) c.share |= 1u << pi;
+            c.mine = e.w & c.share;
+        }
+#endif
     }
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
     // the list length is warp-uniform: pick the unroll that fits

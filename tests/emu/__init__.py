@@ -47,6 +47,13 @@ def variant(tag, defines):
         _lib = saved
 
 
+def shfl_up_calls():
+    """Lane-level __shfl_up_sync calls executed so far by the current library (emu::kShflUp = 2)."""
+    fn = lib().emu_collective_calls
+    fn.restype = ctypes.c_ulonglong
+    return int(fn(2))
+
+
 def call(name, *args):
     L = lib()
     rc = getattr(L, name)(*args)

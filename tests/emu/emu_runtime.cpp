@@ -232,9 +232,12 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body)
     g_body = nullptr;
 }
 
+static unsigned long long g_collective_calls[16];
+
 uint64_t collective(Op op, unsigned mask, uint64_t value, int param)
 {
     Lane* me = g_cur;
+    ++g_collective_calls[(int)op & 15];
     const unsigned lane = (me->tid.x + blockDim.x * (me->tid.y + blockDim.y * me->tid.z)) & 31u;
     if (!(mask >> lane & 1u)) die("a lane calls a warp collective with a mask that does not name it");
     me->op = op; me->mask = mask; me->value = value; me->param = param;
@@ -259,3 +262,6 @@ void misaligned(const void* p, size_t a)
 }
 
 }  // namespace emu
+
+// per-op count of warp collectives executed so far (tests use it to see that a code path was taken)
+extern "C" unsigned long long emu_collective_calls(int op) { return emu::g_collective_calls[op & 15]; }

@@ -276,3 +276,41 @@ def test_emu_static_tile_fast_path_variant_is_bit_identical():
         assert np.array_equal(a, b)
     want = oracle.joint_splat_baseline(feat, Z, motion, (0, 3, N - 1))
     assert rel_err(fast[0][3:4], want) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["smooth", "A", "B"])
+def test_emu_shift_share_variant_is_bit_identical(kind):
+    """-DSLR_GATHER_SHIFT_SHARE=1 (prepared, compiled out of the product build until measured on a
+    B200): east slots take their data from the left lane's west slot by SHFL.UP where expand_kernel
+    found the flow locally one-to-one.  Same bits as the general path; the shuffles really happen
+    for smooth flow."""
+    H, W, C, N = 32, 96, 9, 6
+    feat, Z, motion = _scene(H, W, C, "B" if kind == "B" else "A", 13)
+    if kind == "smooth":        # a gentle shear: one-to-one everywhere, fractional landings
+        ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+        motion = np.stack([0.37 + 0.004 * ys, -0.21 + 0.003 * xs])[None].astype(np.float32)
+    tail = np.abs(feat[:, :1]) + 0.5
+    base = emu.Scene(feat, Z, motion, tail=tail).frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
+    with emu.variant("shift", ["-DSLR_GATHER_SHIFT_SHARE=1"]):
+        before = emu.shfl_up_calls()
+        fast = emu.Scene(feat, Z, motion, tail=tail).frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
+        shuffles = emu.shfl_up_calls() - before
+    for a, b in zip(base, fast):
+        assert np.array_equal(a, b)
+    if kind == "smooth":
+        assert shuffles > 0
+    want = oracle.joint_splat_baseline(feat, Z, motion, (0, 3, N - 1))
+    assert rel_err(fast[0][3:4], want) <= TOL
+
+
+def test_emu_both_prepared_variants_together():
+    H, W, C, N = 24, 96, 4, 5
+    feat, Z, _ = _scene(H, W, C, "A", 14)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    motion = np.zeros((1, 2, H, W), dtype=np.float32)
+    motion[0, 0, :, 64:] = 0.6 + 0.01 * ys[:, 64:]         # the backward splat reaches a few pixels into columns < 64
+    base = emu.Scene(feat, Z, motion).frames(0, N - 1, 0, N)
+    with emu.variant("both", ["-DSLR_GATHER_SHIFT_SHARE=1", "-DSLR_STATIC_TILE_FASTPATH=1"]):
+        sc = emu.Scene(feat, Z, motion)
+        fast = sc.frames(0, N - 1, 0, N)
+    assert np.array_equal(base, fast) and sc.stats["static"] > 0
