@@ -12,8 +12,18 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def pytest_addoption(parser):
+    parser.addoption("--slr-lib", default=os.environ.get("SLR_TEST_LIB"),
+                     help="run the GPU tests against another build of libslr_splat.so (a compile-time variant "
+                          "prebuilt by profiles/build_variants.py); default: the product build")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    lib = config.getoption("--slr-lib")
+    if lib:
+        from slr_sfs_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(lib)
 
 
 def load_golden(name):
