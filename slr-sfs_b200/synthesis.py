@@ -15,7 +15,7 @@ of the sm_100a library, nothing is synchronised with the host, and no
 intermediate ``tenInput`` tensor is materialised.
 
 Two algorithms, same results up to fp32 summation order:
-  * ``frames`` / ``frame``   -- gather pipeline (csrc/clip_pipeline.cu), the fast path;
+  * ``frames`` / ``frame``   -- gather pipeline (csrc/clip_plan.cu, csrc/clip_gather.cu), the fast path;
   * ``frame_scatter``        -- atomic scatter + normalise (csrc/splat_ops.cu), the
                                 design BASELINE.json sketches, kept as measured baseline.
 """
@@ -118,8 +118,8 @@ class JointSplat:
     positions C..C+n_tail-1 of the accumulator.
     """
 
-    #: frames per slr_clip_frames launch (bigger batches amortise the Euler chains,
-    #: smaller ones keep the landing table and the bins inside the 126 MB L2)
+    #: frames per slr_clip_bin / expand / gather launch (the Euler chains are integrated once per run
+    #: of frames whatever the batch; 6-20 measured within 1 %, profiles/README.md)
     batch = int(os.environ.get("SLR_BATCH", "12"))
     #: overlap plan + expand of the next batch with the gather of the current one (two streams)
     pipeline = True
