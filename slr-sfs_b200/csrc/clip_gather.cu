@@ -58,6 +58,15 @@ namespace slr {
 // results); compiled out until it has been measured and parity-tested on a B200.
 #define SLR_GATHER_SHIFT_SHARE 0
 #endif
+#ifndef SLR_GATHER_TAIL_UNROLL
+// 0: list slots beyond the register-resident ones are walked one at a time (list entry, then the
+// source it names: two dependent loads per slot and channel group).  T > 0: T slots at a time, their
+// list entries (read through L1: they are re-read for every channel group) and then their sources
+// loaded as independent batches.  In the benchmark scene 11-12 % of the row pairs have such tails
+// (convergence zones), 5-17 slots long on average.  Prepared and checked on the CPU
+// emulation (bit-identical); compiled out until measured and parity-tested on a B200.
+#define SLR_GATHER_TAIL_UNROLL 0
+#endif
 #ifndef SLR_EXPAND_MINBLOCKS
 #define SLR_EXPAND_MINBLOCKS 6
 #endif
@@ -391,6 +400,28 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
         #pragma unroll
         for (int gi = 0; gi < GI; ++gi) {
             if (K == kRegSlots) {
+#if SLR_GATHER_TAIL_UNROLL
+                constexpr int T = SLR_GATHER_TAIL_UNROLL;
+                for (int k0 = kRegSlots; k0 < c.kmax; k0 += T) {
+                    uint4 e[T];
+                    float4 t[T];
+                    #pragma unroll
+                    for (int j = 0; j < T; ++j)          // slots past kmax: the zero pixel with zero weights
+                        e[j] = k0 + j < c.kmax ? __ldg(c.list + (k0 + j) * 32) : make_uint4((unsigned)c.P, 0u, 0u, 0u);
+                    #pragma unroll
+                    for (int j = 0; j < T; ++j) t[j] = __ldg(px16(Gg + gi * gstride, e[j].x));
+                    #pragma unroll
+                    for (int j = 0; j < T; ++j) {
+                        if (k0 + j < c.kmax) {           // same FMAs in the same order as the one-at-a-time loop
+                            const float w0 = __uint_as_float(e[j].y), w1 = __uint_as_float(e[j].z);
+                            at[gi].x = fmaf(t[j].x, w0, at[gi].x); at[gi].y = fmaf(t[j].y, w0, at[gi].y);
+                            at[gi].z = fmaf(t[j].z, w0, at[gi].z); at[gi].w = fmaf(t[j].w, w0, at[gi].w);
+                            ab[gi].x = fmaf(t[j].x, w1, ab[gi].x); ab[gi].y = fmaf(t[j].y, w1, ab[gi].y);
+                            ab[gi].z = fmaf(t[j].z, w1, ab[gi].z); ab[gi].w = fmaf(t[j].w, w1, ab[gi].w);
+                        }
+                    }
+                }
+#else
                 for (int k = kRegSlots; k < c.kmax; ++k) {
                     const uint4 e = __ldcg(c.list + k * 32);
                     const float4 t = __ldg(px16(Gg + gi * gstride, e.x));
@@ -400,6 +431,7 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
                     ab[gi].x = fmaf(t.x, w1, ab[gi].x); ab[gi].y = fmaf(t.y, w1, ab[gi].y);
                     ab[gi].z = fmaf(t.z, w1, ab[gi].z); ab[gi].w = fmaf(t.w, w1, ab[gi].w);
                 }
+#endif
             }
             float* og = o + 4 * gi * ostride;
             const float rt[4] = {at[gi].x * inv_t, at[gi].y * inv_t, at[gi].z * inv_t, at[gi].w * inv_t};

@@ -314,3 +314,19 @@ def test_emu_both_prepared_variants_together():
         sc = emu.Scene(feat, Z, motion)
         fast = sc.frames(0, N - 1, 0, N)
     assert np.array_equal(base, fast) and sc.stats["static"] > 0
+
+
+def test_emu_tail_unroll_variant_is_bit_identical():
+    """-DSLR_GATHER_TAIL_UNROLL=4 (prepared, compiled out): list slots beyond the register-resident
+    16 are loaded four at a time.  Convergent flows give such tails; same bits as the default."""
+    H, W, C, N = 40, 72, 6, 3
+    feat, Z, sink, squeeze = _sink_scene(H, W, C, 9)
+    for m in (sink, squeeze):
+        sc = emu.Scene(feat, Z, m)
+        base = sc.frames(0, N - 1, 1, 2)
+        with emu.variant("tail4", ["-DSLR_GATHER_TAIL_UNROLL=4"]):
+            fast = emu.Scene(feat, Z, m).frames(0, N - 1, 1, 2)
+        assert np.array_equal(base, fast)
+    with emu.variant("all", ["-DSLR_GATHER_TAIL_UNROLL=4", "-DSLR_GATHER_SHIFT_SHARE=1", "-DSLR_STATIC_TILE_FASTPATH=1"]):
+        every = emu.Scene(feat, Z, squeeze).frames(0, N - 1, 1, 2)
+    assert np.array_equal(every, fast)
