@@ -62,5 +62,9 @@ if __name__ == "__main__":
     rows = [run(768, 1024), run(768, 1024, two_layer=True)]
     for (H, W, b) in [(256, 256, 12), (512, 512, 12), (1024, 1024, 8), (1536, 2048, 3)]:
         rows.append(run(H, W, batch=b))
+    if "--batches" in sys.argv:      # small frames are launch-bound: fewer, larger batches (kMaxFrames = 64)
+        for (H, W) in [(256, 256), (512, 512)]:
+            for b in (20, 30, 60):
+                rows.append(run(H, W, batch=b))
     for r in rows:
         print(json.dumps(r))

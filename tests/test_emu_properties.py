@@ -10,7 +10,7 @@ from conftest import rel_err
 
 emu = pytest.importorskip("emu", reason="tests/emu")
 TOL = 1e-4
-COMMON = dict(deadline=None, max_examples=60, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+COMMON = dict(deadline=None, max_examples=60, derandomize=True, database=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
                                                                   HealthCheck.function_scoped_fixture])
 
 
