@@ -78,6 +78,15 @@ int slr_maxwarpnorm(const float* in, const float* flow, float* scratch, float* o
 int slr_euler(const float* motion, float sign, int T, float* disp, float* visible,
               int64_t H, int64_t W, slr_stream_t stream);
 
+/* Backward of slr_euler with respect to the motion field (the reference's chain is
+ * differentiable through the sampled values, euler_integration_manipulator.py:37-38, which is
+ * what --train_motion relies on: models/animating_softmax_splating.py:514-580).  grad_motion
+ * [2,H,W] is overwritten with
+ *   sum over VALID chains p and their steps k of sign * grad_disp[:, p] at the sample visited in step k;
+ * chains that end invalid carry the sentinel constant (:53-55) and contribute nothing. */
+int slr_euler_grad_motion(const float* motion, float sign, int T, const float* grad_disp,
+                          float* grad_motion, int64_t H, int64_t W, slr_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Joint block level: what forward_flow() does between the encoder and the
  * decoder (models/animating_softmax_splating.py:847-924 and

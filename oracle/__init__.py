@@ -154,6 +154,17 @@ def euler(motion, T):
     return disp, vis
 
 
+def euler_grad_motion(motion, T, grad_disp):
+    """d(sum(displacements * grad_disp)) / d(motion) as autograd derives it from the reference's
+    euler_integration (euler_integration_manipulator.py:36-55); see orc_euler_grad_motion."""
+    motion, grad_disp = _c(motion), _c(grad_disp)
+    assert motion.ndim == 4 and motion.shape[0] == 1 and motion.shape[1] == 2 and grad_disp.shape == motion.shape
+    H, W = motion.shape[2:]
+    out = np.zeros_like(motion)
+    _oracle_lib().orc_euler_grad_motion(_p(motion), ctypes.c_int(int(T)), _p(grad_disp), _p(out), _i64(H), _i64(W))
+    return out
+
+
 # ----------------------------------------------------------------------------
 # the reference's own kernels on the CPU (oracle/_ref)
 # ----------------------------------------------------------------------------

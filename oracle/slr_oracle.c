@@ -245,3 +245,38 @@ void orc_euler(const float *motion, int T, float *disp, float *visible, i64 H, i
             visible[p] = invalid ? 0.0f : 1.0f;
         }
 }
+
+/* Gradient of orc_euler's displacements with respect to the motion field, as torch autograd
+ * derives it from the reference's eager ops (euler_integration_manipulator.py:36-55):
+ *   destination_coords + motion[0][:, iy, ix]     differentiable in the sampled VALUES only (:37-38)
+ *   destination_coords[invalid] = coord[invalid]  cuts the chain of a pixel once it is invalid (:45-46)
+ *   displacements[invalid] = max(H,W)+1           a constant: no gradient for pixels that end invalid (:53-55)
+ * Invalidity is sticky, so a pixel valid at the end was valid throughout and every one of its T
+ * samples receives grad_disp[:, p].  grad_motion is overwritten. */
+void orc_euler_grad_motion(const float *motion, int T, const float *gdisp, float *gmotion, i64 H, i64 W)
+{
+    const i64 P = H * W;
+    for (i64 i = 0; i < 2 * P; ++i) gmotion[i] = 0.0f;
+    for (i64 y = 0; y < H; ++y)
+        for (i64 x = 0; x < W; ++x) {
+            const float cx = (float)x, cy = (float)y;
+            float dx = cx, dy = cy;
+            int invalid = 0;
+            for (int k = 1; k <= T && !invalid; ++k) {
+                const i64 ix = (i64)rintf(dx), iy = (i64)rintf(dy);
+                dx = dx + motion[0 * P + iy * W + ix];
+                dy = dy + motion[1 * P + iy * W + ix];
+                if (dx > (float)(W - 1) || dx < 0.0f || dy > (float)(H - 1) || dy < 0.0f) invalid = 1;
+            }
+            if (invalid) continue;
+            const i64 p = y * W + x;
+            dx = cx; dy = cy;
+            for (int k = 1; k <= T; ++k) {
+                const i64 ix = (i64)rintf(dx), iy = (i64)rintf(dy);
+                gmotion[0 * P + iy * W + ix] += gdisp[0 * P + p];
+                gmotion[1 * P + iy * W + ix] += gdisp[1 * P + p];
+                dx = dx + motion[0 * P + iy * W + ix];
+                dy = dy + motion[1 * P + iy * W + ix];
+            }
+        }
+}

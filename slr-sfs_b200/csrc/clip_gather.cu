@@ -39,34 +39,6 @@ namespace slr {
 #define SLR_GATHER_FRAMES 2            // default CTA shape of rowgather_kernel: frames x row pairs
 #define SLR_GATHER_PAIRS 2             // (measured: 2x2 = 4x1 > 1x4 > 2x4 > 4x4, profiles/r01/sweep_variants.jsonl; 1x4 kept for A/B)
 #endif
-#ifndef SLR_STATIC_TILE_FASTPATH
-// 1: destination tiles whose 256 pixels all have zero motion and whose bin is empty (44 % of the
-// tiles of the benchmark scene) get no lists at all: expand_kernel only flags them (3) and
-// rowgather_kernel reads each pixel's own source directly.  Prepared and checked on the CPU
-// emulation (tests/test_emu_kernels.py builds it with -DSLR_STATIC_TILE_FASTPATH=1); compiled out
-// until it has been measured and parity-tested on a B200.
-#define SLR_STATIC_TILE_FASTPATH 0
-#endif
-#ifndef SLR_GATHER_SHIFT_SHARE
-// 1: where the flow is locally one-to-one, the source in a lane's EAST slot (its north-east /
-// south-east corner lands on the lane's pixel) is the source in the WEST slot of the lane to its
-// left.  expand_kernel records, per lane, for which of the six (west, east) slot pairs that holds;
-// rowgather_kernel then takes the east slot's data from the neighbouring lane with four SHFL.UP
-// and issues the east slot's LDG.128 only for the lanes where it does not hold (lane 0, collisions)
-// -- up to half of the loads of the hot loop.  A pair is treated this way only in row pairs where
-// at least kShareMinLanes lanes benefit.  Prepared and checked on the CPU emulation (bit-identical
-// results); compiled out until it has been measured and parity-tested on a B200.
-#define SLR_GATHER_SHIFT_SHARE 0
-#endif
-#ifndef SLR_GATHER_TAIL_UNROLL
-// 0: list slots beyond the register-resident ones are walked one at a time (list entry, then the
-// source it names: two dependent loads per slot and channel group).  T > 0: T slots at a time, their
-// list entries (read through L1: they are re-read for every channel group) and then their sources
-// loaded as independent batches.  In the benchmark scene 11-12 % of the row pairs have such tails
-// (convergence zones), 5-17 slots long on average.  Prepared and checked on the CPU
-// emulation (bit-identical); compiled out until measured and parity-tested on a B200.
-#define SLR_GATHER_TAIL_UNROLL 0
-#endif
 #ifndef SLR_EXPAND_MINBLOCKS
 #define SLR_EXPAND_MINBLOCKS 6
 #endif
@@ -121,15 +93,6 @@ __host__ __device__ constexpr SlotRole slot_role(int k)
     return k < 8 ? ((k & 1) ? kBottomOnly : kBoth) : (k < kCanon ? kTopOnly : kBoth);
 }
 
-#if SLR_GATHER_SHIFT_SHARE
-// (west, east) canonical slot pairs: same direction and row offset, dx = 0 / 1.
-constexpr int kSlotPairs = 6;
-constexpr int kShareMinLanes = 16;
-__host__ __device__ constexpr int pair_west(int pi) { return pi < 4 ? pi : 8 + 2 * (pi - 4); }
-__host__ __device__ constexpr int pair_east(int pi) { return pi < 4 ? 4 + pi : 9 + 2 * (pi - 4); }
-// pair index of an east slot, -1 for every other slot
-__host__ __device__ constexpr int east_pair(int k) { return (k >= 4 && k < 8) ? k - 4 : k == 9 ? 4 : k == 11 ? 5 : -1; }
-#endif
 
 // ---------------------------------------------------------------------------
 // expand_kernel
@@ -158,18 +121,6 @@ expand_kernel(const GatherParams prm)
     const int64_t pair0 = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile;
     uint4* lists_tile = prm.lists + pair0 * (kListDepth * 32);
 
-#if SLR_STATIC_TILE_FASTPATH
-    {   // nothing lands here and nothing moves here: every pixel receives exactly itself
-        const int X = tx * TW + (tid & 31), Y = ty * TH + (tid >> 5);
-        const bool inside = X < prm.W && Y < prm.H;
-        const int64_t pix = inside ? (int64_t)Y * prm.W + X : 0;
-        const bool still = !inside || (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f);
-        if (__syncthreads_and(still && beg == end)) {
-            if (tid == 0) prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = 3u;
-            return;
-        }
-    }
-#endif
     for (int i = tid; i < kCanon * kCols; i += TILE) tab[i] = make_uint4(kEmpty, 0u, 0u, 0u);
     if (tid < kCols) { occ[tid] = 0u; ovf[tid] = 0u; }
     if (tid == 0) excess_full = 0u;
@@ -247,25 +198,11 @@ expand_kernel(const GatherParams prm)
     const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
     const int64_t pair = pair0 + (tid >> 5);
     if ((tid & 31) == 0) prm.row_k[pair] = (unsigned)kmax;
-#if SLR_GATHER_SHIFT_SHARE
-    unsigned lane_share = 0u;        // bit pi: this lane's east slot of pair pi holds the left lane's west source
-    if ((tid & 31) != 0) {
-        #pragma unroll
-        for (int pi = 0; pi < kSlotPairs; ++pi)     // unclaimed slots compare as equal: both read the all-zero pixel
-            lane_share |= (tab[pair_east(pi) * kCols + tid].x == tab[pair_west(pi) * kCols + tid - 1].x ? 1u : 0u) << pi;
-    }
-#endif
     uint4* dst = prm.lists + pair * (kListDepth * 32) + (tid & 31);
     const uint4 none = make_uint4((unsigned)P, 0u, 0u, 0u);     // the zero pixel, weights 0
     for (int k = 0; k < min(kmax, kSmemSlots); ++k) {
         const bool used = k < kCanon ? (my_occ >> k & 1u) : (k - kCanon < n_ovf);
-#if SLR_GATHER_SHIFT_SHARE
-        uint4 e = used ? tab[k * kCols + tid] : none;
-        if (k == 0) e.w = lane_share;           // the spare word of the lane's first list entry
-        __stcg(dst + k * 32, e);
-#else
         __stcg(dst + k * 32, used ? tab[k * kCols + tid] : none);
-#endif
     }
     // slots past the shared table were written in place; pad this lane's unused ones
     for (int k = max(my_hi, kSmemSlots); k < kmax; ++k) __stcg(dst + k * 32, none);
@@ -290,10 +227,6 @@ struct RowCtx {
     float eps;
     bool in_top, in_bot;
     bool raw;             // flagged tile: write un-normalised sums, heavy_finish_kernel divides
-#if SLR_GATHER_SHIFT_SHARE
-    unsigned share;       // warp-uniform: slot pairs handled by SHFL.UP in this row pair
-    unsigned mine;        // of those, the pairs for which THIS lane takes the neighbour's data
-#endif
 };
 
 // K  = compile-time number of register-resident slots (the warp's list length rounded up);
@@ -348,36 +281,11 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
         #pragma unroll
         for (int kb = 0; kb < K; kb += B) {
             float4 v[GI][B];
-#if SLR_GATHER_SHIFT_SHARE
-            #pragma unroll
-            for (int gi = 0; gi < GI; ++gi) {
-                #pragma unroll
-                for (int k = 0; k < B; ++k) {
-                    const int pi = east_pair(kb + k);
-                    const bool take = pi >= 0 && pair_west(pi) >= kb && (c.mine >> pi & 1u);
-                    if (!take) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
-                }
-            }
-            #pragma unroll
-            for (int gi = 0; gi < GI; ++gi) {
-                #pragma unroll
-                for (int k = 0; k < B; ++k) {
-                    const int pi = east_pair(kb + k);
-                    if (pi >= 0 && pair_west(pi) >= kb && (c.share >> pi & 1u)) {          // warp-uniform
-                        const float4 w = v[gi][pair_west(pi) - kb];
-                        const float4 t = make_float4(__shfl_up_sync(0xffffffffu, w.x, 1), __shfl_up_sync(0xffffffffu, w.y, 1),
-                                                     __shfl_up_sync(0xffffffffu, w.z, 1), __shfl_up_sync(0xffffffffu, w.w, 1));
-                        if (c.mine >> pi & 1u) v[gi][k] = t;
-                    }
-                }
-            }
-#else
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
                 for (int k = 0; k < B; ++k) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
             }
-#endif
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
@@ -400,28 +308,6 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
         #pragma unroll
         for (int gi = 0; gi < GI; ++gi) {
             if (K == kRegSlots) {
-#if SLR_GATHER_TAIL_UNROLL
-                constexpr int T = SLR_GATHER_TAIL_UNROLL;
-                for (int k0 = kRegSlots; k0 < c.kmax; k0 += T) {
-                    uint4 e[T];
-                    float4 t[T];
-                    #pragma unroll
-                    for (int j = 0; j < T; ++j)          // slots past kmax: the zero pixel with zero weights
-                        e[j] = k0 + j < c.kmax ? __ldg(c.list + (k0 + j) * 32) : make_uint4((unsigned)c.P, 0u, 0u, 0u);
-                    #pragma unroll
-                    for (int j = 0; j < T; ++j) t[j] = __ldg(px16(Gg + gi * gstride, e[j].x));
-                    #pragma unroll
-                    for (int j = 0; j < T; ++j) {
-                        if (k0 + j < c.kmax) {           // same FMAs in the same order as the one-at-a-time loop
-                            const float w0 = __uint_as_float(e[j].y), w1 = __uint_as_float(e[j].z);
-                            at[gi].x = fmaf(t[j].x, w0, at[gi].x); at[gi].y = fmaf(t[j].y, w0, at[gi].y);
-                            at[gi].z = fmaf(t[j].z, w0, at[gi].z); at[gi].w = fmaf(t[j].w, w0, at[gi].w);
-                            ab[gi].x = fmaf(t[j].x, w1, ab[gi].x); ab[gi].y = fmaf(t[j].y, w1, ab[gi].y);
-                            ab[gi].z = fmaf(t[j].z, w1, ab[gi].z); ab[gi].w = fmaf(t[j].w, w1, ab[gi].w);
-                        }
-                    }
-                }
-#else
                 for (int k = kRegSlots; k < c.kmax; ++k) {
                     const uint4 e = __ldcg(c.list + k * 32);
                     const float4 t = __ldg(px16(Gg + gi * gstride, e.x));
@@ -431,7 +317,6 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
                     ab[gi].x = fmaf(t.x, w1, ab[gi].x); ab[gi].y = fmaf(t.y, w1, ab[gi].y);
                     ab[gi].z = fmaf(t.z, w1, ab[gi].z); ab[gi].w = fmaf(t.w, w1, ab[gi].w);
                 }
-#endif
             }
             float* og = o + 4 * gi * ostride;
             const float rt[4] = {at[gi].x * inv_t, at[gi].y * inv_t, at[gi].z * inv_t, at[gi].w * inv_t};
@@ -457,66 +342,6 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
     else gather_rows<NT, K, 1>(c, pk, wt, wb, sum_t, sum_b);
 }
 
-#if SLR_STATIC_TILE_FASTPATH
-// A row pair of a static tile (flag 3): each pixel receives exactly its own source with weight
-// a + (1 - a), as expand_kernel's static insert + the general gather would compute it.
-template <int NT>
-__device__ __forceinline__ void gather_static_rows(const GatherParams& prm, int f, int64_t pix, bool in_top, bool in_bot)
-{
-    const int64_t P = prm.P;
-    const float a_f = prm.alphas.a[f];
-    const float w = a_f + (1.0f - a_f);
-    const unsigned p_t = in_top ? (unsigned)pix : (unsigned)P;            // P = the all-zero pixel
-    const unsigned p_b = in_bot ? (unsigned)(pix + prm.W) : (unsigned)P;
-    const int64_t sstride = P + 1;
-    float sum_t[NT + 1], sum_b[NT + 1];
-    #pragma unroll
-    for (int t = 0; t <= NT; ++t) {
-        sum_t[t] = fmaf(__ldg(prm.S + (int64_t)t * sstride + p_t), w, 0.0f);
-        sum_b[t] = fmaf(__ldg(prm.S + (int64_t)t * sstride + p_b), w, 0.0f);
-    }
-    const float inv_t = 1.0f / fmaxf(sum_t[NT], prm.eps), inv_b = 1.0f / fmaxf(sum_b[NT], prm.eps);
-    const size_t gstride = (size_t)(P + 1) * 16;
-    float* o = prm.out + (int64_t)f * prm.C * P + pix;
-    const char* Gg = prm.G;
-    for (int g = 0; g < prm.groups; g += 2, Gg += 2 * gstride, o += 8 * P) {
-        float4 vt[2], vb[2];
-        #pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-            const bool has = g + gi < prm.groups;
-            vt[gi] = has ? __ldg(px16(Gg + gi * gstride, p_t)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            vb[gi] = has ? __ldg(px16(Gg + gi * gstride, p_b)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        #pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-            const float rt[4] = {fmaf(vt[gi].x, w, 0.0f) * inv_t, fmaf(vt[gi].y, w, 0.0f) * inv_t,
-                                 fmaf(vt[gi].z, w, 0.0f) * inv_t, fmaf(vt[gi].w, w, 0.0f) * inv_t};
-            const float rb[4] = {fmaf(vb[gi].x, w, 0.0f) * inv_b, fmaf(vb[gi].y, w, 0.0f) * inv_b,
-                                 fmaf(vb[gi].z, w, 0.0f) * inv_b, fmaf(vb[gi].w, w, 0.0f) * inv_b};
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = 4 * (g + gi) + j;
-                if (c < prm.C) {
-                    if (in_top) __stcs(o + (int64_t)(4 * gi + j) * P, rt[j]);
-                    if (in_bot) __stcs(o + (int64_t)(4 * gi + j) * P + prm.W, rb[j]);
-                }
-            }
-        }
-    }
-    #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        if (!(r ? in_bot : in_top)) continue;
-        const float* sum = r ? sum_b : sum_t;
-        const int64_t px = pix + (r ? prm.W : 0);
-        if (prm.aux) {
-            float* a = prm.aux + (int64_t)f * (NT + 1) * P + px;
-            #pragma unroll
-            for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sum[j];
-        }
-        if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
-    }
-}
-#endif
 
 // CTA shape: F frames x R row pairs (warps) of one destination tile, F * R * 32 threads.  Warps of
 // the SAME tile in consecutive frames read source regions that differ only by one frame's
@@ -540,12 +365,6 @@ rowgather_kernel(const GatherParams prm)
     const int X = tx * TW + (tid & 31), Y = ty * TH + 2 * pr;
     const int64_t P = prm.P;
     const int64_t pix = (int64_t)Y * prm.W + X;
-#if SLR_STATIC_TILE_FASTPATH
-    if (flag == 3u) {
-        gather_static_rows<NT>(prm, f, pix, X < prm.W && Y < prm.H, X < prm.W && Y + 1 < prm.H);
-        return;
-    }
-#endif
     const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + pr;
     const int kmax = (int)__ldg(prm.row_k + pair);
 
@@ -567,15 +386,6 @@ rowgather_kernel(const GatherParams prm)
         pk[k] = e.x;
         wt[k] = __uint_as_float(e.y);
         wb[k] = __uint_as_float(e.z);
-#if SLR_GATHER_SHIFT_SHARE
-        if (k == 0) {
-            c.share = 0u;
-            #pragma unroll
-            for (int pi = 0; pi < kSlotPairs; ++pi)
-                if (__popc(__ballot_sync(0xffffffffu, e.w >> pi & 1u)) >= kShareMinLanes) c.share |= 1u << pi;
-            c.mine = e.w & c.share;
-        }
-#endif
     }
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
     // the list length is warp-uniform: pick the unroll that fits

@@ -74,7 +74,8 @@ __device__ __forceinline__ void euler_step(EulerState& s, const float* __restric
     const float my = __fmul_rn(sign, __ldg(motion + P + at));
     s.dx = __fadd_rn(s.dx, mx);
     s.dy = __fadd_rn(s.dy, my);
-    s.invalid = s.invalid || s.dx > xmax || s.dx < 0.0f || s.dy > ymax || s.dy < 0.0f;
+    // a NaN coordinate fails the test (see euler_kernel): no out-of-range index on the next step
+    s.invalid = s.invalid || !(s.dx <= xmax && s.dx >= 0.0f && s.dy <= ymax && s.dy >= 0.0f);
     if (s.invalid) { s.dx = cx; s.dy = cy; }
 }
 

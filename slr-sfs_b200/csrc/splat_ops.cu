@@ -195,13 +195,55 @@ euler_kernel(const float* __restrict__ motion, float sign, int T, float* __restr
         const float my = __fmul_rn(sign, __ldg(motion + P + at));
         dx = __fadd_rn(dx, mx);
         dy = __fadd_rn(dy, my);
-        invalid = invalid || dx > xmax || dx < 0.0f || dy > ymax || dy < 0.0f;
+        // written so that a NaN coordinate (NaN / inf motion) FAILS the test: the chain turns invalid
+        // instead of indexing the field with (int64_t)rintf(NaN)
+        invalid = invalid || !(dx <= xmax && dx >= 0.0f && dy <= ymax && dy >= 0.0f);
         if (invalid) { dx = cx; dy = cy; }
     }
     const float sentinel = (float)(max(H, W) + 1);
     disp[p] = invalid ? sentinel : __fsub_rn(dx, cx);
     disp[P + p] = invalid ? sentinel : __fsub_rn(dy, cy);
     if (visible) visible[p] = invalid ? 0.0f : 1.0f;
+}
+
+// ---------------------------------------------------------------------------
+// euler backward: gradient of the displacements with respect to the motion field.
+// In the reference the chain is differentiable through the VALUES it samples
+// (destination_coords + motion[0][:, iy, ix], euler_integration_manipulator.py:37-38;
+// the rounded indices carry no gradient), and a pixel that ends invalid has its
+// displacement overwritten by the sentinel constant (:53-55), i.e. no gradient.  So
+//   grad_motion[:, q] += sign * grad_disp[:, p]   for every step of a VALID chain p that sampled q.
+// One thread per pixel: the chain is walked once to learn its validity, then again to
+// add the gradient at every visited sample (fp32 reductions at L2).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+euler_grad_kernel(const float* __restrict__ motion, float sign, int T, const float* __restrict__ gdisp,
+                  float* __restrict__ gmotion, int H, int W)
+{
+    const int64_t P = (int64_t)H * W;
+    const int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (p >= P) return;
+    const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    const float cx = (float)x, cy = (float)y;
+    const float xmax = (float)(W - 1), ymax = (float)(H - 1);
+    float dx = cx, dy = cy;
+    bool invalid = false;
+    for (int k = 0; k < T && !invalid; ++k) {
+        const int64_t at = (int64_t)rintf(dy) * W + (int64_t)rintf(dx);
+        dx = __fadd_rn(dx, __fmul_rn(sign, __ldg(motion + at)));
+        dy = __fadd_rn(dy, __fmul_rn(sign, __ldg(motion + P + at)));
+        invalid = !(dx <= xmax && dx >= 0.0f && dy <= ymax && dy >= 0.0f);
+    }
+    if (invalid) return;
+    const float gx = __fmul_rn(sign, gdisp[p]), gy = __fmul_rn(sign, gdisp[P + p]);
+    dx = cx; dy = cy;
+    for (int k = 0; k < T; ++k) {
+        const int64_t at = (int64_t)rintf(dy) * W + (int64_t)rintf(dx);
+        red_add(gmotion + at, gx);
+        red_add(gmotion + P + at, gy);
+        dx = __fadd_rn(dx, __fmul_rn(sign, __ldg(motion + at)));
+        dy = __fadd_rn(dy, __fmul_rn(sign, __ldg(motion + P + at)));
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -374,6 +416,18 @@ extern "C" int slr_euler(const float* motion, float sign, int T, float* disp, fl
     SLR_CHECK_ARGS(motion && disp && T >= 0 && H > 0 && W > 0 && H * W < (1ll << 31) && (sign == 1.0f || sign == -1.0f),
                    "slr_euler: bad arguments");
     euler_kernel<<<blocks_for(H * W), kBlock, 0, (cudaStream_t)stream_>>>(motion, sign, T, disp, visible, (int)H, (int)W);
+    return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_euler_grad_motion(const float* motion, float sign, int T, const float* grad_disp,
+                                     float* grad_motion, int64_t H, int64_t W, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(motion && grad_disp && grad_motion && T >= 0 && H > 0 && W > 0 && H * W < (1ll << 31) &&
+                   (sign == 1.0f || sign == -1.0f), "slr_euler_grad_motion: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream_;
+    SLR_CUDA(cudaMemsetAsync(grad_motion, 0, sizeof(float) * 2 * (size_t)(H * W), s));
+    if (T > 0)
+        euler_grad_kernel<<<blocks_for(H * W), kBlock, 0, s>>>(motion, sign, T, grad_disp, grad_motion, (int)H, (int)W);
     return SLR_LAUNCH_STATUS();
 }
 

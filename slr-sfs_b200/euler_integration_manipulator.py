@@ -25,12 +25,59 @@ def _as_int(destination_frame):
     return int(destination_frame)
 
 
+def _contiguous_f32(motion):
+    if motion.dtype != torch.float32 or not motion.is_contiguous():
+        motion = motion.float().contiguous()
+    return motion
+
+
+def _integrate(motion, T):
+    """One slr_euler launch: displacements [1,2,H,W], visible [1,1,H,W] after T steps."""
+    height, width = motion.shape[2:]
+    displacements = motion.new_empty(1, 2, height, width)
+    visible_pixels = motion.new_empty(1, 1, height, width)
+    with torch.cuda.device(motion.device):
+        _lib.call("slr_euler", _lib.ptr(motion), 1.0, T, _lib.ptr(displacements), _lib.ptr(visible_pixels),
+                  height, width, _lib.current_stream(motion.device))
+    return displacements, visible_pixels
+
+
+class _FunctionEuler(torch.autograd.Function):
+    """The chain with the reference's autograd behaviour: the displacements are differentiable
+    with respect to the motion VALUES sampled along each chain (reference :37-38; the rounded
+    sample positions carry no gradient), pixels that end invalid hold the sentinel constant
+    (:53-55) and pass no gradient.  This is what --train_motion needs
+    (models/animating_softmax_splating.py:514-580: the flow regressor's output goes through
+    EulerIntegration into the splat, whose gradFlow must reach the regressor)."""
+
+    @staticmethod
+    def forward(ctx, motion, T):
+        motion = _contiguous_f32(motion.detach())
+        ctx.save_for_backward(motion)
+        ctx.T = T
+        displacements, visible_pixels = _integrate(motion, T)
+        ctx.mark_non_differentiable(visible_pixels)
+        return displacements, visible_pixels
+
+    @staticmethod
+    def backward(ctx, grad_displacements, _grad_visible):
+        motion, = ctx.saved_tensors
+        height, width = motion.shape[2:]
+        grad = _contiguous_f32(grad_displacements)
+        grad_motion = motion.new_empty(1, 2, height, width)
+        with torch.cuda.device(motion.device):
+            _lib.call("slr_euler_grad_motion", _lib.ptr(motion), 1.0, ctx.T, _lib.ptr(grad), _lib.ptr(grad_motion),
+                      height, width, _lib.current_stream(motion.device))
+        return grad_motion, None
+
+
 def euler_integration(motion, destination_frame, return_all_frames=False):
     """Repeatedly integrate the Eulerian motion field; see module docstring.
 
     Returns displacements [1,2,H,W] and visible_pixels [1,1,H,W] on ``motion``'s
     device (with ``return_all_frames`` -- broken in the reference, :31,:50 -- the
-    leading dimension is destination_frame+1, one entry per step count).
+    leading dimension is destination_frame+1, one entry per step count).  Differentiable
+    with respect to ``motion`` like the reference's eager ops (see _FunctionEuler).
     """
     assert (motion.dim() == 4)
     b, c, height, width = motion.shape
@@ -40,18 +87,15 @@ def euler_integration(motion, destination_frame, return_all_frames=False):
         raise NotImplementedError()    # the reference hard-codes device='cuda' (:24-35)
     T = _as_int(destination_frame)
     assert T >= 0
-    motion = motion.detach()
-    if motion.dtype != torch.float32 or not motion.is_contiguous():
-        motion = motion.float().contiguous()
     steps = list(range(T + 1)) if return_all_frames else [T]
-    displacements = motion.new_empty(len(steps), 2, height, width)
-    visible_pixels = motion.new_empty(len(steps), 1, height, width)
-    with torch.cuda.device(motion.device):
-        stream = _lib.current_stream(motion.device)
-        for i, t in enumerate(steps):
-            _lib.call("slr_euler", _lib.ptr(motion), 1.0, t, _lib.ptr(displacements[i]),
-                      _lib.ptr(visible_pixels[i]), height, width, stream)
-    return displacements, visible_pixels
+    if motion.requires_grad and torch.is_grad_enabled():
+        results = [_FunctionEuler.apply(motion, t) for t in steps]
+    else:
+        plain = _contiguous_f32(motion.detach())
+        results = [_integrate(plain, t) for t in steps]
+    if len(results) == 1:
+        return results[0]
+    return torch.cat([r[0] for r in results], 0), torch.cat([r[1] for r in results], 0)
 
 
 class EulerIntegration(nn.Module):

@@ -75,8 +75,11 @@ class _BufferPool:
         if pick is not None:
             entries.remove(pick)
             return pick
-        return {"kind": kind, "last": {},
-                "buf": torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)}
+        # a fresh block from the caching allocator may still have queued users on the stream that
+        # allocates it (the current one); whoever writes the entry first -- possibly on another
+        # stream -- is ordered behind them like behind any previous user (take_over)
+        buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        return {"kind": kind, "last": {torch.cuda.current_stream(self.device): _event_now(self.device)}, "buf": buf}
 
     def release(self, entry):
         entries = self.free.setdefault(entry["kind"], [])
@@ -98,6 +101,13 @@ class _BufferPool:
     def used(entry, stream, event):
         """The entry's contents are needed until `event` (recorded on `stream`)."""
         entry["last"][stream] = event
+
+
+def _event_now(device):
+    """An event recorded now on the current stream of `device`."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    return ev
 
 
 def _release_all(pool, entries):
@@ -149,8 +159,10 @@ class JointSplat:
                 inputs_event.record(torch.cuda.current_stream(self.device))
         self._inputs_ready = inputs_event or None
         self._zsub = None
+        self._zsub_alloc = None        # event: the allocating stream's earlier work on the block is done
+        self._zsub_ready = None        # event: Z.max() is in _zsub (computed once, never rewritten)
         self._scene = None
-        self._prepared = None          # event: zsub and the scene buffer are built
+        self._scene_ready = None       # event: the scene buffer is built
         self._table = None             # cached clip table (see _clip_table)
         self._scene_entry = None       # pool entries behind _scene / _table["buf"]
         self._pooled = []              # everything to give back when this object dies
@@ -161,38 +173,42 @@ class JointSplat:
             stream.wait_event(self._inputs_ready)
 
     def _prepare(self):
-        """Z.max() and the pre-weighted, channel-interleaved scene buffer: built once, on the
-        current stream; users on other streams are ordered behind the `_prepared` event."""
+        """Z.max() and the pre-weighted, channel-interleaved scene buffer: each built once, on the
+        stream that first needs it; users on other streams are ordered behind its event.  Z.max()
+        is never recomputed once valid (readers of `zsub` on other streams may still be queued)."""
         cur = torch.cuda.current_stream(self.device)
-        if self._prepared is None:
-            self._wait_inputs(cur)
+        with torch.cuda.device(self.device):
+            s = _lib.current_stream(self.device)
             if self._zsub is not None:
-                self._zsub.record_stream(cur)
-            if self._scene_entry is not None:
-                _BufferPool.take_over(self._scene_entry, cur)
-            with torch.cuda.device(self.device):
-                s = _lib.current_stream(self.device)
-                if self._zsub is not None:
+                if self._zsub_ready is None:
+                    self._wait_inputs(cur)
+                    cur.wait_event(self._zsub_alloc)
+                    self._zsub.record_stream(cur)
                     _lib.call("slr_reduce_max", _lib.ptr(self.Z), self.Z.numel(), _lib.ptr(self._zsub), s)
-                if self._scene is not None:
+                    self._zsub_ready = _event_now(self.device)
+                else:
+                    cur.wait_event(self._zsub_ready)
+                    self._zsub.record_stream(cur)
+            if self._scene is not None:
+                if self._scene_ready is None:
+                    self._wait_inputs(cur)
+                    _BufferPool.take_over(self._scene_entry, cur)
                     _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self._zsub),
                               _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W, s)
-            self._prepared = torch.cuda.Event()
-            self._prepared.record(cur)
-            if self._scene_entry is not None:
-                _BufferPool.used(self._scene_entry, cur, self._prepared)
-        else:
-            cur.wait_event(self._prepared)
+                    self._scene_ready = _event_now(self.device)
+                    _BufferPool.used(self._scene_entry, cur, self._scene_ready)
+                else:
+                    cur.wait_event(self._scene_ready)
 
     def _allocate(self, scene):
         """Allocate what _prepare fills."""
         if self.z_mode == "max" and self._zsub is None:
             self._zsub = torch.empty(1, dtype=torch.float32, device=self.device)
+            self._zsub_alloc = _event_now(self.device)
         if scene and self._scene is None:
             n = _lib.load().slr_scene_bytes(self.C, self.n_tail, self.H, self.W)
             self._scene_entry = self._from_pool("scene", n)
             self._scene = self._scene_entry["buf"]
-            self._prepared = None      # (re)build everything with the scene buffer
 
     def _from_pool(self, kind, nbytes):
         pool = self._shared_state()["pool"]
@@ -226,6 +242,7 @@ class JointSplat:
             # caching allocator does not hand the old block out while queued work still uses it
             ws = st["ws"][slot] = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
             ws.record_stream(side)
+            side.wait_event(_event_now(self.device))     # behind whatever the allocating stream still had queued on the block
         return ws, ws.numel() * 4
 
     def _clip_table(self, start, end, t0, n, side):

@@ -58,3 +58,8 @@ def rel_err(a, ref):
 _TESTS = os.path.dirname(os.path.abspath(__file__))
 if _TESTS not in sys.path:
     sys.path.insert(0, _TESTS)
+
+
+@pytest.fixture(scope="session")
+def golden_euler_grad():
+    return load_golden("euler_grad_ref")

@@ -163,6 +163,26 @@ def make_euler(rng, eul):
     return out
 
 
+def make_euler_grad(rng, eul):
+    """torch autograd through the reference's euler_integration (unmodified): the gradient the
+    motion regressor receives with --train_motion (animating_softmax_splating.py:514-580)."""
+    out = {}
+    for (H, W) in [(9, 13), (16, 16)]:
+        for name, m in motion_fields(rng, H, W).items():
+            for T in [0, 1, 3, 7]:
+                g = rng.standard_normal((1, 2, H, W)).astype(np.float32)
+                mt = torch.from_numpy(m.copy()).requires_grad_(True)
+                with cpu_as_cuda():
+                    d, _ = eul.euler_integration(mt, T)
+                    if d.requires_grad:          # T = 0 returns constants (:33-34)
+                        (d * torch.from_numpy(g)).sum().backward()
+                key = f"{name}_{H}x{W}/T{T}"
+                out[f"{name}_{H}x{W}/motion"] = m
+                out[f"{key}/gdisp"] = g
+                out[f"{key}/gmotion"] = (mt.grad if mt.grad is not None else torch.zeros_like(mt)).numpy().astype(np.float32)
+    return out
+
+
 # ----------------------------------------------------------------------------
 class RefSplat(torch.nn.Module):
     """ModuleSoftsplat('summation') stand-in backed by the reference kernels on CPU."""
@@ -235,12 +255,17 @@ def make_joint(rng, base, two):
 
 
 def main():
-    argparse.ArgumentParser(description=__doc__).parse_args()
     assert oracle.ref_available(), "build oracle/_ref first (python oracle/build.py)"
     rng = np.random.default_rng(20261017)
     eul, base, two = import_reference()
-    for name, data in [("softsplat_ref", make_softsplat(rng)), ("euler_ref", make_euler(rng, eul)),
-                       ("joint_ref", make_joint(rng, base, two))]:
+    only = set(sys.argv[1:])       # e.g. `make_golden.py euler_grad_ref`: regenerate just that file
+    makers = [("softsplat_ref", lambda: make_softsplat(rng)), ("euler_ref", lambda: make_euler(rng, eul)),
+              ("joint_ref", lambda: make_joint(rng, base, two)),
+              ("euler_grad_ref", lambda: make_euler_grad(np.random.default_rng(20261018), eul))]
+    for name, make in makers:
+        if only and name not in only:
+            continue
+        data = make()
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **data)
         print(path, len(data), "arrays", os.path.getsize(path), "bytes")

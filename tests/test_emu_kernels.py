@@ -255,78 +255,15 @@ def test_emu_clip_table_bin_stats_case_shared_with_the_gpu_suite():
     clip_abi_cases.clip_table_bin_stats(clip_abi_cases.EmuBackend())
 
 
-def test_emu_static_tile_fast_path_variant_is_bit_identical():
-    """-DSLR_STATIC_TILE_FASTPATH=1 (prepared, compiled out of the product build until measured on
-    a B200): fully static tiles with empty bins get no lists; same bits as the general path."""
-    H, W, C, N = 40, 96, 5, 7
-    feat, Z, _ = _scene(H, W, C, "A", 11)
-    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
-    motion = np.zeros((1, 2, H, W), dtype=np.float32)
-    motion[0, 0, 8:24, 32:64] = 1.3 * np.sin(xs[8:24, 32:64] / 7.0)       # one moving island, static elsewhere
-    motion[0, 1, 8:24, 32:64] = -0.7
-    tail = np.abs(feat[:, :2]) + 0.5
-    sc = emu.Scene(feat, Z, motion, tail=tail)
-    base = sc.frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
-    assert sc.stats["static"] == 0
-    with emu.variant("static", ["-DSLR_STATIC_TILE_FASTPATH=1"]):
-        sc = emu.Scene(feat, Z, motion, tail=tail)
-        fast = sc.frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
-    assert 0 < sc.stats["static"] < sc.stats["tiles"]           # the island's tiles (and what it reaches) keep their lists
-    for a, b in zip(base, fast):
-        assert np.array_equal(a, b)
-    want = oracle.joint_splat_baseline(feat, Z, motion, (0, 3, N - 1))
-    assert rel_err(fast[0][3:4], want) <= TOL
-
-
-@pytest.mark.parametrize("kind", ["smooth", "A", "B"])
-def test_emu_shift_share_variant_is_bit_identical(kind):
-    """-DSLR_GATHER_SHIFT_SHARE=1 (prepared, compiled out of the product build until measured on a
-    B200): east slots take their data from the left lane's west slot by SHFL.UP where expand_kernel
-    found the flow locally one-to-one.  Same bits as the general path; the shuffles really happen
-    for smooth flow."""
-    H, W, C, N = 32, 96, 9, 6
-    feat, Z, motion = _scene(H, W, C, "B" if kind == "B" else "A", 13)
-    if kind == "smooth":        # a gentle shear: one-to-one everywhere, fractional landings
-        ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
-        motion = np.stack([0.37 + 0.004 * ys, -0.21 + 0.003 * xs])[None].astype(np.float32)
-    tail = np.abs(feat[:, :1]) + 0.5
-    base = emu.Scene(feat, Z, motion, tail=tail).frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
-    with emu.variant("shift", ["-DSLR_GATHER_SHIFT_SHARE=1"]):
-        before = emu.shfl_up_calls()
-        fast = emu.Scene(feat, Z, motion, tail=tail).frames(0, N - 1, 0, N, want_aux=True, want_mask=True)
-        shuffles = emu.shfl_up_calls() - before
-    for a, b in zip(base, fast):
-        assert np.array_equal(a, b)
-    if kind == "smooth":
-        assert shuffles > 0
-    want = oracle.joint_splat_baseline(feat, Z, motion, (0, 3, N - 1))
-    assert rel_err(fast[0][3:4], want) <= TOL
-
-
-def test_emu_both_prepared_variants_together():
-    H, W, C, N = 24, 96, 4, 5
-    feat, Z, _ = _scene(H, W, C, "A", 14)
-    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
-    motion = np.zeros((1, 2, H, W), dtype=np.float32)
-    motion[0, 0, :, 64:] = 0.6 + 0.01 * ys[:, 64:]         # the backward splat reaches a few pixels into columns < 64
-    base = emu.Scene(feat, Z, motion).frames(0, N - 1, 0, N)
-    with emu.variant("both", ["-DSLR_GATHER_SHIFT_SHARE=1", "-DSLR_STATIC_TILE_FASTPATH=1"]):
-        sc = emu.Scene(feat, Z, motion)
-        fast = sc.frames(0, N - 1, 0, N)
-    assert np.array_equal(base, fast) and sc.stats["static"] > 0
-
-
-def test_emu_tail_unroll_variant_is_bit_identical():
-    """-DSLR_GATHER_TAIL_UNROLL=4 (prepared, compiled out): list slots beyond the register-resident
-    16 are loaded four at a time.  Convergent flows give such tails; same bits as the default."""
-    H, W, C, N = 40, 72, 6, 3
-    feat, Z, sink, squeeze = _sink_scene(H, W, C, 9)
-    for m in (sink, squeeze):
-        sc = emu.Scene(feat, Z, m)
-        base = sc.frames(0, N - 1, 1, 2)
-        with emu.variant("tail4", ["-DSLR_GATHER_TAIL_UNROLL=4"]):
-            fast = emu.Scene(feat, Z, m).frames(0, N - 1, 1, 2)
-        assert np.array_equal(base, fast)
-    with emu.variant("all", ["-DSLR_GATHER_TAIL_UNROLL=4", "-DSLR_GATHER_SHIFT_SHARE=1", "-DSLR_STATIC_TILE_FASTPATH=1"]):
-        every = emu.Scene(feat, Z, squeeze).frames(0, N - 1, 1, 2)
-    assert np.array_equal(every, fast)
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_emu_euler_grad_motion_vs_oracle(sign):
+    H, W, T = 19, 27, 9
+    r = _rng(31)
+    motion = r.uniform(-2.0, 2.0, (1, 2, H, W)).astype(np.float32)
+    g = r.standard_normal((1, 2, H, W)).astype(np.float32)
+    got = np.full_like(motion, np.nan)
+    emu.call("slr_euler_grad_motion", emu.p(motion), sign, T, emu.p(g), emu.p(got), H, W, None)
+    want = np.float32(sign) * oracle.euler_grad_motion(np.float32(sign) * motion, T, g)
+    assert rel_err(got, want) <= 1e-6
+    emu.call("slr_euler_grad_motion", emu.p(motion), sign, 0, emu.p(g), emu.p(got), H, W, None)
+    assert not got.any()

@@ -132,3 +132,40 @@ def test_non_finite_flow_is_dropped_not_crashing():
     for (y, x) in bad:
         masked[0, :, y, x] = 0.0
     assert rel_err(out, oracle.softsplat_sum(masked, clean)) <= TOL
+
+
+def test_non_finite_motion_invalidates_the_chain_not_the_context():
+    """NaN / inf motion (a diverging motion network): the reference raises an index error at the
+    next step; ours marks every chain that meets such a value invalid (sentinel displacement, not
+    visible) and must never index the field out of range -- slr_euler and slr_clip_table alike.
+    Chains that never meet a bad pixel are bit-identical to the clean field's."""
+    H, W, T = 12, 18, 6
+    rng = np.random.default_rng(7)
+    motion = rng.uniform(-1.5, 1.5, (1, 2, H, W)).astype(np.float32)
+    bad = [(2, 3, np.nan), (5, 9, np.inf), (8, 14, -np.inf)]
+    dirty = motion.copy()
+    for (y, x, v) in bad:
+        dirty[0, 0, y, x] = v
+    dirty[0, 1, 10, 1] = np.nan
+    disp = np.empty((1, 2, H, W), dtype=np.float32)
+    vis = np.empty((1, 1, H, W), dtype=np.float32)
+    for sign in (1.0, -1.0):
+        emu.call("slr_euler", emu.p(dirty), sign, T, emu.p(disp), emu.p(vis), H, W, None)
+        assert np.isfinite(disp).all()
+        want_d, want_v = oracle.euler(np.float32(sign) * motion, T)
+        # chains that pass through a bad pixel are invalid; find them by perturbing the clean field there
+        probe = motion.copy()
+        for (y, x, _) in bad:
+            probe[0, 0, y, x] += 1000.0
+        probe[0, 1, 10, 1] += 1000.0
+        other_d, _ = oracle.euler(np.float32(sign) * probe, T)
+        untouched = np.all(other_d == want_d, axis=1, keepdims=True)
+        assert np.array_equal(disp[np.broadcast_to(untouched, disp.shape)], want_d[np.broadcast_to(untouched, disp.shape)])
+        assert np.array_equal(vis[untouched], want_v[untouched])
+        for (y, x, _) in bad:
+            assert vis[0, 0, y, x] == 0.0 and disp[0, 0, y, x] == max(H, W) + 1
+    # the clip table walks the same chains: it must survive the same field (ASan build checks the bounds)
+    feat = rng.standard_normal((1, 3, H, W)).astype(np.float32)
+    Z = rng.standard_normal((1, 1, H, W)).astype(np.float32)
+    out = emu.Scene(feat, Z, dirty).frames(0, T, 0, T + 1)
+    assert np.isfinite(out).all()

@@ -186,3 +186,30 @@ def test_euler_return_all_frames(pkg):
     for T in range(6):
         wd, wv = oracle.euler(m, T)
         assert np.array_equal(d[T:T + 1].cpu().numpy(), wd) and np.array_equal(v[T:T + 1].cpu().numpy(), wv)
+
+
+def test_euler_backward_vs_reference_autograd_golden(pkg, golden_euler_grad):
+    """The gradient the motion regressor receives with --train_motion
+    (models/animating_softmax_splating.py:514-580) equals torch autograd through the reference's
+    own eager euler_integration (tests/golden/euler_grad_ref.npz)."""
+    e = golden_euler_grad
+    keys = sorted(k[:-len("/gmotion")] for k in e.files if k.endswith("/gmotion"))
+    for key in keys:
+        field, T = key.rsplit("/T", 1)
+        m = cu(e[field + "/motion"]).requires_grad_(True)
+        d, vis = pkg.euler_integration(m, int(T))
+        assert not vis.requires_grad
+        if d.requires_grad:
+            (d * cu(e[key + "/gdisp"])).sum().backward()
+        got = np.zeros_like(e[key + "/gmotion"]) if m.grad is None else m.grad.cpu().numpy()
+        assert rel_err(got, e[key + "/gmotion"]) <= 1e-6, key
+
+
+def test_euler_module_passes_gradients_to_the_motion_producer(pkg):
+    """EulerIntegration.forward on a batch built from a differentiable producer: gradients reach it
+    (the reference's in-place displacements[b:b+1] = ... keeps the graph)."""
+    w = torch.randn(2, 2, 12, 16, device="cuda", requires_grad=True)
+    motion = 1.5 * torch.tanh(w)
+    d = pkg.EulerIntegration()(motion, torch.tensor([3, 5]))
+    d.square().sum().backward()
+    assert w.grad is not None and torch.isfinite(w.grad).all() and w.grad.abs().sum() > 0

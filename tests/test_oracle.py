@@ -213,3 +213,21 @@ def test_euler_edge_is_valid_and_invalid_is_sticky():
 def test_euler_accepts_one_element_array(golden_euler):
     d, v = oracle.euler(golden_euler["tensorT/motion"], np.array([4]))
     assert np.array_equal(d, golden_euler["tensorT/T4/disp"])
+
+
+def test_euler_grad_matches_reference_autograd(golden_euler_grad):
+    """orc_euler_grad_motion against torch autograd through the reference's own euler_integration
+    (tests/golden/make_golden.py::make_euler_grad).  Sums of few fp32 terms in a different order:
+    1e-6 relative."""
+    e = golden_euler_grad
+    keys = sorted(k[:-len("/gmotion")] for k in e.files if k.endswith("/gmotion"))
+    assert len(keys) >= 40
+    nonzero = 0
+    for key in keys:
+        field, T = key.rsplit("/T", 1)
+        got = oracle.euler_grad_motion(e[field + "/motion"], int(T), e[key + "/gdisp"])
+        want = e[key + "/gmotion"]
+        assert rel_err(got, want) <= 1e-6, key
+        assert np.array_equal(got == 0.0, want == 0.0), key
+        nonzero += int(np.any(want != 0.0))
+    assert nonzero >= 30
