@@ -31,8 +31,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--algo", default=None, choices=[None, "scatter", "gather"],
-                    help="joint-block algorithm (default: the fastest available)")
+    ap.add_argument("--algo", default=None, choices=[None, "scatter", "gather", "level0"],
+                    help="gather (default): the fused clip pipeline; scatter: algorithm A (atomic scatter + normalise); "
+                         "level0: the unedited forward_flow call pattern on the drop-in operators")
+    ap.add_argument("--check", action="store_true",
+                    help="verify every frame of every rank against a single-rank recomputation (checksums, all-gathered)")
     ap.add_argument("--height", type=int, default=768)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--channels", type=int, default=64)
@@ -214,7 +217,9 @@ def cpu_frames_per_second(args, n_frames, threads=None):
     for t in picks:
         oracle.joint_splat_baseline(feat, Z, motion, (0, t, N - 1), splat=splat)
     dt = time.perf_counter() - t0
-    info = {"kind": kind, "cores": threads,
+    info = {"kind": kind, "kind_detail": ("reference splat kernels (their text compiled for the CPU) + ported Euler (oracle C, 1 thread) "
+                                          "+ numpy glue" if use_ref else "oracle C port throughout, 1 thread"),
+            "cores": threads,
             "sample": "%d of %d frames (t=%s) of the %dx%dx%d workload; splat = %s, Euler = oracle C port (1 thread), "
                       "glue = numpy" % (n_frames, N, picks, args.height, args.width, args.channels,
                                         "reference kernel text compiled for CPU (oracle/_ref, OpenMP)" if use_ref
@@ -260,6 +265,30 @@ def reference_gpu_frames_per_second(args, scene, dev):
         return {"error": repr(exc)}
 
 
+def level0_frames_per_second(args, scene):
+    """Informational: frames/s of the UNEDITED forward_flow call pattern on the drop-in operators
+    (slr_sfs_b200.level0: two Euler integrations from zero, eager cat / exp glue, two summation
+    splats, clamp, divide) -- what a user of the reference gets with zero source changes."""
+    try:
+        import torch
+        from slr_sfs_b200 import level0
+        feat, Z, motion = scene
+        N = args.frames
+        picks = [0, N // 4, N // 2, 3 * N // 4, N - 1]
+        level0.forward_flow_block(feat, Z, motion, (0, 1, N - 1))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in picks:
+            level0.forward_flow_block(feat, Z, motion, (0, t, N - 1))
+        e1.record()
+        torch.cuda.synchronize()
+        return {"value": len(picks) / (e0.elapsed_time(e1) / 1000.0), "unit": UNIT, "sample": "frames t=%s, CUDA events" % picks,
+                "what": "install_as_reference_modules() only: slr_euler x2 + torch glue + slr_softsplat_sum_fwd x2 per frame"}
+    except Exception as exc:                                                # informational only
+        return {"error": repr(exc)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -292,7 +321,8 @@ def workload_config(args, algo):
             "height": args.height, "width": args.width, "channels": args.channels, "frames_per_clip": args.frames,
             "motion": args.motion, "algo": algo,
             "l2": "no flush: one frame's working set (features 201 MB + output 201 MB) exceeds the 126 MB L2",
-            "parallelism": "frames of every scene sharded over ranks (one scene per rank per step)"}
+            "parallelism": "one scene per rank per step; frames of every scene sharded over the ranks in contiguous blocks "
+                           "rotated by the scene index; the owner's prepared scene is broadcast (NCCL) inside the timed region"}
 
 
 # --------------------------------------------------------------------------
@@ -318,6 +348,17 @@ def emit(line):
     _JSON_OUT.flush()
 
 
+def frame_checksums(frames):
+    """Per-frame fp64 (sum, sum of |x|, position-weighted sum) of a [k,C,H,W] group: cheap, order-
+    sensitive enough to catch a wrong frame, and small enough to all-gather."""
+    import torch
+    x = frames.double()
+    k = x.shape[0]
+    flat = x.reshape(k, -1)
+    w = torch.linspace(0.5, 1.5, flat.shape[1], device=x.device, dtype=torch.float64)
+    return torch.stack([flat.sum(1), flat.abs().sum(1), (flat * w).sum(1)], 1)
+
+
 def main():
     args = parse()
     claim_stdout()
@@ -330,8 +371,9 @@ def main():
     import __graft_entry__
     __graft_entry__.build()
     import slr_sfs_b200 as pkg
-    from slr_sfs_b200 import workloads, _lib
-    from slr_sfs_b200.sharding import frame_block
+    from slr_sfs_b200 import workloads, _lib, level0
+    from slr_sfs_b200.clip import ClipRunner
+    from slr_sfs_b200.sharding import SceneExchange, all_gather_frames, frame_block
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -345,66 +387,65 @@ def main():
 
     H, W, C, N = args.height, args.width, args.channels, args.frames
     P = H * W
-    algo = args.algo or ("gather" if hasattr(pkg.JointSplat, "frame") else "scatter")
+    algo = args.algo or "gather"
+    if args.batch:
+        pkg.JointSplat.batch = args.batch
+    pkg.JointSplat.pipeline = not args.no_pipeline
+    batch = pkg.JointSplat.batch
 
-    # one scene per rank ("encoded" on that rank); every rank synthesises its frame
-    # block of every scene.  Host copies live in pinned memory for the e2e leg.
-    scenes_host = []
-    for s in range(world):
-        feat, Z, motion = workloads.scene(H, W, C, args.motion, seed=s)
-        scenes_host.append((feat, Z, motion))
-    own = tuple(t.pin_memory() for t in scenes_host[rank])
-    lo, hi = frame_block(N, rank, world)
-
-    def make_joint(feat, Z, motion, resident=False):
-        # resident inputs are complete: the library may start on them while earlier frames still run
-        js = pkg.JointSplat(feat, Z, motion, inputs_event=False if resident else None)
-        if args.batch:
-            js.batch = args.batch
-        js.pipeline = not args.no_pipeline
-        return js
-
-    n_mine = hi - lo
-    # frames requested per frames() call: several batches, so that the library can overlap the
-    # index building of one batch with the gather of the previous one
-    batch = args.batch or pkg.JointSplat.batch
-    nbuf = min(n_mine, 4 * batch)
-    # two output buffers: the consumer of one group of frames (the e2e leg's D2H copy) runs beside
-    # the synthesis of the next group
-    frame_bufs = [torch.empty(nbuf, C, H, W, dtype=torch.float32, device=dev) for _ in range(2)] if algo == "gather" else None
-    buf_free = [None, None]          # events after which a buffer may be overwritten
-
-    def synth_block(js, on_frames=None, chunk=None):
-        """Synthesise this rank's frame block of one scene in groups of `chunk` frames;
-        on_frames(tensor [k,C,H,W]) consumes each finished group (the decoder's place; the e2e leg
-        copies them out) and may return an event that says when the group's buffer is free again."""
-        if algo == "gather":
-            chunk = min(chunk or nbuf, nbuf)
-            js.prepare_clip(0, N - 1, lo, hi - lo)        # Euler chains once for this rank's frame block
-            for i, b0 in enumerate(range(lo, hi, chunk)):
-                nb = min(chunk, hi - b0)
-                slot = i & 1
-                if buf_free[slot] is not None:
-                    torch.cuda.current_stream().wait_event(buf_free[slot])
-                    buf_free[slot] = None
-                out = js.frames(0, N - 1, b0, nb, out=frame_bufs[slot][:nb])
-                if on_frames is not None:
-                    buf_free[slot] = on_frames(out)
-        else:
-            for t in range(lo, hi):
-                out = js.frame_scatter((0, t, N - 1))
-                if on_frames is not None:
-                    on_frames(out)
-        return out
-
-    # resident inputs for the `value` leg
-    resident = [tuple(t.to(dev) for t in sc) for sc in scenes_host]
+    # Scene s is "encoded" on rank s % world and its inputs live ONLY there (device-resident for the
+    # `value` leg, pinned host memory for the e2e leg); every rank synthesises its block of frames of
+    # every scene.  One step = `world` scenes (weak scaling: N frames per GPU per step).
+    own_host = workloads.scene(H, W, C, args.motion, seed=rank)
+    own_pinned = tuple(t.pin_memory() for t in own_host)
+    own_dev = tuple(t.to(dev) for t in own_host)
+    longest = max(frame_block(N, r, world)[1] - frame_block(N, r, world)[0] for r in range(world))
+    runner = ClipRunner(C, H, W, dev, group=min(longest, 4 * batch)) if algo == "gather" else None
+    exchange = None
+    if world > 1 and algo == "gather":
+        exchange = SceneExchange(C, H, W, 0, dev, pkg.JointSplat.scene_buffer_numel(C, 0, H, W))
     torch.cuda.synchronize()
 
-    def step_resident(record=None):
-        for sc in resident:
-            out = synth_block(make_joint(*sc, resident=True))
+    def synth_scene(js, s, on_frames=None, group=None):
+        lo, hi = frame_block(N, rank, world, rotate=s)
+        if algo == "gather":
+            return runner.run(js, 0, N - 1, lo, hi, on_frames, group)
+        out = None
+        for t in range(lo, hi):
+            out = js.frame_scatter((0, t, N - 1)) if algo == "scatter" else level0.forward_flow_block(*own_dev, (0, t, N - 1))
+            if on_frames is not None:
+                on_frames(out, t)
         return out
+
+    def run_scenes(n_scenes, inputs_of_owner, on_frames=None, group=None, exchange_on=True):
+        """`n_scenes` consecutive scenes (scene k is owned by rank k % world).  With more than one
+        rank the PREPARED scene of the owner is broadcast one scene ahead of the synthesis
+        (SceneExchange); `exchange_on=False` skips the broadcast (every rank then prepares its own
+        copy of its own scene: the no-communication reference point)."""
+        main = torch.cuda.current_stream()
+        if exchange is None or not exchange_on:
+            for k in range(n_scenes):
+                inputs = inputs_of_owner()
+                synth_scene(pkg.JointSplat(*inputs, inputs_event=None if inputs[0] is not own_dev[0] else False), k, on_frames, group)
+            return
+        if n_scenes <= 0:
+            return
+        ticket = exchange.post(0, inputs_of_owner if rank == 0 else None)
+        for k in range(n_scenes):
+            nxt = None
+            if k + 1 < n_scenes:
+                o = (k + 1) % world
+                nxt = exchange.post(o, inputs_of_owner if rank == o else None)
+            scene_buf, motion_buf, ready = exchange.take(ticket)
+            js = pkg.JointSplat.from_scene_buffer(scene_buf, motion_buf, C, H, W, ready_event=ready)
+            synth_scene(js, k, on_frames, group)
+            done = torch.cuda.Event()
+            done.record(main)
+            exchange.used(ticket, done)
+            ticket = nxt
+
+    def step_resident(steps=1, exchange_on=True):
+        run_scenes(steps * world, lambda: own_dev, exchange_on=exchange_on)
 
     def barrier():
         torch.cuda.synchronize()
@@ -412,152 +453,206 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def timed(fn):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b))
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(args.warmup):
-        step_resident()
+    step_resident(args.warmup)
     barrier()
     launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # live timing of the dominant kernel only (every bracket costs two event records on the stream)
-    dominant = "slr_clip_gather" if algo == "gather" else "slr_joint_scatter"
+    dominant = {"gather": "slr_clip_gather", "scatter": "slr_joint_scatter", "level0": "slr_softsplat_sum_fwd"}[algo]
     _lib.kernel_timing(True, only=[dominant])
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_begin()
     e0.record()
-    for _ in range(args.steps):
-        step_resident()
+    step_resident(args.steps)
     e1.record()
     barrier()
     sampler.mark_end()
     clocks = sampler.stop()
     ktimes = _lib.kernel_timing(False)
     launches = _lib.launch_count() - launches0
-    ms = e0.elapsed_time(e1)
-    # every entry point on ONE stream, after the timed region: kernel times without the overlap of the
-    # two-stream pipeline (what the ncu launch list shows as shares)
-    iso_steps = max(1, min(3, args.steps))
-    no_pipeline, args.no_pipeline = args.no_pipeline, True
-    step_resident()
-    _lib.kernel_timing(True)
-    for _ in range(iso_steps):
-        step_resident()
-    ktimes_iso = _lib.kernel_timing(False)
-    args.no_pipeline = no_pipeline
+    ms = max_over_ranks(e0.elapsed_time(e1))
     if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
         tl = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(tl)
         launches = int(tl.item())
     frames_total = world * N * args.steps          # world scenes x N frames per step, over all ranks
     value = frames_total / (ms / 1000.0)
 
+    # every entry point on ONE stream, after the timed region: kernel times without the overlap of the
+    # two-stream pipeline (what the ncu launch list shows as shares)
+    iso_steps = max(1, min(3, args.steps))
+    pkg.JointSplat.pipeline = False
+    step_resident(1)
+    _lib.kernel_timing(True)
+    step_resident(iso_steps)
+    ktimes_iso = _lib.kernel_timing(False)
+    pkg.JointSplat.pipeline = not args.no_pipeline
+
+    multi = None
+    if world > 1 and algo == "gather":
+        # the same steps without the broadcast (every rank prepares a private copy of its own scene):
+        # the difference is what the exchange costs beyond what the pipeline hides
+        k = max(1, min(args.steps, 5))
+        step_resident(1, exchange_on=False)
+        ms_nobc = timed(lambda: step_resident(k, exchange_on=False)) / k
+        ms_bc = timed(lambda: step_resident(k)) / k
+        multi = {"broadcast": "prepared scene buffer (%.1f MB) + motion per scene from its owner, NCCL, one scene ahead on a "
+                              "communication stream, inside the timed region" % (pkg.JointSplat.scene_buffer_numel(C, 0, H, W) * 4 / 1e6),
+                 "ms_per_step_with_broadcast": ms_bc, "ms_per_step_without_broadcast": ms_nobc,
+                 "exposed_broadcast_us_per_scene": 1000.0 * (ms_bc - ms_nobc) / world,
+                 "frames_per_rank_per_step": N,
+                 "frame_blocks": "contiguous, rotated by the scene index (every rank: %d frames per %d scenes)" % (N, world)}
+
+    # ---------------- --check: every frame of every scene against a single-rank recomputation -----------------
+    check = None
+    if args.check and algo == "gather":
+        sums = {}
+
+        def collect(k):
+            def on_frames(frames, t0):
+                sums.setdefault(k, []).append(frame_checksums(frames))
+                return None
+            return on_frames
+        main = torch.cuda.current_stream()
+        if exchange is None:
+            synth_scene(pkg.JointSplat(*own_dev, inputs_event=False), 0, collect(0))
+        else:
+            ticket = exchange.post(0, own_dev if rank == 0 else None)
+            for k in range(world):
+                nxt = exchange.post(k + 1, own_dev if rank == k + 1 else None) if k + 1 < world else None
+                scene_buf, motion_buf, ready = exchange.take(ticket)
+                synth_scene(pkg.JointSplat.from_scene_buffer(scene_buf, motion_buf, C, H, W, ready_event=ready), k, collect(k))
+                done = torch.cuda.Event()
+                done.record(main)
+                exchange.used(ticket, done)
+                ticket = nxt
+        gathered = [all_gather_frames(torch.cat(sums[k], 0), N, rotate=k) for k in range(world)]
+        if rank == 0:
+            worst = 0.0
+            for k in range(world):
+                sc = tuple(t.to(dev) for t in workloads.scene(H, W, C, args.motion, seed=k))
+                alone = []
+                js = pkg.JointSplat(*sc)
+                js.prepare_clip(0, N - 1)
+                for t0 in range(0, N, 6):            # other batch boundaries than any rank used
+                    alone.append(frame_checksums(js.frames(0, N - 1, t0, min(6, N - t0))))
+                alone = torch.cat(alone, 0)
+                dev_k = ((gathered[k] - alone).abs() / alone[:, 1:2].clamp(min=1e-30)).max()
+                worst = max(worst, float(dev_k))
+            check = {"frames_checked": world * N, "max_rel_checksum_dev": worst, "ok": worst <= 1e-5,
+                     "what": "per-frame fp64 checksums (sum, |sum|, weighted sum) of every rank's frames, all-gathered, against "
+                             "rank 0 recomputing every scene alone in batches of 6; deviation relative to the frame's sum of |x|"}
+
     # ---------------- e2e: host buffers in, host buffers out, every step -----------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and algo == "gather":
         n_slots = 3
         ring = [torch.empty(1, C, H, W, dtype=torch.float32).pin_memory() for _ in range(n_slots)]
         copy_stream = torch.cuda.Stream(device=dev)
-        in_bytes = sum(t.numel() * 4 for t in own)
-        out_bytes = (hi - lo) * world * C * P * 4
+        in_bytes = sum(t.numel() * 4 for t in own_pinned)
+        state = {"k": 0}
 
-        def step_e2e():
-            # H2D of this rank's scene, broadcast of every scene from its owner, synthesis of
-            # this rank's frame block of every scene, D2H of every synthesised frame.
-            mine = tuple(t.to(dev, non_blocking=True) for t in own)
-            state = {"k": 0}
+        def copy_out(frames, t0):
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                for i in range(frames.shape[0]):
+                    ring[state["k"] % n_slots].copy_(frames[i:i + 1], non_blocking=True)
+                    state["k"] += 1
+                copied = torch.cuda.Event()
+                copied.record()
+            return copied             # the group's buffer must not be overwritten before this
 
-            def copy_out(frames):
-                done = torch.cuda.Event()
-                done.record()
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(done)
-                    for i in range(frames.shape[0]):
-                        ring[state["k"] % n_slots].copy_(frames[i:i + 1], non_blocking=True)
-                        state["k"] += 1
-                    copied = torch.cuda.Event()
-                    copied.record()
-                return copied         # the group's buffer must not be overwritten before this
-
-            for s in range(world):
-                if world > 1:
-                    sc = mine if s == rank else tuple(torch.empty_like(t, device=dev) for t in own)
-                    for t in sc:
-                        dist.broadcast(t, src=s)
-                else:
-                    sc = mine
-                synth_block(make_joint(*sc), copy_out, chunk=batch)
+        def step_e2e(steps=1):
+            # per scene: H2D of the owner's inputs from pinned memory (on the exchange's stream when there is
+            # one), broadcast, synthesis of this rank's frame block, D2H of every synthesised frame
+            def h2d():
+                return tuple(t.to(dev, non_blocking=True) for t in own_pinned)
+            run_scenes(steps * world, h2d, on_frames=copy_out, group=batch)
             copy_stream.synchronize()
 
-        for _ in range(min(args.warmup, 1)):
-            step_e2e()
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
+        step_e2e(min(args.warmup, 1))
         steps_e2e = max(1, min(args.steps, 2))
-        t0.record()
-        for _ in range(steps_e2e):
-            step_e2e()
-        t1.record()
-        barrier()
-        ms_e = t0.elapsed_time(t1)
-        if world > 1:
-            tms = torch.tensor([ms_e], device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms_e = float(tms.item())
+        ms_e = timed(lambda: step_e2e(steps_e2e))
         e2e = {"value": world * N * steps_e2e / (ms_e / 1000.0), "unit": UNIT,
-               "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
+               "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": N * world * C * P * 4,
                "steps": steps_e2e,
-               "note": "per step: pinned-host features+Z+motion -> device (+ NCCL broadcast when N>1), every "
-                       "synthesised [C,H,W] fp32 frame -> pinned host ring (3 slots) on a copy stream, beside the synthesis "
-                       "of the next group of frames (two device buffers)"}
+               "note": "per scene: pinned-host features+Z+motion -> owner's device (+ NCCL broadcast of the prepared scene when "
+                       "N>1), every synthesised [C,H,W] fp32 frame -> pinned host ring (3 slots) on a copy stream, beside the "
+                       "synthesis of the next group of frames (two device buffers).  201 MB per frame leave the device: "
+                       "PCIe-bound (the reference's consumer, the decoder, is on the device and only RGB leaves)"}
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        # dominant kernel: the one with the largest total time in the timed region
         roof = None
         if ktimes:
-            # entry points issued on the side stream are bracketed by events that include their
-            # waits; the dominant kernel is looked for among the ones with algorithmic traffic
             cand = {k: v for k, v in ktimes.items() if _lib.algorithmic_bytes(k, C, P) > 0} or ktimes
             name, (tot_ms, calls) = max(cand.items(), key=lambda kv: kv[1][0])
-            frames_per_call = (hi - lo) * world * args.steps / calls if name.startswith("slr_clip") else 1
+            # frames this RANK put through the entry point in the timed region (rank 0: N per step)
+            frames_per_call = N * args.steps / calls if name.startswith("slr_clip") else 1
             alg_bytes = _lib.algorithmic_bytes(name, C, P) * frames_per_call
             avg_s = tot_ms / 1000.0 / calls
             achieved = alg_bytes / avg_s / 1e9
-            share = tot_ms / (ms if world == 1 else ms)
+            traffic = profiled_traffic(name, frames_per_call)
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": profiled_traffic(name, frames_per_call),
+                    "frac": achieved / peak, "traffic": traffic,
+                    "dram_gbs_actual": None if traffic is None else traffic / avg_s / 1e9,
+                    "dram_frac_actual": None if traffic is None else traffic / avg_s / 1e9 / peak,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_s * 1e6,
-                    "share_of_step": share,
+                    "share_of_step": tot_ms / ms,
                     "measured": "CUDA events around every %s call inside the timed region (two-stream pipeline on: "
                                 "the side stream's kernels share the SMs with it)" % name}
             if name in ktimes_iso:
                 iso_ms, iso_calls = ktimes_iso[name]
-                iso_fpc = (hi - lo) * world * iso_steps / iso_calls if name.startswith("slr_clip") else 1
+                iso_fpc = N * iso_steps / iso_calls if name.startswith("slr_clip") else 1
                 iso_s = iso_ms / 1000.0 / iso_calls
                 iso_ach = _lib.algorithmic_bytes(name, C, P) * iso_fpc / iso_s / 1e9
                 roof["single_stream"] = {"achieved": iso_ach, "frac": iso_ach / peak, "avg_launch_us": iso_s * 1e6,
                                          "steps": iso_steps}
-            roof["all_kernels_ms_per_frame"] = {k: v[0] / max(1, (hi - lo) * world * iso_steps)
-                                                for k, v in ktimes_iso.items()}
-            roof["all_kernels_note"] = "single stream, %d steps after the timed region" % iso_steps
+            roof["all_kernels_ms_per_frame"] = {k: v[0] / max(1, N * iso_steps) for k, v in ktimes_iso.items()}
+            roof["all_kernels_note"] = "rank 0, single stream, %d steps after the timed region" % iso_steps
+            # whole path against the byte counts of SURVEY section 8d: the one-pass floor (inputs once + outputs
+            # once, 4P(2C+3)) is the honest denominator for a design that has no accumulator round trip; the
+            # two-pass figure 4P(4C+5) counts an accumulator write + re-read this design does not perform
+            per_gpu = value / world
+            roof["whole_path"] = {"frames_per_s_per_gpu": per_gpu,
+                                  "frac_one_pass_floor": per_gpu * 4.0 * P * (2 * C + 3) / (peak * 1e9),
+                                  "frac_two_pass_261_planes": per_gpu * 4.0 * P * (4 * C + 5) / (peak * 1e9)}
         cpu = None
         ref_gpu = None
+        lvl0 = None
         if not args.no_cpu_baseline and world == 1:
             fps, info = cpu_frames_per_second(args, max(1, args.cpu_frames))
             cpu = dict(info, value=fps, unit=UNIT)
-            ref_gpu = reference_gpu_frames_per_second(args, resident[0], dev)
+            ref_gpu = reference_gpu_frames_per_second(args, own_dev, dev)
+            lvl0 = level0_frames_per_second(args, own_dev)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, algo), "clocks": clocks, "gpu_launches": launches,
-            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu,
-            "whole_path_roofline_frac": value / world / (peak * 1e9 / (4.0 * P * (4 * C + 5))),
+            "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "level0": lvl0,
+            "multi_gpu": multi, "check": check,
         }
         emit(line)
     if world > 1:

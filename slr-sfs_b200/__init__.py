@@ -7,20 +7,24 @@ Drop-in operator modules (same names and signatures as the reference's):
     slr_sfs_b200.softsplat                      <- models/softsplat.py
     slr_sfs_b200.euler_integration_manipulator  <- models/projection/euler_integration_manipulator.py
 Fused joint block / clip synthesis:
-    slr_sfs_b200.synthesis
+    slr_sfs_b200.synthesis   (JointSplat)      slr_sfs_b200.clip (ClipRunner: a rank's frame block, group by group)
+    slr_sfs_b200.level0      the unedited forward_flow call pattern on the drop-in operators
 """
 from . import _lib
 from . import softsplat
 from . import euler_integration_manipulator
 from . import synthesis
 from . import sharding
+from . import clip
+from . import level0
 from .softsplat import (FunctionSoftsplat, ModuleSoftsplat, ModuleMaximumsplat,
                         ModuleMaximumWarpNormsplat)
 from .euler_integration_manipulator import EulerIntegration, euler_integration
 from .synthesis import JointSplat
+from .clip import ClipRunner
 
 __all__ = ["FunctionSoftsplat", "ModuleSoftsplat", "ModuleMaximumsplat", "ModuleMaximumWarpNormsplat",
-           "EulerIntegration", "euler_integration", "JointSplat", "install_as_reference_modules"]
+           "EulerIntegration", "euler_integration", "JointSplat", "ClipRunner", "install_as_reference_modules"]
 
 
 def install_as_reference_modules():

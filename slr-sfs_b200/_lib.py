@@ -92,6 +92,12 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def on_device(t):
+    """True for tensors the library can work on (CUDA tensors).  The operator modules raise
+    NotImplementedError otherwise, like the reference (softsplat.py:418-419)."""
+    return bool(t.is_cuda)
+
+
 def current_stream(device):
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

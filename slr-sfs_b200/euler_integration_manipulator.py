@@ -83,7 +83,7 @@ def euler_integration(motion, destination_frame, return_all_frames=False):
     b, c, height, width = motion.shape
     assert (b == 1), 'Function only implemented for batch = 1'
     assert (c == 2), f'Input motion field should be Bx2xHxW. Given tensor is: {motion.shape}'
-    if not motion.is_cuda:
+    if not _lib.on_device(motion):
         raise NotImplementedError()    # the reference hard-codes device='cuda' (:24-35)
     T = _as_int(destination_frame)
     assert T >= 0

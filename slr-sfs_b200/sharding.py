@@ -11,13 +11,16 @@ import torch
 import torch.distributed as dist
 
 
-def frame_block(n_frames, rank, world):
+def frame_block(n_frames, rank, world, rotate=0):
     """Contiguous block [lo, hi) of `rank`; block sizes differ by at most one
-    (60 frames over 8 ranks: 8,8,8,8,7,7,7,7)."""
+    (60 frames over 8 ranks: 8,8,8,8,7,7,7,7).  ``rotate`` (e.g. the scene index) shifts which
+    ranks get the longer blocks, so that over `world` scenes every rank synthesises the same
+    number of frames (60 per 8 scenes instead of 64 on four ranks and 56 on the others)."""
     assert 0 <= rank < world and n_frames >= 0
     base, rem = divmod(n_frames, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    r = (rank + rotate) % world
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
 
 
 def broadcast_scene(tensors, src, device=None, group=None):
@@ -50,18 +53,101 @@ def synthesize_sharded(make_frames, n_frames, group=None):
     return lo, hi, (make_frames(lo, hi) if hi > lo else None)
 
 
-def all_gather_frames(local, n_frames, group=None):
+def all_gather_frames(local, n_frames, group=None, rotate=0):
     """Gather small per-frame tensors (e.g. decoded RGB or checksums) from every rank's
-    block into one [n_frames, ...] tensor, in frame order."""
+    block (``frame_block(..., rotate)``) into one [n_frames, ...] tensor, in frame order."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
-    rank = dist.get_rank(group)
-    sizes = [frame_block(n_frames, r, world) for r in range(world)]
+    sizes = [frame_block(n_frames, r, world, rotate) for r in range(world)]
     tail = local.shape[1:]
     longest = max(hi - lo for lo, hi in sizes)
     pad = torch.zeros((longest,) + tuple(tail), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
-    return torch.cat([parts[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)], 0)
+    order = sorted(range(world), key=lambda r: sizes[r][0])
+    return torch.cat([parts[r][: sizes[r][1] - sizes[r][0]] for r in order], 0)
+
+
+class SceneExchange:
+    """The per-scene broadcast of BASELINE.json configs[3], one scene ahead of the synthesis.
+
+    What travels is the PREPARED scene (synthesis.JointSplat.prepare_scene: pre-weighted,
+    channel-interleaved features and e^Z -- the same 204.5 MB as features + Z at 768x1024x64) plus
+    the motion field, so Z.max() and the scene prep run once per scene on its owner instead of
+    once per rank.  Two preallocated slots; the broadcast of scene s+1 is issued on a communication
+    stream while the frames of scene s are synthesised, and a slot is refilled only after the
+    events of its last users.  Every rank must call ``post`` for the same scenes in the same order.
+
+    ``prepare(inputs, scene_out)`` fills a slot's scene buffer on the owner (default: JointSplat);
+    ``broadcast(tensor, src)`` defaults to torch.distributed.broadcast -- both replaceable, which
+    is how the gloo test drives this class on CPU tensors."""
+
+    def __init__(self, C, H, W, n_tail, device, scene_numel, stream=None, prepare=None, broadcast=None, group=None):
+        self.C, self.H, self.W, self.n_tail, self.device = C, H, W, n_tail, torch.device(device)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.on_gpu = self.device.type == "cuda"
+        self.comm = stream if stream is not None else (torch.cuda.Stream(device=self.device) if self.on_gpu else None)
+        self.slots = [(torch.empty(scene_numel, dtype=torch.float32, device=self.device),
+                       torch.empty(1, 2, H, W, dtype=torch.float32, device=self.device)) for _ in range(2)]
+        self.users = [[], []]          # events after which a slot may be refilled
+        self.posted = 0
+        self._prepare = prepare or self._prepare_with_joint_splat
+        self._broadcast = broadcast or (lambda t, src: dist.broadcast(t, src=src, group=self.group))
+
+    def _prepare_with_joint_splat(self, inputs, scene_out):
+        from .synthesis import JointSplat
+        feat, Z, motion = inputs[:3]
+        tail = inputs[3] if len(inputs) > 3 else None
+        JointSplat(feat, Z, motion, tail=tail, inputs_event=False, scene_buffer=scene_out).prepare_scene()
+
+    def post(self, owner, inputs=None):
+        """Start the exchange of the next scene: on `owner` prepare it from ``inputs`` =
+        (features, Z, motion[, tail]) -- or a callable returning them, evaluated on the communication
+        stream -- into the slot, then broadcast slot + motion.  Returns a ticket for ``take``."""
+        slot = self.posted & 1
+        self.posted += 1
+        scene_buf, motion_buf = self.slots[slot]
+        ctx = torch.cuda.stream(self.comm) if self.on_gpu else _null()
+        with ctx:
+            if self.on_gpu:
+                for ev in self.users[slot]:
+                    self.comm.wait_event(ev)
+            self.users[slot] = []
+            if self.rank == owner:
+                assert inputs is not None, "the owner of a scene posts its inputs"
+                if callable(inputs):        # e.g. the H2D copies of the inputs: queued on the communication stream too
+                    inputs = inputs()
+                self._prepare(inputs, scene_buf)
+                motion_buf.copy_(inputs[2].reshape(1, 2, self.H, self.W))
+            if self.world > 1:
+                self._broadcast(scene_buf, owner)
+                self._broadcast(motion_buf, owner)
+            ready = None
+            if self.on_gpu:
+                ready = torch.cuda.Event()
+                ready.record(self.comm)
+        return slot, ready
+
+    def take(self, ticket):
+        """The exchanged scene as (scene_buffer, motion, ready_event).  Users of the buffers must
+        be registered with ``used`` so that the slot is not refilled under them."""
+        slot, ready = ticket
+        scene_buf, motion_buf = self.slots[slot]
+        return scene_buf, motion_buf, ready
+
+    def used(self, ticket, event):
+        """The slot's contents are needed until `event`."""
+        if event is not None:
+            self.users[ticket[0]].append(event)
+
+
+class _null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False

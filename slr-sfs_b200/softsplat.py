@@ -27,10 +27,10 @@ def _check_pair(input, flow):
     assert (input.shape[3] == flow.shape[3])
     assert (input.is_contiguous() == True)
     assert (flow.is_contiguous() == True)
-    if input.is_cuda == False:
+    if _lib.on_device(input) == False:
         raise NotImplementedError()
     assert input.dtype == torch.float32 and flow.dtype == torch.float32
-    assert flow.is_cuda and flow.device == input.device and flow.shape[0] == input.shape[0]
+    assert _lib.on_device(flow) and flow.device == input.device and flow.shape[0] == input.shape[0]
 
 
 class _FunctionSoftsplat(torch.autograd.Function):
@@ -54,7 +54,7 @@ class _FunctionSoftsplat(torch.autograd.Function):
     def backward(self, gradOutput):
         input, flow = self.saved_tensors
         assert (gradOutput.is_contiguous() == True)       # softsplat.py:438
-        if input.is_cuda == False:
+        if _lib.on_device(input) == False:
             raise NotImplementedError()
         B, C, H, W = input.shape
         gradInput = input.new_empty([B, C, H, W]) if self.needs_input_grad[0] == True else None

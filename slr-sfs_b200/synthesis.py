@@ -139,20 +139,45 @@ class JointSplat:
     # of the next scene overlaps the gather of the previous one.
     _shared = {}
 
-    def __init__(self, features, Z, motion, z_mode="max", tail=None, inputs_event=None):
+    def __init__(self, features, Z, motion, z_mode="max", tail=None, inputs_event=None, scene_buffer=None):
         """``inputs_event``: a CUDA event after which the inputs are valid.  None (default): one is
         recorded now on the current stream (whatever produced the inputs was queued there);
-        False: the inputs are already complete (lets the side stream start at once)."""
+        False: the inputs are already complete (lets the side stream start at once).
+        ``scene_buffer``: caller-owned storage (``scene_buffer_numel`` floats) for the prepared scene
+        instead of a pooled one -- e.g. a broadcast slot (sharding.SceneExchange)."""
         assert features.dim() == 4 and features.shape[0] == 1
         self.feat = _req(features.detach(), "features")
         self.C, self.H, self.W = features.shape[1:]
         self.Z = _req(Z.detach().reshape(1, 1, self.H, self.W), "Z")
-        self.motion = _req(motion.detach().reshape(1, 2, self.H, self.W), "motion")
         self.tail = None if tail is None else _req(tail.detach(), "tail")
         self.n_tail = 0 if tail is None else tail.shape[1]
         assert z_mode in ("max", "v1")
         self.z_mode = z_mode
-        self.device = features.device
+        self._init_common(motion, inputs_event, scene_buffer)
+
+    @staticmethod
+    def scene_buffer_numel(C, n_tail, H, W):
+        """fp32 elements of a prepared scene buffer (slr_scene_bytes / 4)."""
+        return (_lib.load().slr_scene_bytes(C, n_tail, H, W) + 3) // 4
+
+    @classmethod
+    def from_scene_buffer(cls, scene_buffer, motion, C, H, W, n_tail=0, ready_event=None):
+        """A synthesiser over an ALREADY PREPARED scene buffer (built by another JointSplat's
+        ``prepare_scene`` -- possibly on another rank and broadcast): no features, no Z, no scene
+        prep; only the gather path (``frames`` / ``frame``) is available.  ``ready_event``: after
+        which the buffer and ``motion`` are valid (None: recorded now on the current stream;
+        False: already complete)."""
+        self = cls.__new__(cls)
+        self.feat = self.Z = self.tail = None
+        self.C, self.H, self.W, self.n_tail = int(C), int(H), int(W), int(n_tail)
+        self.z_mode = "v1"                      # no Z.max() to compute: e^(Z - max) is inside the buffer
+        self._init_common(motion, ready_event, scene_buffer)
+        self._scene_ready = self._inputs_ready or _event_now(self.device)
+        return self
+
+    def _init_common(self, motion, inputs_event, scene_buffer):
+        self.motion = _req(motion.detach().reshape(1, 2, self.H, self.W), "motion")
+        self.device = motion.device
         if inputs_event is None:
             with torch.cuda.device(self.device):
                 inputs_event = torch.cuda.Event()
@@ -167,6 +192,22 @@ class JointSplat:
         self._scene_entry = None       # pool entries behind _scene / _table["buf"]
         self._pooled = []              # everything to give back when this object dies
         self._finalizer = None
+        if scene_buffer is not None:
+            need = self.scene_buffer_numel(self.C, self.n_tail, self.H, self.W)
+            assert scene_buffer.is_cuda and scene_buffer.dtype == torch.float32 and scene_buffer.is_contiguous() \
+                and scene_buffer.numel() >= need and scene_buffer.data_ptr() % 16 == 0
+            self._scene = scene_buffer
+            # caller-owned: same bookkeeping as a pool entry (users' events), never handed to the pool
+            self._scene_entry = {"kind": "external", "last": {}, "buf": scene_buffer}
+
+    def prepare_scene(self):
+        """Build Z.max() and the scene buffer NOW on the current stream (normally done lazily by the
+        first ``frames`` call, on the side stream) and return the buffer -- what the owner of a scene
+        broadcasts to the other ranks."""
+        with torch.cuda.device(self.device):
+            self._allocate(scene=True)
+            self._prepare()
+        return self._scene
 
     def _wait_inputs(self, stream):
         if self._inputs_ready is not None:
@@ -354,6 +395,7 @@ class JointSplat:
 
     # -- scatter variant: Euler x2 -> atomic scatter of both directions -> normalise
     def accumulate_scatter(self, index, alpha=None):
+        assert self.feat is not None, "the scatter variant needs the features (not available from_scene_buffer)"
         start, mid, end = _index_triplet(index)
         if alpha is None:
             alpha = blend_alpha(start, mid, end)

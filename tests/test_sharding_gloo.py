@@ -60,6 +60,34 @@ def _worker(rank, world, port, tmp):
         sums = sharding.all_gather_frames(mine.double().sum(dim=(1, 2, 3)).reshape(-1, 1), N)
         full = make(0, N).double().sum(dim=(1, 2, 3)).reshape(-1, 1)
         assert torch.equal(sums, full)
+        # SceneExchange: every rank owns one scene; the prepared buffer travels, two slots are reused
+        numel = 5 * H * W
+        prepared = []
+
+        def prepare(inputs, out):           # stand-in for JointSplat.prepare_scene (the GPU suite runs the real one)
+            prepared.append(1)
+            out[:4 * H * W] = (inputs[0] * inputs[1].exp()).reshape(-1)
+            out[4 * H * W:] = inputs[1].exp().reshape(-1)
+
+        ex = sharding.SceneExchange(C, H, W, 0, "cpu", numel, prepare=prepare)
+        n_scenes = 5
+        scenes = [workloads.scene(H, W, C, "A", seed=10 + s) for s in range(n_scenes)]
+        ticket = ex.post(0 % world, scenes[0] if rank == 0 % world else None)
+        for sidx in range(n_scenes):
+            nxt = None
+            if sidx + 1 < n_scenes:
+                o = (sidx + 1) % world
+                nxt = ex.post(o, scenes[sidx + 1] if rank == o else None)
+            buf, mot, ready = ex.take(ticket)
+            f, z, m = scenes[sidx]
+            assert ready is None and torch.equal(mot, m)
+            assert torch.equal(buf[:4 * H * W], (f * z.exp()).reshape(-1)) and torch.equal(buf[4 * H * W:], z.exp().reshape(-1))
+            ex.used(ticket, None)
+            ticket = nxt
+        assert len(prepared) == len([s for s in range(n_scenes) if s % world == rank])      # once per scene, on its owner only
+        # rotated frame blocks: over `world` scenes every rank gets the same number of frames
+        per_rank = sum(hi - lo for lo, hi in (sharding.frame_block(N, rank, world, rotate=s) for s in range(world)))
+        assert per_rank == N
         with open(os.path.join(tmp, "ok%d" % rank), "w") as fh:
             fh.write("ok")
     finally:
