@@ -403,7 +403,8 @@ def main():
     runner = ClipRunner(C, H, W, dev, group=min(longest, 4 * batch)) if algo == "gather" else None
     exchange = None
     if world > 1 and algo == "gather":
-        exchange = SceneExchange(C, H, W, 0, dev, pkg.JointSplat.scene_buffer_numel(C, 0, H, W))
+        exchange = SceneExchange(C, H, W, 0, dev, pkg.JointSplat.scene_buffer_numel(C, 0, H, W),
+                                 core_numel=pkg.JointSplat.scene_core_numel(C, 0, H, W))
     torch.cuda.synchronize()
 
     def synth_scene(js, s, on_frames=None, group=None):
@@ -436,8 +437,8 @@ def main():
             if k + 1 < n_scenes:
                 o = (k + 1) % world
                 nxt = exchange.post(o, inputs_of_owner if rank == o else None)
-            scene_buf, motion_buf, ready = exchange.take(ticket)
-            js = pkg.JointSplat.from_scene_buffer(scene_buf, motion_buf, C, H, W, ready_event=ready)
+            scene_buf, motion_buf, ready, core_only = exchange.take(ticket)
+            js = pkg.JointSplat.from_scene_buffer(scene_buf, motion_buf, C, H, W, ready_event=ready, core_only=core_only)
             synth_scene(js, k, on_frames, group)
             done = torch.cuda.Event()
             done.record(main)
@@ -514,8 +515,8 @@ def main():
         step_resident(1, exchange_on=False)
         ms_nobc = timed(lambda: step_resident(k, exchange_on=False)) / k
         ms_bc = timed(lambda: step_resident(k)) / k
-        multi = {"broadcast": "prepared scene buffer (%.1f MB) + motion per scene from its owner, NCCL, one scene ahead on a "
-                              "communication stream, inside the timed region" % (pkg.JointSplat.scene_buffer_numel(C, 0, H, W) * 4 / 1e6),
+        multi = {"broadcast": "core of the prepared scene (%.1f MB) + motion per scene from its owner, NCCL, one scene ahead on a "
+                              "communication stream, inside the timed region" % (pkg.JointSplat.scene_core_numel(C, 0, H, W) * 4 / 1e6),
                  "ms_per_step_with_broadcast": ms_bc, "ms_per_step_without_broadcast": ms_nobc,
                  "exposed_broadcast_us_per_scene": 1000.0 * (ms_bc - ms_nobc) / world,
                  "frames_per_rank_per_step": N,
@@ -538,8 +539,9 @@ def main():
             ticket = exchange.post(0, own_dev if rank == 0 else None)
             for k in range(world):
                 nxt = exchange.post(k + 1, own_dev if rank == k + 1 else None) if k + 1 < world else None
-                scene_buf, motion_buf, ready = exchange.take(ticket)
-                synth_scene(pkg.JointSplat.from_scene_buffer(scene_buf, motion_buf, C, H, W, ready_event=ready), k, collect(k))
+                scene_buf, motion_buf, ready, core_only = exchange.take(ticket)
+                synth_scene(pkg.JointSplat.from_scene_buffer(scene_buf, motion_buf, C, H, W, ready_event=ready,
+                                                             core_only=core_only), k, collect(k))
                 done = torch.cuda.Event()
                 done.record(main)
                 exchange.used(ticket, done)

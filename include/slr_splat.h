@@ -129,12 +129,21 @@ int slr_normalize(const float* acc, float* out, float* mask, int64_t n_out, int6
  * index = [start, t, end]; forward_flow(batch).
  * ------------------------------------------------------------------------- */
 
-/* Bytes of the per-scene buffer slr_scene_prep fills. */
+/* Bytes of the per-scene buffer slr_scene_prep fills (64-byte aligned storage). */
 size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W);
+
+/* Bytes of the leading part of that buffer from which slr_scene_quilt derives the rest: what has to
+ * travel when a prepared scene is broadcast to other GPUs (BASELINE.json configs[3]). */
+size_t slr_scene_core_bytes(int64_t C, int n_tail, int64_t H, int64_t W);
+
+/* Rebuilds the trailing (TMA-friendly, pixel-major, bank-swizzled) copy of the features inside a
+ * scene buffer from its leading part.  slr_scene_prep does this itself; a rank that received only
+ * slr_scene_core_bytes of a scene calls it once before synthesising frames. */
+int slr_scene_quilt(void* scene, int64_t C, int n_tail, int64_t H, int64_t W, slr_stream_t stream);
 
 /* Once per scene (features, Z and motion are constant over the clip): writes the
  * pre-weighted, channel-interleaved features feat[c]*e^(Z - *zsub) and the scalar
- * planes (tail..., e^(Z - *zsub)) into `scene` (16-byte aligned,
+ * planes (tail..., e^(Z - *zsub)) into `scene` (64-byte aligned,
  * slr_scene_bytes).  zsub / tail as in slr_joint_scatter; n_tail <= 2. */
 int slr_scene_prep(const float* feat, const float* z, const float* zsub,
                    const float* tail, int n_tail, void* scene,
@@ -203,9 +212,9 @@ int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, int64_t W, in
  * `stream`).  After slr_clip_expand on `workspace`: stats[0] = flagged destination tiles of the batch
  * (some lane's source list was cut at the list depth), stats[1] = of those, tiles done entirely by
  * per-pair reductions from their bins, stats[2] = (destination, source) pairs beyond the list
- * depth, stats[3] = capacity of that excess list, stats[4] = tiles served without lists (all pixels
- * static, nothing lands there; 0 unless the library was built with that fast path), stats[5] = tiles
- * x frames of the batch. */
+ * depth, stats[3] = capacity of that excess list, stats[4] (valid after slr_clip_gather) = tiles whose
+ * sources did not fit the shared-memory staging area and were gathered through L1 instead,
+ * stats[5] = tiles x frames of the batch. */
 int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,
                         uint32_t stats[6], slr_stream_t stream);
 

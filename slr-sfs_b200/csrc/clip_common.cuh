@@ -27,6 +27,36 @@ constexpr int kListDepth = SLR_LIST_DEPTH;   // slots per lane in the global lis
 
 struct FrameAlphas { float a[kMaxFrames]; };
 
+// Row-pair list entry (uint4): x = source pixel | set << kSetShift, y / z = weights for the lane's top /
+// bottom pixel, w = the source's (row << 16 | column).  The set says which staged region of the
+// destination tile the source belongs to (stagegather_kernel stages the three separately: the
+// forward and the backward sources of a tile lie a whole displacement apart):
+constexpr int kSetShift = 28;                       // H * W < 2^27: the bits above are free
+constexpr unsigned kPixelMask = (1u << kSetShift) - 1u;
+enum SourceSet { kSetForward = 0, kSetBackward = 1, kSetSelf = 2, kSets = 3 };   // self: static pixels receive themselves
+__host__ __device__ __forceinline__ unsigned pack_xy(int x, int y) { return (unsigned)y << 16 | (unsigned)x; }
+
+// Scene buffer (slr_scene_prep), three regions:
+//   G4  [groups][P + 1] float4   channel groups of 4, pre-weighted by e^(Z - zsub); pixel P is all-zero
+//   S   [n_tail + 1][P + 1] float  scalar planes (2-layer tail channels, then e^(Z - zsub))
+//   Q   [chunks][P + 1] x 64 B   the same features in chunks of 16 channels, pixel-major: the four float4
+//                                units of a pixel are stored at unit ^ quilt_swizzle(column), so that a warp
+//                                reading one unit of 8 consecutive pixels from shared memory (64-byte pitch)
+//                                hits 8 different 16-byte bank groups.  Rows of Q are what the TMA unit
+//                                copies into shared memory for stagegather_kernel.
+constexpr int kChunkChannels = 16;
+constexpr int kChunkBytes = 64;                      // per pixel and chunk
+__host__ __device__ __forceinline__ unsigned quilt_swizzle(unsigned x) { return (x >> 1) & 3u; }
+__host__ __device__ __forceinline__ int64_t scene_core_floats(int64_t C, int n_tail, int64_t P)
+{
+    return (((C + 3) / 4) * 4 + n_tail + 1) * (P + 1);
+}
+__host__ __device__ __forceinline__ int64_t scene_quilt_offset_floats(int64_t C, int n_tail, int64_t P)
+{
+    return (scene_core_floats(C, n_tail, P) + 15) / 16 * 16;          // 64-byte aligned
+}
+__host__ __device__ __forceinline__ int64_t scene_chunks(int64_t C) { return (C + kChunkChannels - 1) / kChunkChannels; }
+
 // Destination tiles touched by a footprint, in a fixed order shared by the count
 // and the fill pass.  East / south columns only count when their weight is
 // non-zero (landing exactly on a cell -- static pixels -- touches one cell).
@@ -92,6 +122,7 @@ struct Workspace {
     uint4* lists;         // [n][n_tiles * 4][kListDepth][32]  row-pair lists (source, w_top, w_bottom, -)
     unsigned* row_k;      // [n][n_tiles * 4]    slots in use per row pair
     unsigned* tile_flag;  // [n][n_tiles]        1 = heavy tile
+    unsigned* fallback;   // [n][n_tiles]        1 = stagegather_kernel left the tile to rowgather_kernel
     unsigned* flag_list;  // [n * n_tiles]       compacted heavy tiles
     unsigned* flag_count; // [1]
     uint4* excess;        // [excess_cap]        pairs beyond kListDepth (dest pixel, source, weight, frame)
@@ -144,6 +175,7 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.lists = (uint4*)(p + o);       o += align_up(sizeof(uint4) * 32 * kListDepth * (size_t)(tiles * kPairsPerTile) * n);
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * kPairsPerTile * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
+    w.fallback = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.excess_cap = (unsigned)std::min<int64_t>(2 * P * n, 1ll << 30);

@@ -25,6 +25,7 @@
 //   heavy_*_kernel    tiles with a lane deeper than the lists hold (convergence zones of the
 //                     flow): per-pair fp32 reductions at L2, cost linear in pairs.
 #include "clip_common.cuh"
+#include "tma.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -60,7 +61,7 @@ struct GatherParams {
     const unsigned* offsets;   // [frames][n_tiles + 1]
     uint4* lists;              // [frames][n_tiles * 4][kListDepth][32]
     unsigned* row_k;           // [frames][n_tiles * 4]    slots in use per row pair
-    unsigned* tile_flag;       // [frames][n_tiles]: 0 normal, 3 = static tile without lists (fast path), 1 = some lane's list was cut at kListDepth (the
+    unsigned* tile_flag;       // [frames][n_tiles]: 0 normal, 1 = some lane's list was cut at kListDepth (the
                                // rest is in `excess`), 2 = excess list full: the whole tile goes the heavy way
     unsigned* flag_list;       // [frames * n_tiles]: compacted (tile * n_frames + f) of the flagged tiles
     unsigned* flag_count;      // [1], zeroed by slr_clip_plan
@@ -68,6 +69,9 @@ struct GatherParams {
     unsigned* excess_count;    // [1], zeroed by slr_clip_plan
     unsigned excess_cap;
     float* heavy_sums;         // [frames][3][P] (tail..., norm) sums of flagged tiles
+    const char* Q;             // [chunks] planes of (P + 1) x 64 B: the staged copy of G (clip_common.cuh)
+    unsigned* fallback;        // [frames][n_tiles]: 1 = stagegather_kernel left the tile to rowgather_kernel
+    int only_fallback;         // rowgather_kernel: skip the tiles stagegather_kernel has done
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -127,10 +131,11 @@ expand_kernel(const GatherParams prm)
     __syncthreads();
 
     // a pair whose canonical slot belongs to another source: the lane's next overflow slot
-    auto spill = [&](int lx, int ly, unsigned p, float w) {
+    // `p` carries the source's set in its top bits (clip_common.cuh), `xy` its (row << 16 | column)
+    auto spill = [&](int lx, int ly, unsigned p, float w, unsigned xy) {
         const int col = (ly >> 1) * TW + lx, r = ly & 1;
         const int so = kCanon + (int)atomicAdd(&ovf[col], 1u);
-        const uint4 e = make_uint4(p, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, 0u);
+        const uint4 e = make_uint4(p, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, xy);
         if (so < kSmemSlots) {
             tab[so * kCols + col] = e;
         } else if (so < kListDepth) {     // deeper than the shared table: straight to its place in the global list
@@ -140,7 +145,7 @@ expand_kernel(const GatherParams prm)
             // reduction at L2 after the gather (heavy_excess_kernel)
             const unsigned i = atomicAdd(prm.excess_count, 1u);
             const unsigned dpix = (unsigned)((ty * TH + ly) * prm.W + tx * TW + lx);
-            if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, p, __float_as_uint(w), (unsigned)f));
+            if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, p & kPixelMask, __float_as_uint(w), (unsigned)f));
             else excess_full = 1u;
         }
     };
@@ -148,13 +153,16 @@ expand_kernel(const GatherParams prm)
         return tab + canon_slot(dir, (ly & 1) - dy, dx) * kCols + (ly >> 1) * TW + lx;
     };
     // one (destination pixel, source, weight) pair -> its lane's list
-    auto insert = [&](int lx, int ly, unsigned p, float w, unsigned dir, int dx, int dy) {
+    auto insert = [&](int lx, int ly, unsigned p, float w, unsigned dir, int dx, int dy, unsigned xy) {
         uint4* cell = cell_of(lx, ly, dir, dx, dy);
         const unsigned old = atomicCAS(&cell->x, kEmpty, p);
-        if (old == kEmpty) atomicOr(&occ[(ly >> 1) * TW + lx], 1u << canon_slot(dir, (ly & 1) - dy, dx));
+        if (old == kEmpty) {
+            atomicOr(&occ[(ly >> 1) * TW + lx], 1u << canon_slot(dir, (ly & 1) - dy, dx));
+            cell->w = xy;
+        }
         // the slot is this source's: the other row's corner of the same source shares it
         if (old == kEmpty || old == p) ((ly & 1) ? cell->z : cell->y) = __float_as_uint(w);
-        else spill(lx, ly, p, w);
+        else spill(lx, ly, p, w, xy);
     };
 
     {   // a destination pixel with exactly zero motion receives itself with weight a + (1 - a)
@@ -164,7 +172,7 @@ expand_kernel(const GatherParams prm)
         if (X < prm.W && Y < prm.H) {
             const int64_t pix = (int64_t)Y * prm.W + X;
             if (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f)
-                insert(lx, ly, (unsigned)pix, a_f + a_b, 0u, 0, 0);
+                insert(lx, ly, (unsigned)pix | (unsigned)kSetSelf << kSetShift, a_f + a_b, 0u, 0, 0, pack_xy(X, Y));
         }
     }
     for (unsigned e = beg + tid; e < end; e += TILE) {
@@ -178,7 +186,7 @@ expand_kernel(const GatherParams prm)
             const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
             const float wa = fp.w[k] * a;
             if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
-                insert(lx, ly, pd & ~kDirBit, wa, dir, k & 1, k >> 1);
+                insert(lx, ly, (pd & ~kDirBit) | dir << kSetShift, wa, dir, k & 1, k >> 1, __float_as_uint(en.w));
         }
     }
     __syncthreads();
@@ -260,7 +268,7 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
             const uint4 e = __ldcg(c.list + k * 32);
             #pragma unroll
             for (int t = 0; t <= NT; ++t) {
-                const float s = __ldg(c.S + (int64_t)t * sstride + e.x);
+                const float s = __ldg(c.S + (int64_t)t * sstride + (e.x & kPixelMask));
                 sum_t[t] = fmaf(s, __uint_as_float(e.y), sum_t[t]);
                 sum_b[t] = fmaf(s, __uint_as_float(e.z), sum_b[t]);
             }
@@ -310,7 +318,7 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
             if (K == kRegSlots) {
                 for (int k = kRegSlots; k < c.kmax; ++k) {
                     const uint4 e = __ldcg(c.list + k * 32);
-                    const float4 t = __ldg(px16(Gg + gi * gstride, e.x));
+                    const float4 t = __ldg(px16(Gg + gi * gstride, e.x & kPixelMask));
                     const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
                     at[gi].x = fmaf(t.x, w0, at[gi].x); at[gi].y = fmaf(t.y, w0, at[gi].y);
                     at[gi].z = fmaf(t.z, w0, at[gi].z); at[gi].w = fmaf(t.w, w0, at[gi].w);
@@ -361,6 +369,7 @@ rowgather_kernel(const GatherParams prm)
     if (f >= prm.n_frames) return;
     const unsigned flag = __ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile);
     if (flag == 2u) return;                                   // done entirely by the heavy kernels
+    if (prm.only_fallback && __ldcg(prm.fallback + (int64_t)f * prm.n_tiles + tile) == 0u) return;
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     const int X = tx * TW + (tid & 31), Y = ty * TH + 2 * pr;
     const int64_t P = prm.P;
@@ -383,7 +392,7 @@ rowgather_kernel(const GatherParams prm)
     for (int k = 0; k < kRegSlots; ++k) {
         uint4 e = make_uint4((unsigned)P, 0u, 0u, 0u);
         if (k < kmax) e = __ldcg(c.list + k * 32);
-        pk[k] = e.x;
+        pk[k] = e.x & kPixelMask;
         wt[k] = __uint_as_float(e.y);
         wb[k] = __uint_as_float(e.z);
     }
@@ -402,6 +411,354 @@ rowgather_kernel(const GatherParams prm)
         const float* sum = r ? sum_b : sum_t;
         const int64_t px = pix + (r ? prm.W : 0);
         if (c.raw) {        // the excess pairs are still to come: leave the sums for heavy_finish_kernel
+            float* hs = prm.heavy_sums + (int64_t)f * 3 * P + px;
+            #pragma unroll
+            for (int j = 0; j <= NT; ++j) hs[(int64_t)j * P] = sum[j];
+            continue;
+        }
+        if (prm.aux) {
+            float* a = prm.aux + (int64_t)f * (NT + 1) * P + px;
+            #pragma unroll
+            for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sum[j];
+        }
+        if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stagegather_kernel: the gather with its sources STAGED IN SHARED MEMORY BY THE TMA UNIT.
+//
+// rowgather_kernel above pulls every (slot, channel group) with an LDG.128 through L1: on B200 it is
+// bound by the L1 data pipe (73 % of peak wavefronts, 43 % of the sectors missing L1; profiles/r01),
+// not by HBM.  Here a CTA owns one destination tile in kStageFrames consecutive frames.  It
+//   1. reads its lists and works out which source pixels they name: per source set (forward / backward /
+//      static self) and source row the column range [xlo, xhi] -- the "plan", built with shared-memory
+//      min / max (one atomic per warp and slot where the flow is regular);
+//   2. for every chunk of 16 channels copies exactly those row segments (64 bytes per pixel in the Q
+//      region of the scene buffer) into shared memory with cp.async.bulk -- no registers, no L1, no
+//      LSU wavefronts; the copies of chunk q+1 fly while chunk q is being consumed;
+//   3. gathers with LDS.128 (128 B/clk/SM whatever the alignment; the units of a pixel are swizzled by
+//      its column, so 8 consecutive pixels hit 8 different bank groups), same register accumulators,
+//      same normalise-and-store epilogue as rowgather_kernel.
+// The two frames of a CTA share one staged region (their sources differ by one frame's displacement), so a
+// source pixel crosses the L2 -> SM link once per two frames.  Tiles whose sources do not fit the staging area
+// (convergence zones; incoherent flow) are flagged and left to rowgather_kernel.
+// ---------------------------------------------------------------------------
+constexpr int kStageFrames = 2;
+constexpr int kStageWarps = kStageFrames * kPairsPerTile;      // one warp per (frame, row pair)
+constexpr int kStageThreads = 32 * kStageWarps;
+constexpr int kPlanRows = 128;                                 // source rows per set (hashed by row % kPlanRows)
+#ifndef SLR_STAGE_BYTES
+#define SLR_STAGE_BYTES (104 * 1024)
+#endif
+constexpr int kStageBytes = SLR_STAGE_BYTES;                   // staging area per CTA (two CTAs of 104 KB + the plan per SM)
+constexpr int kStagePixels1 = kStageBytes / kChunkBytes - 1;           // one stage  (pixel 0 = the all-zero pixel)
+constexpr int kStagePixels2 = kStageBytes / 2 / kChunkBytes - 1;       // two stages (double buffered)
+constexpr int kMaxCopies = kSets * kPlanRows;
+constexpr int kCopyLenBits = 12;
+
+struct StagePlan {
+    int ylo[kSets], yhi[kSets];
+    int xlo[kSets][kPlanRows], xhi[kSets][kPlanRows];
+    int rowoff[kSets][kPlanRows];          // staged pixel index of a source = rowoff[set][row % kPlanRows] + column
+    unsigned copy_src[kMaxCopies];         // first source pixel of a row segment
+    unsigned copy_dst[kMaxCopies];         // staged pixel index << kCopyLenBits | pixels
+    int n_copies, stages;
+    tma::Barrier full[2];
+};
+
+struct StageCtx {
+    const char* Q;            // chunk plane 0
+    unsigned char* stage;     // staging area
+    StagePlan* plan;
+    const uint4* list;        // this lane's column of the row-pair list
+    float* out_top;
+    int64_t P;
+    int W, C, kmax, chunks, warp;
+    unsigned my_bytes;        // bytes per chunk of the copies this warp issues
+    float inv_t, inv_b;
+    bool in_top, in_bot;
+};
+
+// Issues this warp's share of the copies of chunk q into its stage and announces their bytes.
+__device__ __forceinline__ void stage_issue(const StageCtx& c, int q)
+{
+    StagePlan& plan = *c.plan;
+    const int s = plan.stages == 2 ? (q & 1) : 0;
+    unsigned char* base = c.stage + (size_t)s * (kStageBytes / 2);
+    if (tma::elect_one()) {
+        tma::arrive_expect_tx(&plan.full[s], c.my_bytes);
+        const char* src = c.Q + (size_t)q * (size_t)(c.P + 1) * kChunkBytes;
+        for (int i = c.warp; i < plan.n_copies; i += kStageWarps) {
+            const unsigned d = plan.copy_dst[i];
+            tma::load(base + (size_t)(d >> kCopyLenBits) * kChunkBytes, src + (size_t)plan.copy_src[i] * kChunkBytes,
+                      (d & ((1u << kCopyLenBits) - 1u)) * kChunkBytes, &plan.full[s]);
+        }
+    }
+    __syncwarp();
+}
+
+// The chunk loop of one warp.  K = compile-time number of register-resident slots (0: a warp without
+// work -- no frame, or a whole-tile heavy tile -- that only takes part in the copies and barriers).
+template <int NT, int K>
+__device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&pk)[kRegSlots],
+                                           const float (&wt)[kRegSlots], const float (&wb)[kRegSlots])
+{
+    StagePlan& plan = *c.plan;
+    const int n_stage = plan.stages;
+    const size_t ostride = (size_t)c.P;
+    stage_issue(c, 0);
+    for (int q = 0; q < c.chunks; ++q) {
+        if (q + 1 < c.chunks) {
+            // the stage chunk q+1 goes to was read for chunk q-1 (two stages) or q (one): every warp must be done with it
+            if (n_stage == 2) { if (q >= 1) __syncthreads(); stage_issue(c, q + 1); }
+        }
+        const int s = n_stage == 2 ? (q & 1) : 0;
+        tma::wait(&plan.full[s], (unsigned)(n_stage == 2 ? (q >> 1) : q) & 1u);
+        if (K > 0) {
+            const unsigned char* base = c.stage + (size_t)s * (kStageBytes / 2);
+            float* o = c.out_top + (size_t)q * kChunkChannels * ostride;
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {                  // the chunk's four channel groups
+                const int ch0 = q * kChunkChannels + 4 * u;
+                if (ch0 < c.C) {
+                    constexpr int B = K == 0 ? 1 : (K <= 8 ? K : K / 2);      // loads in flight (shared-memory latency is short)
+                    float4 at = make_float4(0.0f, 0.0f, 0.0f, 0.0f), ab = at;
+                    #pragma unroll
+                    for (int kb = 0; kb < K; kb += B) {
+                        float4 v[B];
+                        #pragma unroll
+                        for (int k = 0; k < B; ++k)
+                            v[k] = *reinterpret_cast<const float4*>(base + (pk[kb + k] ^ ((unsigned)u << 4)));
+                        #pragma unroll
+                        for (int k = 0; k < B; ++k) {
+                            if (slot_role(kb + k) != kBottomOnly) {
+                                at.x = fmaf(v[k].x, wt[kb + k], at.x); at.y = fmaf(v[k].y, wt[kb + k], at.y);
+                                at.z = fmaf(v[k].z, wt[kb + k], at.z); at.w = fmaf(v[k].w, wt[kb + k], at.w);
+                            }
+                            if (slot_role(kb + k) != kTopOnly) {
+                                ab.x = fmaf(v[k].x, wb[kb + k], ab.x); ab.y = fmaf(v[k].y, wb[kb + k], ab.y);
+                                ab.z = fmaf(v[k].z, wb[kb + k], ab.z); ab.w = fmaf(v[k].w, wb[kb + k], ab.w);
+                            }
+                        }
+                    }
+                    if (K == kRegSlots) {
+                        for (int k = kRegSlots; k < c.kmax; ++k) {      // slots beyond the registers: converted in place by the prologue
+                            const uint4 e = __ldcg(c.list + k * 32);
+                            const float4 t = *reinterpret_cast<const float4*>(base + (e.x ^ ((unsigned)u << 4)));
+                            const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
+                            at.x = fmaf(t.x, w0, at.x); at.y = fmaf(t.y, w0, at.y);
+                            at.z = fmaf(t.z, w0, at.z); at.w = fmaf(t.w, w0, at.w);
+                            ab.x = fmaf(t.x, w1, ab.x); ab.y = fmaf(t.y, w1, ab.y);
+                            ab.z = fmaf(t.z, w1, ab.z); ab.w = fmaf(t.w, w1, ab.w);
+                        }
+                    }
+                    float* og = o + (size_t)(4 * u) * ostride;
+                    const float rt[4] = {at.x * c.inv_t, at.y * c.inv_t, at.z * c.inv_t, at.w * c.inv_t};
+                    const float rb[4] = {ab.x * c.inv_b, ab.y * c.inv_b, ab.z * c.inv_b, ab.w * c.inv_b};
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (ch0 + j < c.C) {
+                            if (c.in_top) __stcs(og + j * ostride, rt[j]);
+                            if (c.in_bot) __stcs(og + j * ostride + c.W, rb[j]);
+                        }
+                    }
+                }
+            }
+        }
+        if (n_stage == 1 && q + 1 < c.chunks) { __syncthreads(); stage_issue(c, q + 1); }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kStageThreads, 2)
+stagegather_kernel(const GatherParams prm)
+{
+    SLR_DYNAMIC_SMEM(stage_mem);
+    __shared__ StagePlan plan;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_fg = (prm.n_frames + kStageFrames - 1) / kStageFrames;
+    const int tile = (int)(blockIdx.x / (unsigned)n_fg);
+    const int f = (int)(blockIdx.x % (unsigned)n_fg) * kStageFrames + warp / kPairsPerTile, pr = warp % kPairsPerTile;
+    const bool have_frame = f < prm.n_frames;
+    const unsigned flag = have_frame ? __ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile) : 2u;
+    const bool active = flag != 2u;                      // warp-uniform; flag 2 = done entirely by the heavy kernels
+    const int64_t P = prm.P;
+
+    for (int i = tid; i < kSets * kPlanRows; i += kStageThreads) { (&plan.xlo[0][0])[i] = 0x7fffffff; (&plan.xhi[0][0])[i] = -1; }
+    if (tid < kSets) { plan.ylo[tid] = 0x7fffffff; plan.yhi[tid] = -1; }
+    if (tid < 8)      // staged pixel 0 of either stage: the all-zero pixel unused list slots read
+        reinterpret_cast<float4*>(stage_mem + (size_t)(tid >> 2) * (kStageBytes / 2))[tid & 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (tid == 0) {
+        tma::init(&plan.full[0], kStageWarps);
+        tma::init(&plan.full[1], kStageWarps);
+        tma::fence_init();
+    }
+    __syncthreads();
+
+    const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+    const int X = tx * TW + lane, Y = ty * TH + 2 * pr;
+    const int64_t pix = (int64_t)Y * prm.W + X;
+    const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + pr;
+    const int kmax = active ? (int)__ldg(prm.row_k + pair) : 0;
+
+    StageCtx c;
+    c.Q = prm.Q; c.stage = stage_mem; c.plan = &plan; c.P = P; c.W = prm.W; c.C = prm.C; c.kmax = kmax;
+    c.chunks = (int)scene_chunks(prm.C); c.warp = warp;
+    c.list = prm.lists + pair * (kListDepth * 32) + lane;
+    c.out_top = prm.out + (int64_t)f * prm.C * P + pix;
+    c.in_top = active && X < prm.W && Y < prm.H;
+    c.in_bot = active && X < prm.W && Y + 1 < prm.H;
+
+    // ---- the lists: entries, scalar-plane sums (tail channels, then the normaliser), and their sources into the plan
+    unsigned pk[kRegSlots], sxy[kRegSlots];
+    float wt[kRegSlots], wb[kRegSlots];
+    #pragma unroll
+    for (int k = 0; k < kRegSlots; ++k) {
+        uint4 e = make_uint4((unsigned)P, 0u, 0u, 0u);
+        if (k < kmax) e = __ldcg(c.list + k * 32);
+        pk[k] = e.x; sxy[k] = e.w;
+        wt[k] = __uint_as_float(e.y);
+        wb[k] = __uint_as_float(e.z);
+    }
+    float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
+    {
+        const int64_t sstride = P + 1;
+        #pragma unroll
+        for (int k = 0; k < kRegSlots; ++k) {
+            if (k < kmax) {                              // warp-uniform
+                #pragma unroll
+                for (int t = 0; t <= NT; ++t) {
+                    const float s = __ldg(prm.S + (int64_t)t * sstride + (pk[k] & kPixelMask));
+                    if (slot_role(k) != kBottomOnly) sum_t[t] = fmaf(s, wt[k], sum_t[t]);
+                    if (slot_role(k) != kTopOnly) sum_b[t] = fmaf(s, wb[k], sum_b[t]);
+                }
+            }
+        }
+        for (int k = kRegSlots; k < kmax; ++k) {
+            const uint4 e = __ldcg(c.list + k * 32);
+            #pragma unroll
+            for (int t = 0; t <= NT; ++t) {
+                const float s = __ldg(prm.S + (int64_t)t * sstride + (e.x & kPixelMask));
+                sum_t[t] = fmaf(s, __uint_as_float(e.y), sum_t[t]);
+                sum_b[t] = fmaf(s, __uint_as_float(e.z), sum_b[t]);
+            }
+        }
+    }
+    const bool raw = flag == 1u;          // flagged tile: un-normalised sums, heavy_finish_kernel divides
+    c.inv_t = raw ? 1.0f : 1.0f / fmaxf(sum_t[NT], prm.eps);
+    c.inv_b = raw ? 1.0f : 1.0f / fmaxf(sum_b[NT], prm.eps);
+
+    // one source pixel of one lane into the plan; where the whole warp names the same (set, row) -- regular
+    // flow -- one lane does the four shared-memory atomics for all
+    auto note = [&](unsigned ex, unsigned exy) {
+        const bool used = (ex & kPixelMask) != (unsigned)P;
+        const unsigned m_used = __ballot_sync(0xffffffffu, used);
+        if (m_used == 0u) return;
+        const int set = (int)(ex >> kSetShift), x = (int)(exy & 0xffffu), y = (int)(exy >> 16);
+        const unsigned key = (unsigned)set << 16 | (unsigned)y;
+        const int leader = __ffs(m_used) - 1;
+        const unsigned key0 = __shfl_sync(0xffffffffu, key, leader);
+        if (__all_sync(0xffffffffu, !used || key == key0)) {
+            const int xmin = __reduce_min_sync(0xffffffffu, used ? x : 0x7fffffff);
+            const int xmax = __reduce_max_sync(0xffffffffu, used ? x : -1);
+            if (lane == leader) {
+                atomicMin(&plan.ylo[set], y); atomicMax(&plan.yhi[set], y);
+                atomicMin(&plan.xlo[set][y & (kPlanRows - 1)], xmin); atomicMax(&plan.xhi[set][y & (kPlanRows - 1)], xmax);
+            }
+        } else if (used) {
+            atomicMin(&plan.ylo[set], y); atomicMax(&plan.yhi[set], y);
+            atomicMin(&plan.xlo[set][y & (kPlanRows - 1)], x); atomicMax(&plan.xhi[set][y & (kPlanRows - 1)], x);
+        }
+    };
+    #pragma unroll
+    for (int k = 0; k < kRegSlots; ++k)
+        if (k < kmax) note(pk[k], sxy[k]);
+    for (int k = kRegSlots; k < kmax; ++k) {
+        const uint4 e = __ldcg(c.list + k * 32);
+        note(e.x, e.w);
+    }
+    __syncthreads();
+
+    // ---- plan -> staged offsets of the rows and the list of copies (warp 0)
+    if (warp == 0) {
+        int total = 1, n_copies = 0;          // staged pixel 0 is the zero pixel
+        bool ok = true;
+        #pragma unroll
+        for (int set = 0; set < kSets; ++set) {
+            const int ylo = plan.ylo[set], yhi = plan.yhi[set];
+            if (yhi < ylo) continue;
+            if (yhi - ylo >= kPlanRows) { ok = false; continue; }
+            for (int r0 = 0; r0 < kPlanRows; r0 += 32) {
+                const int r = r0 + lane;
+                const int lo = plan.xlo[set][r], hi = plan.xhi[set][r];
+                const int len = hi >= lo ? hi - lo + 1 : 0;
+                int incl = len;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int off = total + incl - len;
+                const unsigned m = __ballot_sync(0xffffffffu, len > 0);
+                if (len >= (1 << kCopyLenBits)) ok = false;
+                if (len > 0 && off + len <= kStagePixels1 + 1) {
+                    const int y = ylo + ((r - ylo) & (kPlanRows - 1));       // the row of [ylo, yhi] that hashes to r
+                    const int i = n_copies + __popc(m & ((1u << lane) - 1u));
+                    plan.rowoff[set][r] = off - lo;
+                    plan.copy_src[i] = (unsigned)(y * prm.W + lo);
+                    plan.copy_dst[i] = (unsigned)off << kCopyLenBits | (unsigned)len;
+                }
+                total += __shfl_sync(0xffffffffu, incl, 31);
+                n_copies += __popc(m);
+            }
+        }
+        ok = __all_sync(0xffffffffu, ok) && total <= kStagePixels1 + 1;
+        if (lane == 0) {
+            plan.n_copies = n_copies;
+            plan.stages = !ok ? 0 : (total <= kStagePixels2 + 1 ? 2 : 1);
+        }
+    }
+    __syncthreads();
+    const int n_stage = plan.stages;
+    if (have_frame && pr == 0 && lane == 0) prm.fallback[(int64_t)f * prm.n_tiles + tile] = n_stage == 0 ? 1u : 0u;
+    if (n_stage == 0) return;               // the sources do not fit: rowgather_kernel does this tile
+
+    // ---- list entries -> byte offsets into a stage (pixel index * 64 | unit swizzle of the column)
+    auto staged = [&](unsigned ex, unsigned exy) -> unsigned {
+        if ((ex & kPixelMask) == (unsigned)P) return 0u;
+        const int set = (int)(ex >> kSetShift), x = (int)(exy & 0xffffu), y = (int)(exy >> 16);
+        const int idx = plan.rowoff[set][y & (kPlanRows - 1)] + x;
+        return (unsigned)idx * kChunkBytes | quilt_swizzle((unsigned)x) << 4;
+    };
+    #pragma unroll
+    for (int k = 0; k < kRegSlots; ++k) pk[k] = staged(pk[k], sxy[k]);
+    for (int k = kRegSlots; k < kmax; ++k) {
+        uint4 e = __ldcg(c.list + k * 32);
+        e.x = staged(e.x, e.w);
+        __stcg(const_cast<uint4*>(c.list) + k * 32, e);
+    }
+    {
+        unsigned bytes = 0;
+        for (int i = warp; i < plan.n_copies; i += kStageWarps) bytes += (plan.copy_dst[i] & ((1u << kCopyLenBits) - 1u)) * kChunkBytes;
+        c.my_bytes = bytes;
+    }
+
+    // the list length is warp-uniform: pick the unroll that fits
+    if (!active) stage_rows<NT, 0>(c, pk, wt, wb);
+    else if (kmax <= 2) stage_rows<NT, 2>(c, pk, wt, wb);
+    else if (kmax <= 4) stage_rows<NT, 4>(c, pk, wt, wb);
+    else if (kmax <= 6) stage_rows<NT, 6>(c, pk, wt, wb);
+    else if (kmax <= 8) stage_rows<NT, 8>(c, pk, wt, wb);
+    else if (kmax <= 12) stage_rows<NT, 12>(c, pk, wt, wb);
+    else stage_rows<NT, 16>(c, pk, wt, wb);
+
+    #pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (!(r ? c.in_bot : c.in_top)) continue;
+        const float* sum = r ? sum_b : sum_t;
+        const int64_t px = pix + (r ? prm.W : 0);
+        if (raw) {          // the excess pairs are still to come: leave the sums for heavy_finish_kernel
             float* hs = prm.heavy_sums + (int64_t)f * 3 * P + px;
             #pragma unroll
             for (int j = 0; j <= NT; ++j) hs[(int64_t)j * P] = sum[j];
@@ -629,6 +986,9 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     const int groups = (int)((C + 3) / 4);
     prm.G = (const char*)scene;
     prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
+    prm.Q = (const char*)((const float*)scene + scene_quilt_offset_floats(C, n_tail, P));
+    prm.fallback = ws.fallback;
+    prm.only_fallback = 0;
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;
@@ -658,6 +1018,25 @@ GatherShape gather_shape()
     int f = 0, r = 0;
     if (e && sscanf(e, "%dx%d", &f, &r) == 2) { g.frames = f; g.pairs = r; }
     return g;
+}
+
+// SLR_GATHER_MODE=ldg: rowgather_kernel for every tile (the round-1 path, kept for A/B runs and as the
+// fallback of the staged path); default: stagegather_kernel first.
+bool gather_staged()
+{
+    const char* e = getenv("SLR_GATHER_MODE");
+    return !(e && strcmp(e, "ldg") == 0);
+}
+
+template <int NT>
+void launch_stagegather(const GatherParams& prm, unsigned grid, cudaStream_t s)
+{
+    static bool configured = false;      // per process and instantiation; setting it twice is harmless
+    if (!configured) {
+        cudaFuncSetAttribute((const void*)stagegather_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);
+        configured = true;
+    }
+    stagegather_kernel<NT><<<grid, kStageThreads, kStageBytes, s>>>(prm);
 }
 
 template <int F, int R>
@@ -694,9 +1073,20 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                                out, aux, mask, workspace, workspace_bytes);
     if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (gather_staged()) {
+        // sources staged in shared memory by the TMA unit; the tiles whose sources do not fit are flagged ...
+        const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + kStageFrames - 1) / kStageFrames);
+        if (n_tail == 0) launch_stagegather<0>(prm, grid, s);
+        else if (n_tail == 1) launch_stagegather<1>(prm, grid, s);
+        else launch_stagegather<2>(prm, grid, s);
+        const int rc2 = SLR_LAUNCH_STATUS();
+        if (rc2) return rc2;
+        prm.only_fallback = 1;          // ... and done by the L1 gather below
+    }
     const GatherShape shape = gather_shape();
-    if (shape.frames == 1 && shape.pairs == 4) launch_rowgather<1, 4>(prm, n_tail, (cudaStream_t)stream_);
-    else launch_rowgather<2, 2>(prm, n_tail, (cudaStream_t)stream_);
+    if (shape.frames == 1 && shape.pairs == 4) launch_rowgather<1, 4>(prm, n_tail, s);
+    else launch_rowgather<2, 2>(prm, n_tail, s);
     return SLR_LAUNCH_STATUS();
 }
 
@@ -758,14 +1148,18 @@ extern "C" int slr_clip_stats_host(const void* workspace, size_t workspace_bytes
     cudaStream_t s = (cudaStream_t)stream_;
     const int64_t tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * n_frames;
     uint32_t n_flag = 0, n_excess = 0;
-    std::vector<uint32_t> flags((size_t)tiles);
+    std::vector<uint32_t> flags((size_t)tiles), fallback((size_t)tiles);
     SLR_CUDA(cudaMemcpyAsync(&n_flag, ws.flag_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     SLR_CUDA(cudaMemcpyAsync(&n_excess, ws.excess_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     SLR_CUDA(cudaMemcpyAsync(flags.data(), ws.tile_flag, sizeof(uint32_t) * (size_t)tiles, cudaMemcpyDeviceToHost, s));
+    SLR_CUDA(cudaMemcpyAsync(fallback.data(), ws.fallback, sizeof(uint32_t) * (size_t)tiles, cudaMemcpyDeviceToHost, s));
     SLR_CUDA(cudaStreamSynchronize(s));
-    uint32_t n_full = 0, n_static = 0;
-    for (uint32_t v : flags) { n_full += v == 2u; n_static += v == 3u; }
+    uint32_t n_full = 0, n_fallback = 0;
+    for (size_t i = 0; i < (size_t)tiles; ++i) {
+        n_full += flags[i] == 2u;
+        n_fallback += gather_staged() && flags[i] != 2u && fallback[i] == 1u;
+    }
     stats[0] = n_flag; stats[1] = n_full; stats[2] = n_excess; stats[3] = ws.excess_cap;
-    stats[4] = n_static; stats[5] = (uint32_t)tiles;
+    stats[4] = n_fallback; stats[5] = (uint32_t)tiles;
     return 0;
 }

@@ -57,6 +57,30 @@ scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, c
 }
 
 // ---------------------------------------------------------------------------
+// scene_quilt: the Q region of the scene buffer from its G4 region (clip_common.cuh): chunks of 16
+// channels, 64 bytes per pixel, float4 units swizzled by the pixel's column.  Pure data movement;
+// its own kernel so that a rank that RECEIVED the G4 / S regions (sharding.SceneExchange broadcasts
+// only those) can derive Q locally.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scene_quilt_kernel(const float4* __restrict__ G4, float4* __restrict__ Q, int groups, int W, int64_t P)
+{
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p > P) return;
+    const int q = blockIdx.y;
+    const unsigned sw = p < P ? quilt_swizzle((unsigned)(p % W)) : 0u;
+    float4 u[4];
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int g = 4 * q + j;
+        u[j] = g < groups ? __ldg(G4 + (int64_t)g * (P + 1) + p) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    float4* dst = Q + ((int64_t)q * (P + 1) + p) * 4;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j ^ sw] = u[j];
+}
+
+// ---------------------------------------------------------------------------
 // euler_table: both chains for frames f = 0..n-1 of the batch.
 //   forward  steps of frame f: steps_f0 + f      (t - start)
 //   backward steps of frame f: steps_b0 - f      (end - t + 1)
@@ -187,7 +211,7 @@ bin_scan_kernel(unsigned* __restrict__ counts, unsigned* __restrict__ offsets, i
 }
 
 // ---------------------------------------------------------------------------
-// bin_fill: append (pixel | direction, landing x, landing y) to every touched tile.
+// bin_fill: append (pixel | direction, landing x, landing y, pixel's row << 16 | column) to every touched tile.
 // grid: (ceil(P/256), frames)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -203,6 +227,7 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
     const unsigned* off = offsets + (int64_t)f * (n_tiles + 1);
     unsigned* cur = cursors + (int64_t)f * n_tiles;
     float4* e = ent + (int64_t)f * cap;
+    const unsigned xy = pack_xy((int)(p % W), (int)(p / W));      // the source's own coordinates, for the staging plan
     #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
         const float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
@@ -220,7 +245,7 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
             const unsigned slot = warp_reserve(cur, tiles[k]);
             if (tiles[k] >= 0) {
                 const int64_t at = (int64_t)off[tiles[k]] + slot;
-                e[at] = make_float4(__uint_as_float((unsigned)p | (dir ? kDirBit : 0u)), ox, oy, 0.0f);
+                e[at] = make_float4(__uint_as_float((unsigned)p | (dir ? kDirBit : 0u)), ox, oy, __uint_as_float(xy));
             }
         }
     }
@@ -241,10 +266,29 @@ extern "C" size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames)
     return carve(nullptr, H, W, n_frames).bytes;
 }
 
+extern "C" size_t slr_scene_core_bytes(int64_t C, int n_tail, int64_t H, int64_t W)
+{
+    if (C <= 0 || n_tail < 0 || H <= 0 || W <= 0) return 0;
+    return sizeof(float) * (size_t)scene_core_floats(C, n_tail, H * W);
+}
+
 extern "C" size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W)
 {
     if (C <= 0 || n_tail < 0 || H <= 0 || W <= 0) return 0;
-    return sizeof(float) * (size_t)(((C + 3) / 4) * 4 + n_tail + 1) * (size_t)(H * W + 1);
+    const int64_t P = H * W;
+    return sizeof(float) * (size_t)(scene_quilt_offset_floats(C, n_tail, P) + scene_chunks(C) * (P + 1) * (kChunkBytes / 4));
+}
+
+extern "C" int slr_scene_quilt(void* scene, int64_t C, int n_tail, int64_t H, int64_t W, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) && n_tail >= 0 && n_tail <= 2 &&
+                   ((uintptr_t)scene & 63) == 0, "slr_scene_quilt: bad arguments");
+    const int64_t P = H * W;
+    const int groups = (int)((C + 3) / 4);
+    float4* Q = (float4*)((float*)scene + scene_quilt_offset_floats(C, n_tail, P));
+    dim3 grid((unsigned)((P + 1 + 255) / 256), (unsigned)scene_chunks(C), 1);
+    scene_quilt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float4*)scene, Q, groups, (int)W, P);
+    return SLR_LAUNCH_STATUS();
 }
 
 extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zsub,
@@ -252,7 +296,7 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
                               int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(feat && z && scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
-                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 15) == 0,
+                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 63) == 0,
                    "slr_scene_prep: bad arguments");
     const int64_t P = H * W;
     const int groups = (int)((C + 3) / 4);
@@ -260,7 +304,9 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
     float* S = (float*)scene + (int64_t)groups * 4 * (P + 1);
     dim3 grid((unsigned)((P + 1 + 255) / 256), (unsigned)std::min(groups, 4), 1);
     scene_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(feat, z, zsub, tail, n_tail, G4, S, (int)C, P);
-    return SLR_LAUNCH_STATUS();
+    const int rc = SLR_LAUNCH_STATUS();
+    if (rc) return rc;
+    return slr_scene_quilt(scene, C, n_tail, H, W, stream_);
 }
 
 namespace {

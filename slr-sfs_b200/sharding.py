@@ -73,9 +73,9 @@ def all_gather_frames(local, n_frames, group=None, rotate=0):
 class SceneExchange:
     """The per-scene broadcast of BASELINE.json configs[3], one scene ahead of the synthesis.
 
-    What travels is the PREPARED scene (synthesis.JointSplat.prepare_scene: pre-weighted,
-    channel-interleaved features and e^Z -- the same 204.5 MB as features + Z at 768x1024x64) plus
-    the motion field, so Z.max() and the scene prep run once per scene on its owner instead of
+    What travels is the core of the PREPARED scene (synthesis.JointSplat.prepare_scene: pre-weighted,
+    channel-interleaved features and e^Z -- the same 204.5 MB as features + Z at 768x1024x64; the
+    receivers rebuild the staged copy behind it locally) plus the motion field, so Z.max() and the scene prep run once per scene on its owner instead of
     once per rank.  Two preallocated slots; the broadcast of scene s+1 is issued on a communication
     stream while the frames of scene s are synthesised, and a slot is refilled only after the
     events of its last users.  Every rank must call ``post`` for the same scenes in the same order.
@@ -84,7 +84,8 @@ class SceneExchange:
     ``broadcast(tensor, src)`` defaults to torch.distributed.broadcast -- both replaceable, which
     is how the gloo test drives this class on CPU tensors."""
 
-    def __init__(self, C, H, W, n_tail, device, scene_numel, stream=None, prepare=None, broadcast=None, group=None):
+    def __init__(self, C, H, W, n_tail, device, scene_numel, core_numel=None, stream=None, prepare=None, broadcast=None,
+                 group=None):
         self.C, self.H, self.W, self.n_tail, self.device = C, H, W, n_tail, torch.device(device)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -93,6 +94,7 @@ class SceneExchange:
         self.comm = stream if stream is not None else (torch.cuda.Stream(device=self.device) if self.on_gpu else None)
         self.slots = [(torch.empty(scene_numel, dtype=torch.float32, device=self.device),
                        torch.empty(1, 2, H, W, dtype=torch.float32, device=self.device)) for _ in range(2)]
+        self.core_numel = scene_numel if core_numel is None else core_numel     # leading elements that travel
         self.users = [[], []]          # events after which a slot may be refilled
         self.posted = 0
         self._prepare = prepare or self._prepare_with_joint_splat
@@ -124,20 +126,22 @@ class SceneExchange:
                 self._prepare(inputs, scene_buf)
                 motion_buf.copy_(inputs[2].reshape(1, 2, self.H, self.W))
             if self.world > 1:
-                self._broadcast(scene_buf, owner)
+                self._broadcast(scene_buf[:self.core_numel], owner)
                 self._broadcast(motion_buf, owner)
             ready = None
             if self.on_gpu:
                 ready = torch.cuda.Event()
                 ready.record(self.comm)
-        return slot, ready
+        return slot, ready, owner
 
     def take(self, ticket):
-        """The exchanged scene as (scene_buffer, motion, ready_event).  Users of the buffers must
-        be registered with ``used`` so that the slot is not refilled under them."""
-        slot, ready = ticket
+        """The exchanged scene as (scene_buffer, motion, ready_event, core_only).  ``core_only``: this
+        rank received only the first ``core_numel`` elements (JointSplat.from_scene_buffer rebuilds
+        the rest).  Users of the buffers must be registered with ``used`` so that the slot is not
+        refilled under them."""
+        slot, ready, owner = ticket
         scene_buf, motion_buf = self.slots[slot]
-        return scene_buf, motion_buf, ready
+        return scene_buf, motion_buf, ready, (self.rank != owner and self.core_numel < scene_buf.numel())
 
     def used(self, ticket, event):
         """The slot's contents are needed until `event`."""

@@ -160,19 +160,28 @@ class JointSplat:
         """fp32 elements of a prepared scene buffer (slr_scene_bytes / 4)."""
         return (_lib.load().slr_scene_bytes(C, n_tail, H, W) + 3) // 4
 
+    @staticmethod
+    def scene_core_numel(C, n_tail, H, W):
+        """fp32 elements of the leading part of a scene buffer from which the rest can be rebuilt
+        (slr_scene_core_bytes / 4): what has to travel when a prepared scene is broadcast."""
+        return (_lib.load().slr_scene_core_bytes(C, n_tail, H, W) + 3) // 4
+
     @classmethod
-    def from_scene_buffer(cls, scene_buffer, motion, C, H, W, n_tail=0, ready_event=None):
+    def from_scene_buffer(cls, scene_buffer, motion, C, H, W, n_tail=0, ready_event=None, core_only=False):
         """A synthesiser over an ALREADY PREPARED scene buffer (built by another JointSplat's
         ``prepare_scene`` -- possibly on another rank and broadcast): no features, no Z, no scene
         prep; only the gather path (``frames`` / ``frame``) is available.  ``ready_event``: after
         which the buffer and ``motion`` are valid (None: recorded now on the current stream;
-        False: already complete)."""
+        False: already complete).  ``core_only``: only the first ``scene_core_numel`` elements are
+        valid (that is all a broadcast needs to carry); the staged copy behind them is rebuilt here
+        (slr_scene_quilt) before the first frame."""
         self = cls.__new__(cls)
         self.feat = self.Z = self.tail = None
         self.C, self.H, self.W, self.n_tail = int(C), int(H), int(W), int(n_tail)
         self.z_mode = "v1"                      # no Z.max() to compute: e^(Z - max) is inside the buffer
         self._init_common(motion, ready_event, scene_buffer)
-        self._scene_ready = self._inputs_ready or _event_now(self.device)
+        if not core_only:
+            self._scene_ready = self._inputs_ready or _event_now(self.device)
         return self
 
     def _init_common(self, motion, inputs_event, scene_buffer):
@@ -195,7 +204,7 @@ class JointSplat:
         if scene_buffer is not None:
             need = self.scene_buffer_numel(self.C, self.n_tail, self.H, self.W)
             assert scene_buffer.is_cuda and scene_buffer.dtype == torch.float32 and scene_buffer.is_contiguous() \
-                and scene_buffer.numel() >= need and scene_buffer.data_ptr() % 16 == 0
+                and scene_buffer.numel() >= need and scene_buffer.data_ptr() % 64 == 0
             self._scene = scene_buffer
             # caller-owned: same bookkeeping as a pool entry (users' events), never handed to the pool
             self._scene_entry = {"kind": "external", "last": {}, "buf": scene_buffer}
@@ -234,8 +243,11 @@ class JointSplat:
                 if self._scene_ready is None:
                     self._wait_inputs(cur)
                     _BufferPool.take_over(self._scene_entry, cur)
-                    _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self._zsub),
-                              _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W, s)
+                    if self.feat is None:       # a received scene core (from_scene_buffer(core_only=True))
+                        _lib.call("slr_scene_quilt", _lib.ptr(self._scene), self.C, self.n_tail, self.H, self.W, s)
+                    else:
+                        _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self._zsub),
+                                  _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W, s)
                     self._scene_ready = _event_now(self.device)
                     _BufferPool.used(self._scene_entry, cur, self._scene_ready)
                 else:

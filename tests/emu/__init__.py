@@ -125,6 +125,6 @@ class Scene:
             call("slr_clip_frames", p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)
         st = (ctypes.c_uint32 * 6)()
         call("slr_clip_stats_host", p(ws), nb, H, W, n, st, None)
-        self.stats = dict(flagged=st[0], full=st[1], excess=st[2], excess_cap=st[3], static=st[4], tiles=st[5])
+        self.stats = dict(flagged=st[0], full=st[1], excess=st[2], excess_cap=st[3], fallback=st[4], tiles=st[5])
         res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
         return res if len(res) > 1 else out

@@ -267,3 +267,109 @@ def test_emu_euler_grad_motion_vs_oracle(sign):
     assert rel_err(got, want) <= 1e-6
     emu.call("slr_euler_grad_motion", emu.p(motion), sign, 0, emu.p(g), emu.p(got), H, W, None)
     assert not got.any()
+
+
+# ---------------------------------------------------------------------------
+# stagegather_kernel (sources staged in shared memory by bulk copies) vs rowgather_kernel (through L1)
+# ---------------------------------------------------------------------------
+def _both_modes(monkeypatch, make):
+    monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+    sc = make()
+    ldg = sc.frames(0, sc.N - 1, 0, sc.N, want_aux=True, want_mask=True)
+    assert sc.stats["fallback"] == 0
+    monkeypatch.delenv("SLR_GATHER_MODE")
+    sc = make()
+    staged = sc.frames(0, sc.N - 1, 0, sc.N, want_aux=True, want_mask=True)
+    return ldg, staged, sc.stats
+
+
+@pytest.mark.parametrize("C", [3, 16, 21, 40])
+def test_emu_staged_gather_matches_l1_gather_smooth_flow(monkeypatch, C):
+    """Regular flow: every tile is staged (no fallback), and the staged gather adds the same
+    products in the same order as the L1 gather -- bit-identical outputs, for channel counts
+    that are not multiples of the 16-channel chunk too."""
+    H, W, N = 40, 100, 5
+    feat, Z, motion = _scene(H, W, C, "A", 17)
+    tail = np.abs(feat[:, :2]) + 0.5
+
+    def make():
+        sc = emu.Scene(feat, Z, motion, tail=tail)
+        sc.N = N
+        return sc
+    ldg, staged, stats = _both_modes(monkeypatch, make)
+    assert stats["fallback"] == 0
+    for a, b in zip(ldg, staged):
+        assert np.array_equal(a, b)
+    want = oracle.joint_splat_baseline(feat, Z, motion, (0, 3, N - 1))
+    assert rel_err(staged[0][3:4], want) <= TOL
+
+
+def test_emu_staged_gather_odd_frame_count_and_ragged_edges(monkeypatch):
+    H, W, C, N = 37, 67, 5, 3          # 3 frames: the second CTA of a tile has one frame only; ragged tiles
+    feat, Z, motion = _scene(H, W, C, "A", 18)
+
+    def make():
+        sc = emu.Scene(feat, Z, motion)
+        sc.N = N
+        return sc
+    ldg, staged, stats = _both_modes(monkeypatch, make)
+    for a, b in zip(ldg, staged):
+        assert np.array_equal(a, b)
+    for t in range(N):
+        assert rel_err(staged[0][t:t + 1], oracle.joint_splat_baseline(feat, Z, motion, (0, t, N - 1))) <= TOL
+
+
+def test_emu_staged_gather_incoherent_flow_falls_back(monkeypatch):
+    """i.i.d. flow of +-8 px over several steps scatters a tile's sources over more rows / pixels than
+    the staging area holds: those tiles are flagged and gathered through L1; results unchanged."""
+    H, W, C, N = 192, 96, 4, 14
+    feat, Z, motion = _scene(H, W, C, "B", 19)
+
+    def make():
+        sc = emu.Scene(feat, Z, motion)
+        sc.N = N
+        return sc
+    monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+    sc = make()
+    ldg = sc.frames(0, N - 1, 5, 4)
+    monkeypatch.delenv("SLR_GATHER_MODE")
+    sc = make()
+    staged = sc.frames(0, N - 1, 5, 4)
+    assert sc.stats["fallback"] > 0
+    assert np.array_equal(ldg, staged)
+
+
+def test_emu_staged_gather_deep_lists_and_heavy_tiles(monkeypatch):
+    """Convergent flows: list slots beyond the 16 in registers are converted in place and read per
+    channel group; flagged tiles leave raw sums to the heavy kernels -- through the staged path too."""
+    H, W, C, N = 40, 72, 6, 3
+    feat, Z, sink, squeeze = _sink_scene(H, W, C, 9)
+    for m in (sink, squeeze):
+        monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+        ldg = emu.Scene(feat, Z, m).frames(0, N - 1, 1, 2)
+        monkeypatch.delenv("SLR_GATHER_MODE")
+        sc = emu.Scene(feat, Z, m)
+        staged = sc.frames(0, N - 1, 1, 2)
+        assert sc.stats["fallback"] < sc.stats["tiles"]
+        assert rel_err(staged, ldg) <= 1e-6           # heavy tiles add their excess pairs with atomics: same on the emulator
+        for i, t in enumerate((1, 2)):
+            assert rel_err(staged[i:i + 1], oracle.joint_splat_baseline(feat, Z, m, (0, t, N - 1))) <= TOL
+
+
+def test_emu_staged_gather_single_stage_and_capacity_fallback(monkeypatch):
+    """With a small staging area (compile-time variant) the same scene exercises all three cases:
+    tiles that fit twice (double buffered), tiles that fit once (single stage: the copies of the next
+    chunk wait for the gather of the current one) and tiles that do not fit (L1 fallback)."""
+    H, W, C, N = 40, 100, 37, 6
+    feat, Z, motion = _scene(H, W, C, "A", 23)
+    monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+    ldg = emu.Scene(feat, Z, motion).frames(0, N - 1, 0, N)
+    monkeypatch.delenv("SLR_GATHER_MODE")
+    seen = []
+    for nbytes in (64 * 1024, 40 * 1024, 24 * 1024):
+        with emu.variant("stage%d" % nbytes, ["-DSLR_STAGE_BYTES=%d" % nbytes]):
+            sc = emu.Scene(feat, Z, motion)
+            got = sc.frames(0, N - 1, 0, N)
+            seen.append(sc.stats["fallback"])
+        assert np.array_equal(got, ldg), nbytes
+    assert seen[0] <= seen[1] <= seen[2] and seen[2] > 0 and seen[0] < sc.stats["tiles"]

@@ -78,7 +78,8 @@ def _worker(rank, world, port, tmp):
             if sidx + 1 < n_scenes:
                 o = (sidx + 1) % world
                 nxt = ex.post(o, scenes[sidx + 1] if rank == o else None)
-            buf, mot, ready = ex.take(ticket)
+            buf, mot, ready, core_only = ex.take(ticket)
+            assert not core_only
             f, z, m = scenes[sidx]
             assert ready is None and torch.equal(mot, m)
             assert torch.equal(buf[:4 * H * W], (f * z.exp()).reshape(-1)) and torch.equal(buf[4 * H * W:], z.exp().reshape(-1))
