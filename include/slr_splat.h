@@ -129,7 +129,7 @@ int slr_normalize(const float* acc, float* out, float* mask, int64_t n_out, int6
  * index = [start, t, end]; forward_flow(batch).
  * ------------------------------------------------------------------------- */
 
-/* Bytes of the per-scene buffer slr_scene_prep fills (64-byte aligned storage). */
+/* Bytes of the per-scene buffer slr_scene_prep fills (16-byte aligned storage). */
 size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W);
 
 /* Bytes of the leading part of that buffer from which slr_scene_quilt derives the rest: what has to
@@ -143,7 +143,7 @@ int slr_scene_quilt(void* scene, int64_t C, int n_tail, int64_t H, int64_t W, sl
 
 /* Once per scene (features, Z and motion are constant over the clip): writes the
  * pre-weighted, channel-interleaved features feat[c]*e^(Z - *zsub) and the scalar
- * planes (tail..., e^(Z - *zsub)) into `scene` (64-byte aligned,
+ * planes (tail..., e^(Z - *zsub)) into `scene` (16-byte aligned,
  * slr_scene_bytes).  zsub / tail as in slr_joint_scatter; n_tail <= 2. */
 int slr_scene_prep(const float* feat, const float* z, const float* zsub,
                    const float* tail, int n_tail, void* scene,

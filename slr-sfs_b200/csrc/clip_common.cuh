@@ -27,6 +27,20 @@ constexpr int kListDepth = SLR_LIST_DEPTH;   // slots per lane in the global lis
 
 struct FrameAlphas { float a[kMaxFrames]; };
 
+// Staging plan of one (destination tile, frame pair), written by expand_kernel and executed by
+// stagegather_kernel: which rows of blocks of the Q region to copy where in shared memory.
+constexpr int kStageFrames = 2;                      // frames that share one staged source region
+constexpr int kPlanRows = 128;                       // source rows per set a plan can describe
+constexpr int kPlanSets = 3;
+constexpr int kMaxCopies = kPlanSets * kPlanRows;
+constexpr int kCopyLenBits = 12;
+struct StageRecord {
+    unsigned n_copies;
+    unsigned stages;                                 // 0: does not fit -> rowgather_kernel; 1 / 2: single / double buffered
+    unsigned copy_src[kMaxCopies];                   // first block (within a chunk plane of Q) of a row segment
+    unsigned copy_dst[kMaxCopies];                   // staged block index << kCopyLenBits | blocks
+};
+
 // Row-pair list entry (uint4): x = source pixel | set << kSetShift, y / z = weights for the lane's top /
 // bottom pixel, w = the source's (row << 16 | column).  The set says which staged region of the
 // destination tile the source belongs to (stagegather_kernel stages the three separately: the
@@ -34,26 +48,35 @@ struct FrameAlphas { float a[kMaxFrames]; };
 constexpr int kSetShift = 28;                       // H * W < 2^27: the bits above are free
 constexpr unsigned kPixelMask = (1u << kSetShift) - 1u;
 enum SourceSet { kSetForward = 0, kSetBackward = 1, kSetSelf = 2, kSets = 3 };   // self: static pixels receive themselves
+
 __host__ __device__ __forceinline__ unsigned pack_xy(int x, int y) { return (unsigned)y << 16 | (unsigned)x; }
 
 // Scene buffer (slr_scene_prep), three regions:
 //   G4  [groups][P + 1] float4   channel groups of 4, pre-weighted by e^(Z - zsub); pixel P is all-zero
 //   S   [n_tail + 1][P + 1] float  scalar planes (2-layer tail channels, then e^(Z - zsub))
-//   Q   [chunks][P + 1] x 64 B   the same features in chunks of 16 channels, pixel-major: the four float4
-//                                units of a pixel are stored at unit ^ quilt_swizzle(column), so that a warp
-//                                reading one unit of 8 consecutive pixels from shared memory (64-byte pitch)
-//                                hits 8 different 16-byte bank groups.  Rows of Q are what the TMA unit
-//                                copies into shared memory for stagegather_kernel.
+//   Q   [chunks][H * Wb + 1] x 128 B   the same features in chunks of 16 channels, pixel-PAIR-major: a block
+//                                holds the 2 x 4 float4 units of the horizontally adjacent pixels (2b, y) and
+//                                (2b + 1, y), b < Wb = ceil(W / 2); unit u of pixel x sits in slot quilt_slot(x) ^ u.
+//                                Rows of blocks are what the TMA unit copies into shared memory for
+//                                stagegather_kernel; the slot permutation makes a warp that reads one unit of 8
+//                                pixels at column stride 1 OR 2 hit 8 different 16-byte bank groups.
 constexpr int kChunkChannels = 16;
-constexpr int kChunkBytes = 64;                      // per pixel and chunk
-__host__ __device__ __forceinline__ unsigned quilt_swizzle(unsigned x) { return (x >> 1) & 3u; }
+constexpr int kBlockBytes = 128;                     // per pixel pair and chunk
+__host__ __device__ __forceinline__ unsigned quilt_slot(unsigned x) { return ((x & 1u) << 2) ^ ((x >> 1) & 7u); }
+// byte offset of unit 0 of pixel column x inside a row of blocks that starts at block `row_block` (units u: ^ (u << 4))
+__host__ __device__ __forceinline__ unsigned quilt_offset(unsigned row_block, unsigned x)
+{
+    return (row_block + (x >> 1)) * kBlockBytes + (quilt_slot(x) << 4);
+}
+__host__ __device__ __forceinline__ int64_t quilt_row_blocks(int64_t W) { return (W + 1) / 2; }
+__host__ __device__ __forceinline__ int64_t quilt_plane_blocks(int64_t H, int64_t W) { return H * quilt_row_blocks(W) + 1; }
 __host__ __device__ __forceinline__ int64_t scene_core_floats(int64_t C, int n_tail, int64_t P)
 {
     return (((C + 3) / 4) * 4 + n_tail + 1) * (P + 1);
 }
 __host__ __device__ __forceinline__ int64_t scene_quilt_offset_floats(int64_t C, int n_tail, int64_t P)
 {
-    return (scene_core_floats(C, n_tail, P) + 15) / 16 * 16;          // 64-byte aligned
+    return (scene_core_floats(C, n_tail, P) + 31) / 32 * 32;          // 128-byte aligned
 }
 __host__ __device__ __forceinline__ int64_t scene_chunks(int64_t C) { return (C + kChunkChannels - 1) / kChunkChannels; }
 
@@ -122,7 +145,8 @@ struct Workspace {
     uint4* lists;         // [n][n_tiles * 4][kListDepth][32]  row-pair lists (source, w_top, w_bottom, -)
     unsigned* row_k;      // [n][n_tiles * 4]    slots in use per row pair
     unsigned* tile_flag;  // [n][n_tiles]        1 = heavy tile
-    unsigned* fallback;   // [n][n_tiles]        1 = stagegather_kernel left the tile to rowgather_kernel
+    unsigned* fallback;   // [n][n_tiles]        1 = the tile's sources do not fit the staging area: rowgather_kernel does it
+    slr::StageRecord* records;   // [ceil(n / 2)][n_tiles]   staging plans (expand_kernel -> stagegather_kernel)
     unsigned* flag_list;  // [n * n_tiles]       compacted heavy tiles
     unsigned* flag_count; // [1]
     uint4* excess;        // [excess_cap]        pairs beyond kListDepth (dest pixel, source, weight, frame)
@@ -176,6 +200,7 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * kPairsPerTile * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.fallback = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
+    w.records = (slr::StageRecord*)(p + o); o += align_up(sizeof(slr::StageRecord) * tiles * ((n + kStageFrames - 1) / kStageFrames));
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.excess_cap = (unsigned)std::min<int64_t>(2 * P * n, 1ll << 30);

@@ -52,6 +52,12 @@ constexpr int kCols = TW * kPairsPerTile;   // 128 lanes (columns of row pairs) 
 #endif
 constexpr int kHeavyGroups = SLR_HEAVY_GROUPS;   // channel groups per work item of heavy_scatter_kernel
 constexpr unsigned kEmpty = 0xffffffffu;
+#ifndef SLR_STAGE_BYTES
+#define SLR_STAGE_BYTES (104 * 1024)
+#endif
+constexpr int kStageBytes = SLR_STAGE_BYTES;                   // staging area per CTA of stagegather_kernel (two CTAs per SM)
+constexpr int kStageBlocks1 = kStageBytes / kBlockBytes - 1;           // one stage  (block 0 = the all-zero block)
+constexpr int kStageBlocks2 = kStageBytes / 2 / kBlockBytes - 1;       // two stages (double buffered)
 
 struct GatherParams {
     const char* G;             // [groups] planes of (P + 1) float4; pixel P of every plane is all-zero
@@ -72,6 +78,8 @@ struct GatherParams {
     const char* Q;             // [chunks] planes of (P + 1) x 64 B: the staged copy of G (clip_common.cuh)
     unsigned* fallback;        // [frames][n_tiles]: 1 = stagegather_kernel left the tile to rowgather_kernel
     int only_fallback;         // rowgather_kernel: skip the tiles stagegather_kernel has done
+    int staged;                // expand_kernel: plan the staging (stagegather_kernel follows) or not (rowgather_kernel for all)
+    StageRecord* records;      // [frame pairs][n_tiles] staging plans
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -100,120 +108,233 @@ __host__ __device__ constexpr SlotRole slot_role(int k)
 
 // ---------------------------------------------------------------------------
 // expand_kernel
-// A canonical slot of a lane is claimed (atomicCAS on its source field) by the first source that
-// asks for it; a second source with the same (direction, row offset, east/west) -- the flow
-// compresses there -- goes to the lane's overflow slots.  (A variant that claims with plain stores
-// and re-reads after a barrier, no shared-memory atomics, measured the same: the claims are not
-// what bounds this kernel, profiles/README.md.)
+// One CTA per (destination tile, pair of consecutive frames).
+//
+// Phase A/B (staged gather only): the STAGING PLAN of the tile for the frame pair.  Every bin entry of the
+// tile in either frame names a source pixel; per source set (forward / backward / static self) and source
+// row the kernel takes the column range of the sources (one pair of warp reductions per 32 consecutive
+// entries, which mostly share their row, then shared-memory min / max), lays the row segments out in the
+// staging area and writes the list of copies to the tile's StageRecord.  Both frames share the region:
+// their sources differ by one frame's displacement.  If the region does not fit, the tile's frames are
+// flagged for rowgather_kernel and keep global pixel indices in their lists.
+//
+// Phase C, per frame: bin -> per-lane (source, w_top, w_bottom) lists of the tile's 4 row pairs.  A
+// canonical slot of a lane is claimed (atomicCAS on its source field) by the first source that asks for
+// it; a second source with the same (direction, row offset, east/west) -- the flow compresses there --
+// goes to the lane's overflow slots.  For a staged tile the source field is the byte offset of the
+// source in the staging area (final: stagegather_kernel uses it as it is).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned plan_key(unsigned set, unsigned xy)      // (set, row, column), ordered like the plan's rows
+{
+    return set << 30 | (xy >> 16 & 0x3fffu) << 16 | (xy & 0xffffu);
+}
+
 __global__ void __launch_bounds__(TILE, SLR_EXPAND_MINBLOCKS)
 expand_kernel(const GatherParams prm)
 {
-    __shared__ uint4 tab[kSmemSlots * kCols];      // tab[slot * kCols + col] = (source, w_top, w_bottom, -)
+    __shared__ uint4 tab[kSmemSlots * kCols];      // tab[slot * kCols + col] = (source, w_top, w_bottom, row << 16 | column)
     __shared__ unsigned occ[kCols];                // used canonical slots (bit mask)
     __shared__ unsigned ovf[kCols];                // overflow slots in use (kCanon, kCanon + 1, ...)
     __shared__ unsigned excess_full;               // the global excess list ran out of room
+    __shared__ int row_block[kSets][kPlanRows];    // staged block of column 0 of a source row (hashed by row % kPlanRows)
+    __shared__ int ylo[kSets], yhi[kSets];
+    __shared__ unsigned stages_s;
+    static_assert(sizeof(tab) >= 2 * kSets * kPlanRows * sizeof(int), "the plan's column ranges alias the list table");
+    int* xlo = reinterpret_cast<int*>(tab);        // [kSets][kPlanRows], phases A and B only
+    int* xhi = xlo + kSets * kPlanRows;
 
-    const int tid = threadIdx.x;
-    const int f = blockIdx.x % prm.n_frames, tile = blockIdx.x / prm.n_frames;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_fg = (prm.n_frames + kStageFrames - 1) / kStageFrames;
+    const int fg = (int)(blockIdx.x % (unsigned)n_fg), tile = (int)(blockIdx.x / (unsigned)n_fg);
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     const int64_t P = prm.P;
-    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
-    const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
-    const unsigned beg = __ldg(off + tile), end = __ldg(off + tile + 1);
-    const float4* ent = prm.ent + (int64_t)f * prm.cap;
-    const int64_t pair0 = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile;
-    uint4* lists_tile = prm.lists + pair0 * (kListDepth * 32);
+    const int X = tx * TW + lane, Y = ty * TH + warp;         // this thread's destination pixel
+    const bool inside = X < prm.W && Y < prm.H;
+    const int64_t pix = inside ? (int64_t)Y * prm.W + X : 0;
+    const bool still = inside && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
 
-    for (int i = tid; i < kCanon * kCols; i += TILE) tab[i] = make_uint4(kEmpty, 0u, 0u, 0u);
-    if (tid < kCols) { occ[tid] = 0u; ovf[tid] = 0u; }
-    if (tid == 0) excess_full = 0u;
-    __syncthreads();
-
-    // a pair whose canonical slot belongs to another source: the lane's next overflow slot
-    // `p` carries the source's set in its top bits (clip_common.cuh), `xy` its (row << 16 | column)
-    auto spill = [&](int lx, int ly, unsigned p, float w, unsigned xy) {
-        const int col = (ly >> 1) * TW + lx, r = ly & 1;
-        const int so = kCanon + (int)atomicAdd(&ovf[col], 1u);
-        const uint4 e = make_uint4(p, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, xy);
-        if (so < kSmemSlots) {
-            tab[so * kCols + col] = e;
-        } else if (so < kListDepth) {     // deeper than the shared table: straight to its place in the global list
-            __stcg(lists_tile + ((int64_t)(ly >> 1) * kListDepth + so) * 32 + lx, e);
-        } else {
-            // deeper than the lists (a convergence point): this one pair is added by an fp32
-            // reduction at L2 after the gather (heavy_excess_kernel)
-            const unsigned i = atomicAdd(prm.excess_count, 1u);
-            const unsigned dpix = (unsigned)((ty * TH + ly) * prm.W + tx * TW + lx);
-            if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, p & kPixelMask, __float_as_uint(w), (unsigned)f));
-            else excess_full = 1u;
+    unsigned stages = 0u;
+    if (prm.staged) {
+        for (int i = tid; i < kSets * kPlanRows; i += TILE) { xlo[i] = 0x7fffffff; xhi[i] = -1; }
+        if (tid < kSets) { ylo[tid] = 0x7fffffff; yhi[tid] = -1; }
+        __syncthreads();
+        auto note = [&](unsigned set, int y, int x0, int x1) {
+            atomicMin(&ylo[set], y); atomicMax(&yhi[set], y);
+            atomicMin(&xlo[set * kPlanRows + (y & (kPlanRows - 1))], x0);
+            atomicMax(&xhi[set * kPlanRows + (y & (kPlanRows - 1))], x1);
+        };
+        for (int fi = 0; fi < kStageFrames; ++fi) {
+            const int f = fg * kStageFrames + fi;
+            if (f >= prm.n_frames) break;
+            const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+            const unsigned beg = __ldg(off + tile), end = __ldg(off + tile + 1);
+            const float4* ent = prm.ent + (int64_t)f * prm.cap;
+            for (unsigned e0 = beg + 32u * warp; e0 < end; e0 += TILE) {       // warp-uniform trip count
+                const unsigned e = e0 + lane;
+                const bool valid = e < end;
+                unsigned key = 0u;
+                if (valid) {
+                    const float4 en = __ldg(ent + e);
+                    key = plan_key(__float_as_uint(en.x) >> 31, __float_as_uint(en.w));
+                }
+                const unsigned k0 = __reduce_min_sync(0xffffffffu, valid ? key : 0xffffffffu);
+                const unsigned k1 = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
+                if ((k0 >> 16) == (k1 >> 16)) {          // one (set, row) for the whole warp: the usual case
+                    if (lane == 0) note(k0 >> 30, (int)(k0 >> 16 & 0x3fffu), (int)(k0 & 0xffffu), (int)(k1 & 0xffffu));
+                } else if (valid) {
+                    note(key >> 30, (int)(key >> 16 & 0x3fffu), (int)(key & 0xffffu), (int)(key & 0xffffu));
+                }
+            }
         }
-    };
-    auto cell_of = [&](int lx, int ly, unsigned dir, int dx, int dy) {
-        return tab + canon_slot(dir, (ly & 1) - dy, dx) * kCols + (ly >> 1) * TW + lx;
-    };
-    // one (destination pixel, source, weight) pair -> its lane's list
-    auto insert = [&](int lx, int ly, unsigned p, float w, unsigned dir, int dx, int dy, unsigned xy) {
-        uint4* cell = cell_of(lx, ly, dir, dx, dy);
-        const unsigned old = atomicCAS(&cell->x, kEmpty, p);
-        if (old == kEmpty) {
-            atomicOr(&occ[(ly >> 1) * TW + lx], 1u << canon_slot(dir, (ly & 1) - dy, dx));
-            cell->w = xy;
+        {   // static pixels receive themselves: the tile's own rows (a warp is one tile row)
+            const unsigned m = __ballot_sync(0xffffffffu, still);
+            if (m != 0u && lane == 0) note((unsigned)kSetSelf, Y, tx * TW + __ffs((int)m) - 1, tx * TW + 31 - __clz((int)m));
         }
-        // the slot is this source's: the other row's corner of the same source shares it
-        if (old == kEmpty || old == p) ((ly & 1) ? cell->z : cell->y) = __float_as_uint(w);
-        else spill(lx, ly, p, w, xy);
+        __syncthreads();
+        if (warp == 0) {          // lay the row segments out: whole blocks (pixel pairs), block 0 is the all-zero block
+            StageRecord* rec = prm.records + (int64_t)fg * prm.n_tiles + tile;
+            const int Wb = (int)quilt_row_blocks(prm.W);
+            int total = 1, n_copies = 0;
+            bool ok = true;
+            #pragma unroll
+            for (int set = 0; set < kSets; ++set) {
+                const int y0 = ylo[set], y1 = yhi[set];
+                if (y1 < y0) continue;
+                if (y1 - y0 >= kPlanRows) { ok = false; continue; }
+                for (int r0 = 0; r0 < kPlanRows; r0 += 32) {
+                    const int r = r0 + lane;
+                    const int lo = xlo[set * kPlanRows + r], hi = xhi[set * kPlanRows + r];
+                    const int len = hi >= lo ? (hi >> 1) - (lo >> 1) + 1 : 0;       // blocks
+                    int incl = len;
+                    #pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const int at = total + incl - len;
+                    const unsigned m = __ballot_sync(0xffffffffu, len > 0);
+                    if (len >= (1 << kCopyLenBits)) ok = false;
+                    if (len > 0 && at + len <= kStageBlocks1 + 1) {
+                        const int y = y0 + ((r - y0) & (kPlanRows - 1));       // the row of [y0, y1] that hashes to r
+                        const int i = n_copies + __popc(m & ((1u << lane) - 1u));
+                        row_block[set][r] = at - (lo >> 1);
+                        rec->copy_src[i] = (unsigned)(y * Wb + (lo >> 1));
+                        rec->copy_dst[i] = (unsigned)at << kCopyLenBits | (unsigned)len;
+                    }
+                    total += __shfl_sync(0xffffffffu, incl, 31);
+                    n_copies += __popc(m);
+                }
+            }
+            ok = __all_sync(0xffffffffu, ok) && total <= kStageBlocks1 + 1;
+            if (lane == 0) {
+                stages_s = !ok ? 0u : (total <= kStageBlocks2 + 1 ? 2u : 1u);
+                rec->n_copies = (unsigned)n_copies;
+                rec->stages = stages_s;
+            }
+        }
+        __syncthreads();
+        stages = stages_s;
+    }
+    // the source field of a list entry: staged byte offset, or global pixel | set
+    auto source_field = [&](unsigned set, unsigned p, unsigned xy) -> unsigned {
+        if (stages == 0u) return p | set << kSetShift;
+        return quilt_offset((unsigned)row_block[set][xy >> 16 & (kPlanRows - 1)], xy & 0xffffu);
     };
+    // unused slots: the all-zero pixel, weights 0 (its (row, column) = (H, 0) is pixel P of the scalar planes)
+    const uint4 none = make_uint4(stages == 0u ? (unsigned)P : 0u, 0u, 0u, pack_xy(0, prm.H));
 
-    {   // a destination pixel with exactly zero motion receives itself with weight a + (1 - a)
+    for (int fi = 0; fi < kStageFrames; ++fi) {
+        const int f = fg * kStageFrames + fi;
+        if (f >= prm.n_frames) break;
+        const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+        const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
+        const unsigned beg = __ldg(off + tile), end = __ldg(off + tile + 1);
+        const float4* ent = prm.ent + (int64_t)f * prm.cap;
+        const int64_t pair0 = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile;
+        uint4* lists_tile = prm.lists + pair0 * (kListDepth * 32);
+
+        __syncthreads();            // the table is free: phase B, or the previous frame's write-out, is over
+        for (int i = tid; i < kCanon * kCols; i += TILE) tab[i] = make_uint4(kEmpty, 0u, 0u, 0u);
+        if (tid < kCols) { occ[tid] = 0u; ovf[tid] = 0u; }
+        if (tid == 0) excess_full = 0u;
+        __syncthreads();
+
+        // a pair whose canonical slot belongs to another source: the lane's next overflow slot
+        // (`src`: source field of the entry; `p`: the source's pixel, for the excess list)
+        auto spill = [&](int lx, int ly, unsigned src, unsigned p, float w, unsigned xy) {
+            const int col = (ly >> 1) * TW + lx, r = ly & 1;
+            const int so = kCanon + (int)atomicAdd(&ovf[col], 1u);
+            const uint4 e = make_uint4(src, r ? 0u : __float_as_uint(w), r ? __float_as_uint(w) : 0u, xy);
+            if (so < kSmemSlots) {
+                tab[so * kCols + col] = e;
+            } else if (so < kListDepth) {     // deeper than the shared table: straight to its place in the global list
+                __stcg(lists_tile + ((int64_t)(ly >> 1) * kListDepth + so) * 32 + lx, e);
+            } else {
+                // deeper than the lists (a convergence point): this one pair is added by an fp32
+                // reduction at L2 after the gather (heavy_excess_kernel)
+                const unsigned i = atomicAdd(prm.excess_count, 1u);
+                const unsigned dpix = (unsigned)((ty * TH + ly) * prm.W + tx * TW + lx);
+                if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, p, __float_as_uint(w), (unsigned)f));
+                else excess_full = 1u;
+            }
+        };
+        // one (destination pixel, source, weight) pair -> its lane's list
+        auto insert = [&](int lx, int ly, unsigned src, unsigned p, float w, unsigned dir, int dx, int dy, unsigned xy) {
+            uint4* cell = tab + canon_slot(dir, (ly & 1) - dy, dx) * kCols + (ly >> 1) * TW + lx;
+            const unsigned old = atomicCAS(&cell->x, kEmpty, src);
+            if (old == kEmpty) {
+                atomicOr(&occ[(ly >> 1) * TW + lx], 1u << canon_slot(dir, (ly & 1) - dy, dx));
+                cell->w = xy;
+            }
+            // the slot is this source's: the other row's corner of the same source shares it
+            if (old == kEmpty || old == src) ((ly & 1) ? cell->z : cell->y) = __float_as_uint(w);
+            else spill(lx, ly, src, p, w, xy);
+        };
+
+        // a destination pixel with exactly zero motion receives itself with weight a + (1 - a)
         // (its forward and backward splat both land exactly on it); it was not binned
-        const int lx = tid & 31, ly = tid >> 5;
-        const int X = tx * TW + lx, Y = ty * TH + ly;
-        if (X < prm.W && Y < prm.H) {
-            const int64_t pix = (int64_t)Y * prm.W + X;
-            if (__ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f)
-                insert(lx, ly, (unsigned)pix | (unsigned)kSetSelf << kSetShift, a_f + a_b, 0u, 0, 0, pack_xy(X, Y));
+        if (still) insert(lane, warp, source_field((unsigned)kSetSelf, (unsigned)pix, pack_xy(X, Y)), (unsigned)pix, a_f + a_b, 0u, 0, 0, pack_xy(X, Y));
+        for (unsigned e = beg + tid; e < end; e += TILE) {
+            const float4 en = __ldcs(ent + e);
+            const unsigned pd = __float_as_uint(en.x), xy = __float_as_uint(en.w);
+            const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
+            const unsigned dir = pd >> 31;
+            const float a = dir ? a_b : a_f;
+            const unsigned src = source_field(dir, pd & ~kDirBit, xy);
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
+                const float wa = fp.w[k] * a;
+                if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
+                    insert(lx, ly, src, pd & ~kDirBit, wa, dir, k & 1, k >> 1, xy);
+            }
+        }
+        __syncthreads();
+        const bool deep = tid < kCols && kCanon + (int)ovf[tid] > kListDepth;
+        const int any_deep = __syncthreads_or(deep);
+        const unsigned flag = excess_full ? 2u : (any_deep ? 1u : 0u);
+        if (tid == 0) {
+            prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = flag;
+            prm.fallback[(int64_t)f * prm.n_tiles + tile] = prm.staged && stages == 0u ? 1u : 0u;
+            if (flag) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = (unsigned)(tile * prm.n_frames + f);
+        }
+        if (flag != 2u && tid < kCols) {
+            // write the lists out, slot-major per row pair
+            const unsigned my_occ = occ[tid];
+            const int n_ovf = min((int)ovf[tid], kListDepth - kCanon);     // the rest is in the excess list
+            const int my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz(my_occ);    // slots [0, my_hi) may be used
+            const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
+            const int64_t pair = pair0 + (tid >> 5);
+            if ((tid & 31) == 0) prm.row_k[pair] = (unsigned)kmax;
+            uint4* dst = prm.lists + pair * (kListDepth * 32) + (tid & 31);
+            for (int k = 0; k < min(kmax, kSmemSlots); ++k) {
+                const bool used = k < kCanon ? (my_occ >> k & 1u) : (k - kCanon < n_ovf);
+                __stcg(dst + k * 32, used ? tab[k * kCols + tid] : none);
+            }
+            // slots past the shared table were written in place; pad this lane's unused ones
+            for (int k = max(my_hi, kSmemSlots); k < kmax; ++k) __stcg(dst + k * 32, none);
         }
     }
-    for (unsigned e = beg + tid; e < end; e += TILE) {
-        const float4 en = __ldcs(ent + e);
-        const unsigned pd = __float_as_uint(en.x);
-        const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
-        const unsigned dir = pd >> 31;
-        const float a = dir ? a_b : a_f;
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int lx = fp.x0 + (k & 1) - tx * TW, ly = fp.y0 + (k >> 1) - ty * TH;
-            const float wa = fp.w[k] * a;
-            if ((fp.ok >> k & 1u) && lx >= 0 && lx < TW && ly >= 0 && ly < TH && wa != 0.0f)
-                insert(lx, ly, (pd & ~kDirBit) | dir << kSetShift, wa, dir, k & 1, k >> 1, __float_as_uint(en.w));
-        }
-    }
-    __syncthreads();
-    const bool deep = tid < kCols && kCanon + (int)ovf[tid] > kListDepth;
-    const int any_deep = __syncthreads_or(deep);
-    const unsigned flag = excess_full ? 2u : (any_deep ? 1u : 0u);
-    if (tid == 0) {
-        prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = flag;
-        if (flag) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = blockIdx.x;
-    }
-    if (flag == 2u || tid >= kCols) return;
-
-    // write the lists out, slot-major per row pair
-    const unsigned my_occ = occ[tid];
-    const int n_ovf = min((int)ovf[tid], kListDepth - kCanon);     // the rest is in the excess list
-    const int my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz(my_occ);    // slots [0, my_hi) may be used
-    const int kmax = __reduce_max_sync(0xffffffffu, my_hi);
-    const int64_t pair = pair0 + (tid >> 5);
-    if ((tid & 31) == 0) prm.row_k[pair] = (unsigned)kmax;
-    uint4* dst = prm.lists + pair * (kListDepth * 32) + (tid & 31);
-    const uint4 none = make_uint4((unsigned)P, 0u, 0u, 0u);     // the zero pixel, weights 0
-    for (int k = 0; k < min(kmax, kSmemSlots); ++k) {
-        const bool used = k < kCanon ? (my_occ >> k & 1u) : (k - kCanon < n_ovf);
-        __stcg(dst + k * 32, used ? tab[k * kCols + tid] : none);
-    }
-    // slots past the shared table were written in place; pad this lane's unused ones
-    for (int k = max(my_hi, kSmemSlots); k < kmax; ++k) __stcg(dst + k * 32, none);
 }
 
 // ---------------------------------------------------------------------------
@@ -430,51 +551,40 @@ rowgather_kernel(const GatherParams prm)
 //
 // rowgather_kernel above pulls every (slot, channel group) with an LDG.128 through L1: on B200 it is
 // bound by the L1 data pipe (73 % of peak wavefronts, 43 % of the sectors missing L1; profiles/r01),
-// not by HBM.  Here a CTA owns one destination tile in kStageFrames consecutive frames.  It
-//   1. reads its lists and works out which source pixels they name: per source set (forward / backward /
-//      static self) and source row the column range [xlo, xhi] -- the "plan", built with shared-memory
-//      min / max (one atomic per warp and slot where the flow is regular);
-//   2. for every chunk of 16 channels copies exactly those row segments (64 bytes per pixel in the Q
-//      region of the scene buffer) into shared memory with cp.async.bulk -- no registers, no L1, no
-//      LSU wavefronts; the copies of chunk q+1 fly while chunk q is being consumed;
-//   3. gathers with LDS.128 (128 B/clk/SM whatever the alignment; the units of a pixel are swizzled by
-//      its column, so 8 consecutive pixels hit 8 different bank groups), same register accumulators,
-//      same normalise-and-store epilogue as rowgather_kernel.
+// not by HBM.  Here a CTA owns one destination tile in kStageFrames consecutive frames and executes
+// the staging plan expand_kernel made for it (StageRecord):
+//   * for every chunk of 16 channels the row segments the tile's sources lie in are copied from the Q
+//     region of the scene buffer (128-byte blocks of two pixels) into shared memory with cp.async.bulk
+//     -- no registers, no L1, no LSU wavefronts; each warp issues a share of the copies (one elected
+//     lane), all of them complete on one transaction barrier per stage, and the copies of chunk q+1
+//     fly while chunk q is being consumed (two stages; one when the region is large);
+//   * the lanes gather with LDS.128 from the offsets their list entries already hold (128 B/clk/SM
+//     whatever the alignment; the slot permutation of the blocks keeps 8 neighbouring pixels on 8
+//     different bank groups), same register accumulators and normalise-and-store epilogue as
+//     rowgather_kernel.
 // The two frames of a CTA share one staged region (their sources differ by one frame's displacement), so a
 // source pixel crosses the L2 -> SM link once per two frames.  Tiles whose sources do not fit the staging area
-// (convergence zones; incoherent flow) are flagged and left to rowgather_kernel.
+// (convergence zones; incoherent flow) were flagged by expand_kernel and are left to rowgather_kernel.
 // ---------------------------------------------------------------------------
-constexpr int kStageFrames = 2;
 constexpr int kStageWarps = kStageFrames * kPairsPerTile;      // one warp per (frame, row pair)
 constexpr int kStageThreads = 32 * kStageWarps;
-constexpr int kPlanRows = 128;                                 // source rows per set (hashed by row % kPlanRows)
-#ifndef SLR_STAGE_BYTES
-#define SLR_STAGE_BYTES (104 * 1024)
-#endif
-constexpr int kStageBytes = SLR_STAGE_BYTES;                   // staging area per CTA (two CTAs of 104 KB + the plan per SM)
-constexpr int kStagePixels1 = kStageBytes / kChunkBytes - 1;           // one stage  (pixel 0 = the all-zero pixel)
-constexpr int kStagePixels2 = kStageBytes / 2 / kChunkBytes - 1;       // two stages (double buffered)
-constexpr int kMaxCopies = kSets * kPlanRows;
-constexpr int kCopyLenBits = 12;
+constexpr int kTailBatch = 4;                                  // list slots beyond the registers are read this many at a time
 
-struct StagePlan {
-    int ylo[kSets], yhi[kSets];
-    int xlo[kSets][kPlanRows], xhi[kSets][kPlanRows];
-    int rowoff[kSets][kPlanRows];          // staged pixel index of a source = rowoff[set][row % kPlanRows] + column
-    unsigned copy_src[kMaxCopies];         // first source pixel of a row segment
-    unsigned copy_dst[kMaxCopies];         // staged pixel index << kCopyLenBits | pixels
-    int n_copies, stages;
+struct StageShared {
+    unsigned copy_src[kMaxCopies];
+    unsigned copy_dst[kMaxCopies];
     tma::Barrier full[2];
 };
 
 struct StageCtx {
     const char* Q;            // chunk plane 0
+    size_t plane_bytes;       // bytes of a chunk plane
     unsigned char* stage;     // staging area
-    StagePlan* plan;
+    StageShared* sh;
     const uint4* list;        // this lane's column of the row-pair list
     float* out_top;
     int64_t P;
-    int W, C, kmax, chunks, warp;
+    int W, C, kmax, chunks, warp, n_copies, n_stage;
     unsigned my_bytes;        // bytes per chunk of the copies this warp issues
     float inv_t, inv_b;
     bool in_top, in_bot;
@@ -483,16 +593,15 @@ struct StageCtx {
 // Issues this warp's share of the copies of chunk q into its stage and announces their bytes.
 __device__ __forceinline__ void stage_issue(const StageCtx& c, int q)
 {
-    StagePlan& plan = *c.plan;
-    const int s = plan.stages == 2 ? (q & 1) : 0;
+    const int s = c.n_stage == 2 ? (q & 1) : 0;
     unsigned char* base = c.stage + (size_t)s * (kStageBytes / 2);
     if (tma::elect_one()) {
-        tma::arrive_expect_tx(&plan.full[s], c.my_bytes);
-        const char* src = c.Q + (size_t)q * (size_t)(c.P + 1) * kChunkBytes;
-        for (int i = c.warp; i < plan.n_copies; i += kStageWarps) {
-            const unsigned d = plan.copy_dst[i];
-            tma::load(base + (size_t)(d >> kCopyLenBits) * kChunkBytes, src + (size_t)plan.copy_src[i] * kChunkBytes,
-                      (d & ((1u << kCopyLenBits) - 1u)) * kChunkBytes, &plan.full[s]);
+        tma::arrive_expect_tx(&c.sh->full[s], c.my_bytes);
+        const char* src = c.Q + (size_t)q * c.plane_bytes;
+        for (int i = c.warp; i < c.n_copies; i += kStageWarps) {
+            const unsigned d = c.sh->copy_dst[i];
+            tma::load(base + (size_t)(d >> kCopyLenBits) * kBlockBytes, src + (size_t)c.sh->copy_src[i] * kBlockBytes,
+                      (d & ((1u << kCopyLenBits) - 1u)) * kBlockBytes, &c.sh->full[s]);
         }
     }
     __syncwarp();
@@ -504,17 +613,17 @@ template <int NT, int K>
 __device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&pk)[kRegSlots],
                                            const float (&wt)[kRegSlots], const float (&wb)[kRegSlots])
 {
-    StagePlan& plan = *c.plan;
-    const int n_stage = plan.stages;
+    const int n_stage = c.n_stage;
     const size_t ostride = (size_t)c.P;
     stage_issue(c, 0);
     for (int q = 0; q < c.chunks; ++q) {
-        if (q + 1 < c.chunks) {
-            // the stage chunk q+1 goes to was read for chunk q-1 (two stages) or q (one): every warp must be done with it
-            if (n_stage == 2) { if (q >= 1) __syncthreads(); stage_issue(c, q + 1); }
+        if (n_stage == 2 && q + 1 < c.chunks) {
+            // the stage chunk q+1 goes to was read for chunk q-1: every warp must be done with it
+            if (q >= 1) __syncthreads();
+            stage_issue(c, q + 1);
         }
         const int s = n_stage == 2 ? (q & 1) : 0;
-        tma::wait(&plan.full[s], (unsigned)(n_stage == 2 ? (q >> 1) : q) & 1u);
+        tma::wait(&c.sh->full[s], (unsigned)(n_stage == 2 ? (q >> 1) : q) & 1u);
         if (K > 0) {
             const unsigned char* base = c.stage + (size_t)s * (kStageBytes / 2);
             float* o = c.out_top + (size_t)q * kChunkChannels * ostride;
@@ -543,14 +652,28 @@ __device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&p
                         }
                     }
                     if (K == kRegSlots) {
-                        for (int k = kRegSlots; k < c.kmax; ++k) {      // slots beyond the registers: converted in place by the prologue
-                            const uint4 e = __ldcg(c.list + k * 32);
-                            const float4 t = *reinterpret_cast<const float4*>(base + (e.x ^ ((unsigned)u << 4)));
-                            const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
-                            at.x = fmaf(t.x, w0, at.x); at.y = fmaf(t.y, w0, at.y);
-                            at.z = fmaf(t.z, w0, at.z); at.w = fmaf(t.w, w0, at.w);
-                            ab.x = fmaf(t.x, w1, ab.x); ab.y = fmaf(t.y, w1, ab.y);
-                            ab.z = fmaf(t.z, w1, ab.z); ab.w = fmaf(t.w, w1, ab.w);
+                        // slots beyond the registers: their entries come back from L1 (they are re-read for every
+                        // channel group), kTailBatch at a time so that the entry loads and then the shared-memory
+                        // loads of a batch overlap; same FMAs in the same order as one at a time
+                        for (int k0 = kRegSlots; k0 < c.kmax; k0 += kTailBatch) {
+                            uint4 e[kTailBatch];
+                            float4 t[kTailBatch];
+                            #pragma unroll
+                            for (int j = 0; j < kTailBatch; ++j)
+                                e[j] = k0 + j < c.kmax ? __ldca(c.list + (k0 + j) * 32) : make_uint4(0u, 0u, 0u, 0u);
+                            #pragma unroll
+                            for (int j = 0; j < kTailBatch; ++j)
+                                t[j] = *reinterpret_cast<const float4*>(base + (e[j].x ^ ((unsigned)u << 4)));
+                            #pragma unroll
+                            for (int j = 0; j < kTailBatch; ++j) {
+                                if (k0 + j < c.kmax) {
+                                    const float w0 = __uint_as_float(e[j].y), w1 = __uint_as_float(e[j].z);
+                                    at.x = fmaf(t[j].x, w0, at.x); at.y = fmaf(t[j].y, w0, at.y);
+                                    at.z = fmaf(t[j].z, w0, at.z); at.w = fmaf(t[j].w, w0, at.w);
+                                    ab.x = fmaf(t[j].x, w1, ab.x); ab.y = fmaf(t[j].y, w1, ab.y);
+                                    ab.z = fmaf(t[j].z, w1, ab.z); ab.w = fmaf(t[j].w, w1, ab.w);
+                                }
+                            }
                         }
                     }
                     float* og = o + (size_t)(4 * u) * ostride;
@@ -575,26 +698,31 @@ __global__ void __launch_bounds__(kStageThreads, 2)
 stagegather_kernel(const GatherParams prm)
 {
     SLR_DYNAMIC_SMEM(stage_mem);
-    __shared__ StagePlan plan;
+    __shared__ StageShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_fg = (prm.n_frames + kStageFrames - 1) / kStageFrames;
-    const int tile = (int)(blockIdx.x / (unsigned)n_fg);
-    const int f = (int)(blockIdx.x % (unsigned)n_fg) * kStageFrames + warp / kPairsPerTile, pr = warp % kPairsPerTile;
+    const int fg = (int)(blockIdx.x % (unsigned)n_fg), tile = (int)(blockIdx.x / (unsigned)n_fg);
+    const StageRecord* rec = prm.records + (int64_t)fg * prm.n_tiles + tile;
+    const int n_stage = (int)__ldcg(&rec->stages);
+    if (n_stage == 0) return;               // the sources do not fit: rowgather_kernel does this tile
+    const int n_copies = (int)__ldcg(&rec->n_copies);
+    const int f = fg * kStageFrames + warp / kPairsPerTile, pr = warp % kPairsPerTile;
     const bool have_frame = f < prm.n_frames;
     const unsigned flag = have_frame ? __ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile) : 2u;
     const bool active = flag != 2u;                      // warp-uniform; flag 2 = done entirely by the heavy kernels
     const int64_t P = prm.P;
 
-    for (int i = tid; i < kSets * kPlanRows; i += kStageThreads) { (&plan.xlo[0][0])[i] = 0x7fffffff; (&plan.xhi[0][0])[i] = -1; }
-    if (tid < kSets) { plan.ylo[tid] = 0x7fffffff; plan.yhi[tid] = -1; }
-    if (tid < 8)      // staged pixel 0 of either stage: the all-zero pixel unused list slots read
-        reinterpret_cast<float4*>(stage_mem + (size_t)(tid >> 2) * (kStageBytes / 2))[tid & 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int i = tid; i < n_copies; i += kStageThreads) {
+        sh.copy_src[i] = __ldcg(rec->copy_src + i);
+        sh.copy_dst[i] = __ldcg(rec->copy_dst + i);
+    }
+    if (tid < 16)     // staged block 0 of either stage: the all-zero block unused list slots read
+        reinterpret_cast<float4*>(stage_mem + (size_t)(tid >> 3) * (kStageBytes / 2))[tid & 7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (tid == 0) {
-        tma::init(&plan.full[0], kStageWarps);
-        tma::init(&plan.full[1], kStageWarps);
+        tma::init(&sh.full[0], kStageWarps);
+        tma::init(&sh.full[1], kStageWarps);
         tma::fence_init();
     }
-    __syncthreads();
 
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     const int X = tx * TW + lane, Y = ty * TH + 2 * pr;
@@ -603,33 +731,36 @@ stagegather_kernel(const GatherParams prm)
     const int kmax = active ? (int)__ldg(prm.row_k + pair) : 0;
 
     StageCtx c;
-    c.Q = prm.Q; c.stage = stage_mem; c.plan = &plan; c.P = P; c.W = prm.W; c.C = prm.C; c.kmax = kmax;
-    c.chunks = (int)scene_chunks(prm.C); c.warp = warp;
+    c.Q = prm.Q; c.plane_bytes = (size_t)quilt_plane_blocks(prm.H, prm.W) * kBlockBytes;
+    c.stage = stage_mem; c.sh = &sh; c.P = P; c.W = prm.W; c.C = prm.C; c.kmax = kmax;
+    c.chunks = (int)scene_chunks(prm.C); c.warp = warp; c.n_copies = n_copies; c.n_stage = n_stage;
     c.list = prm.lists + pair * (kListDepth * 32) + lane;
     c.out_top = prm.out + (int64_t)f * prm.C * P + pix;
     c.in_top = active && X < prm.W && Y < prm.H;
     c.in_bot = active && X < prm.W && Y + 1 < prm.H;
 
-    // ---- the lists: entries, scalar-plane sums (tail channels, then the normaliser), and their sources into the plan
-    unsigned pk[kRegSlots], sxy[kRegSlots];
+    // ---- the lists: staged offsets and weights, and the scalar-plane sums (tail channels, then the normaliser)
+    unsigned pk[kRegSlots];
     float wt[kRegSlots], wb[kRegSlots];
-    #pragma unroll
-    for (int k = 0; k < kRegSlots; ++k) {
-        uint4 e = make_uint4((unsigned)P, 0u, 0u, 0u);
-        if (k < kmax) e = __ldcg(c.list + k * 32);
-        pk[k] = e.x; sxy[k] = e.w;
-        wt[k] = __uint_as_float(e.y);
-        wb[k] = __uint_as_float(e.z);
-    }
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
     {
+        unsigned sxy[kRegSlots];
+        #pragma unroll
+        for (int k = 0; k < kRegSlots; ++k) {
+            uint4 e = make_uint4(0u, 0u, 0u, pack_xy(0, prm.H));
+            if (k < kmax) e = __ldcg(c.list + k * 32);
+            pk[k] = e.x; sxy[k] = e.w;
+            wt[k] = __uint_as_float(e.y);
+            wb[k] = __uint_as_float(e.z);
+        }
         const int64_t sstride = P + 1;
         #pragma unroll
         for (int k = 0; k < kRegSlots; ++k) {
             if (k < kmax) {                              // warp-uniform
+                const unsigned p = (sxy[k] >> 16) * (unsigned)prm.W + (sxy[k] & 0xffffu);
                 #pragma unroll
                 for (int t = 0; t <= NT; ++t) {
-                    const float s = __ldg(prm.S + (int64_t)t * sstride + (pk[k] & kPixelMask));
+                    const float s = __ldg(prm.S + (int64_t)t * sstride + p);
                     if (slot_role(k) != kBottomOnly) sum_t[t] = fmaf(s, wt[k], sum_t[t]);
                     if (slot_role(k) != kTopOnly) sum_b[t] = fmaf(s, wb[k], sum_b[t]);
                 }
@@ -637,9 +768,10 @@ stagegather_kernel(const GatherParams prm)
         }
         for (int k = kRegSlots; k < kmax; ++k) {
             const uint4 e = __ldcg(c.list + k * 32);
+            const unsigned p = (e.w >> 16) * (unsigned)prm.W + (e.w & 0xffffu);
             #pragma unroll
             for (int t = 0; t <= NT; ++t) {
-                const float s = __ldg(prm.S + (int64_t)t * sstride + (e.x & kPixelMask));
+                const float s = __ldg(prm.S + (int64_t)t * sstride + p);
                 sum_t[t] = fmaf(s, __uint_as_float(e.y), sum_t[t]);
                 sum_b[t] = fmaf(s, __uint_as_float(e.z), sum_b[t]);
             }
@@ -649,98 +781,10 @@ stagegather_kernel(const GatherParams prm)
     c.inv_t = raw ? 1.0f : 1.0f / fmaxf(sum_t[NT], prm.eps);
     c.inv_b = raw ? 1.0f : 1.0f / fmaxf(sum_b[NT], prm.eps);
 
-    // one source pixel of one lane into the plan; where the whole warp names the same (set, row) -- regular
-    // flow -- one lane does the four shared-memory atomics for all
-    auto note = [&](unsigned ex, unsigned exy) {
-        const bool used = (ex & kPixelMask) != (unsigned)P;
-        const unsigned m_used = __ballot_sync(0xffffffffu, used);
-        if (m_used == 0u) return;
-        const int set = (int)(ex >> kSetShift), x = (int)(exy & 0xffffu), y = (int)(exy >> 16);
-        const unsigned key = (unsigned)set << 16 | (unsigned)y;
-        const int leader = __ffs(m_used) - 1;
-        const unsigned key0 = __shfl_sync(0xffffffffu, key, leader);
-        if (__all_sync(0xffffffffu, !used || key == key0)) {
-            const int xmin = __reduce_min_sync(0xffffffffu, used ? x : 0x7fffffff);
-            const int xmax = __reduce_max_sync(0xffffffffu, used ? x : -1);
-            if (lane == leader) {
-                atomicMin(&plan.ylo[set], y); atomicMax(&plan.yhi[set], y);
-                atomicMin(&plan.xlo[set][y & (kPlanRows - 1)], xmin); atomicMax(&plan.xhi[set][y & (kPlanRows - 1)], xmax);
-            }
-        } else if (used) {
-            atomicMin(&plan.ylo[set], y); atomicMax(&plan.yhi[set], y);
-            atomicMin(&plan.xlo[set][y & (kPlanRows - 1)], x); atomicMax(&plan.xhi[set][y & (kPlanRows - 1)], x);
-        }
-    };
-    #pragma unroll
-    for (int k = 0; k < kRegSlots; ++k)
-        if (k < kmax) note(pk[k], sxy[k]);
-    for (int k = kRegSlots; k < kmax; ++k) {
-        const uint4 e = __ldcg(c.list + k * 32);
-        note(e.x, e.w);
-    }
-    __syncthreads();
-
-    // ---- plan -> staged offsets of the rows and the list of copies (warp 0)
-    if (warp == 0) {
-        int total = 1, n_copies = 0;          // staged pixel 0 is the zero pixel
-        bool ok = true;
-        #pragma unroll
-        for (int set = 0; set < kSets; ++set) {
-            const int ylo = plan.ylo[set], yhi = plan.yhi[set];
-            if (yhi < ylo) continue;
-            if (yhi - ylo >= kPlanRows) { ok = false; continue; }
-            for (int r0 = 0; r0 < kPlanRows; r0 += 32) {
-                const int r = r0 + lane;
-                const int lo = plan.xlo[set][r], hi = plan.xhi[set][r];
-                const int len = hi >= lo ? hi - lo + 1 : 0;
-                int incl = len;
-                #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const int off = total + incl - len;
-                const unsigned m = __ballot_sync(0xffffffffu, len > 0);
-                if (len >= (1 << kCopyLenBits)) ok = false;
-                if (len > 0 && off + len <= kStagePixels1 + 1) {
-                    const int y = ylo + ((r - ylo) & (kPlanRows - 1));       // the row of [ylo, yhi] that hashes to r
-                    const int i = n_copies + __popc(m & ((1u << lane) - 1u));
-                    plan.rowoff[set][r] = off - lo;
-                    plan.copy_src[i] = (unsigned)(y * prm.W + lo);
-                    plan.copy_dst[i] = (unsigned)off << kCopyLenBits | (unsigned)len;
-                }
-                total += __shfl_sync(0xffffffffu, incl, 31);
-                n_copies += __popc(m);
-            }
-        }
-        ok = __all_sync(0xffffffffu, ok) && total <= kStagePixels1 + 1;
-        if (lane == 0) {
-            plan.n_copies = n_copies;
-            plan.stages = !ok ? 0 : (total <= kStagePixels2 + 1 ? 2 : 1);
-        }
-    }
-    __syncthreads();
-    const int n_stage = plan.stages;
-    if (have_frame && pr == 0 && lane == 0) prm.fallback[(int64_t)f * prm.n_tiles + tile] = n_stage == 0 ? 1u : 0u;
-    if (n_stage == 0) return;               // the sources do not fit: rowgather_kernel does this tile
-
-    // ---- list entries -> byte offsets into a stage (pixel index * 64 | unit swizzle of the column)
-    auto staged = [&](unsigned ex, unsigned exy) -> unsigned {
-        if ((ex & kPixelMask) == (unsigned)P) return 0u;
-        const int set = (int)(ex >> kSetShift), x = (int)(exy & 0xffffu), y = (int)(exy >> 16);
-        const int idx = plan.rowoff[set][y & (kPlanRows - 1)] + x;
-        return (unsigned)idx * kChunkBytes | quilt_swizzle((unsigned)x) << 4;
-    };
-    #pragma unroll
-    for (int k = 0; k < kRegSlots; ++k) pk[k] = staged(pk[k], sxy[k]);
-    for (int k = kRegSlots; k < kmax; ++k) {
-        uint4 e = __ldcg(c.list + k * 32);
-        e.x = staged(e.x, e.w);
-        __stcg(const_cast<uint4*>(c.list) + k * 32, e);
-    }
+    __syncthreads();                      // copy list, zero blocks and barriers are in place
     {
         unsigned bytes = 0;
-        for (int i = warp; i < plan.n_copies; i += kStageWarps) bytes += (plan.copy_dst[i] & ((1u << kCopyLenBits) - 1u)) * kChunkBytes;
+        for (int i = warp; i < n_copies; i += kStageWarps) bytes += (sh.copy_dst[i] & ((1u << kCopyLenBits) - 1u)) * kBlockBytes;
         c.my_bytes = bytes;
     }
 
@@ -970,6 +1014,14 @@ using slr_host::Workspace;
 
 namespace {
 
+// SLR_GATHER_MODE=ldg: rowgather_kernel for every tile (the round-1 path, kept for A/B runs and as the
+// fallback of the staged path); default: stagegather_kernel first.
+bool gather_staged()
+{
+    const char* e = getenv("SLR_GATHER_MODE");
+    return !(e && strcmp(e, "ldg") == 0);
+}
+
 // Fills the kernel parameters shared by slr_clip_expand and slr_clip_gather.
 int make_params(GatherParams& prm, const void* scene, const float* motion, int64_t C, int n_tail,
                 int64_t H, int64_t W, int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
@@ -989,6 +1041,9 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     prm.Q = (const char*)((const float*)scene + scene_quilt_offset_floats(C, n_tail, P));
     prm.fallback = ws.fallback;
     prm.only_fallback = 0;
+    prm.records = ws.records;
+    // the plan packs a source row into 14 bits and a column into 16 (plan_key)
+    prm.staged = gather_staged() && H <= 16384 && W <= 65535 ? 1 : 0;
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;
@@ -1018,14 +1073,6 @@ GatherShape gather_shape()
     int f = 0, r = 0;
     if (e && sscanf(e, "%dx%d", &f, &r) == 2) { g.frames = f; g.pairs = r; }
     return g;
-}
-
-// SLR_GATHER_MODE=ldg: rowgather_kernel for every tile (the round-1 path, kept for A/B runs and as the
-// fallback of the staged path); default: stagegather_kernel first.
-bool gather_staged()
-{
-    const char* e = getenv("SLR_GATHER_MODE");
-    return !(e && strcmp(e, "ldg") == 0);
 }
 
 template <int NT>
@@ -1058,7 +1105,7 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                                nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
-    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
+    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + kStageFrames - 1) / kStageFrames);
     expand_kernel<<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
     return SLR_LAUNCH_STATUS();
 }
@@ -1074,7 +1121,7 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
                                out, aux, mask, workspace, workspace_bytes);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream_;
-    if (gather_staged()) {
+    if (prm.staged) {
         // sources staged in shared memory by the TMA unit; the tiles whose sources do not fit are flagged ...
         const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + kStageFrames - 1) / kStageFrames);
         if (n_tail == 0) launch_stagegather<0>(prm, grid, s);
@@ -1157,7 +1204,7 @@ extern "C" int slr_clip_stats_host(const void* workspace, size_t workspace_bytes
     uint32_t n_full = 0, n_fallback = 0;
     for (size_t i = 0; i < (size_t)tiles; ++i) {
         n_full += flags[i] == 2u;
-        n_fallback += gather_staged() && flags[i] != 2u && fallback[i] == 1u;
+        n_fallback += flags[i] != 2u && fallback[i] == 1u;
     }
     stats[0] = n_flag; stats[1] = n_full; stats[2] = n_excess; stats[3] = ws.excess_cap;
     stats[4] = n_fallback; stats[5] = (uint32_t)tiles;

@@ -58,26 +58,33 @@ scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, c
 
 // ---------------------------------------------------------------------------
 // scene_quilt: the Q region of the scene buffer from its G4 region (clip_common.cuh): chunks of 16
-// channels, 64 bytes per pixel, float4 units swizzled by the pixel's column.  Pure data movement;
+// channels, 128-byte blocks of two horizontally adjacent pixels, float4 units permuted by the column.  Pure data movement;
 // its own kernel so that a rank that RECEIVED the G4 / S regions (sharding.SceneExchange broadcasts
 // only those) can derive Q locally.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-scene_quilt_kernel(const float4* __restrict__ G4, float4* __restrict__ Q, int groups, int W, int64_t P)
+scene_quilt_kernel(const float4* __restrict__ G4, float4* __restrict__ Q, int groups, int H, int W, int64_t P)
 {
-    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (p > P) return;
+    // one thread per (pixel column slot of a block row, chunk): x runs over 2 * Wb columns (the last may be padding)
+    const int Wb = (int)quilt_row_blocks(W);
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t n = (int64_t)H * Wb * 2;
     const int q = blockIdx.y;
-    const unsigned sw = p < P ? quilt_swizzle((unsigned)(p % W)) : 0u;
-    float4 u[4];
-    #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int g = 4 * q + j;
-        u[j] = g < groups ? __ldg(G4 + (int64_t)g * (P + 1) + p) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4* plane = Q + (int64_t)q * quilt_plane_blocks(H, W) * (kBlockBytes / 16);
+    if (i >= n) {
+        if (i < n + 8) plane[n * 4 + (i - n)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // the trailing all-zero block
+        return;
     }
-    float4* dst = Q + ((int64_t)q * (P + 1) + p) * 4;
+    const int y = (int)(i / (2 * Wb)), x = (int)(i - (int64_t)y * 2 * Wb);
+    const bool real = x < W;
+    const int64_t p = real ? (int64_t)y * W + x : P;              // padding column of an odd-width image: the zero pixel
+    float4* block = plane + ((int64_t)y * Wb + (x >> 1)) * (kBlockBytes / 16);
+    const unsigned slot = quilt_slot((unsigned)x);
     #pragma unroll
-    for (int j = 0; j < 4; ++j) dst[j ^ sw] = u[j];
+    for (int u = 0; u < 4; ++u) {
+        const int g = 4 * q + u;
+        block[slot ^ (unsigned)u] = g < groups ? __ldg(G4 + (int64_t)g * (P + 1) + p) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -276,18 +283,19 @@ extern "C" size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W)
 {
     if (C <= 0 || n_tail < 0 || H <= 0 || W <= 0) return 0;
     const int64_t P = H * W;
-    return sizeof(float) * (size_t)(scene_quilt_offset_floats(C, n_tail, P) + scene_chunks(C) * (P + 1) * (kChunkBytes / 4));
+    return sizeof(float) * (size_t)(scene_quilt_offset_floats(C, n_tail, P) + scene_chunks(C) * quilt_plane_blocks(H, W) * (kBlockBytes / 4));
 }
 
 extern "C" int slr_scene_quilt(void* scene, int64_t C, int n_tail, int64_t H, int64_t W, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) && n_tail >= 0 && n_tail <= 2 &&
-                   ((uintptr_t)scene & 63) == 0, "slr_scene_quilt: bad arguments");
+                   ((uintptr_t)scene & 15) == 0, "slr_scene_quilt: bad arguments");
     const int64_t P = H * W;
     const int groups = (int)((C + 3) / 4);
     float4* Q = (float4*)((float*)scene + scene_quilt_offset_floats(C, n_tail, P));
-    dim3 grid((unsigned)((P + 1 + 255) / 256), (unsigned)scene_chunks(C), 1);
-    scene_quilt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float4*)scene, Q, groups, (int)W, P);
+    const int64_t n = H * quilt_row_blocks(W) * 2 + 8;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)scene_chunks(C), 1);
+    scene_quilt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float4*)scene, Q, groups, (int)H, (int)W, P);
     return SLR_LAUNCH_STATUS();
 }
 
@@ -296,7 +304,7 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
                               int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(feat && z && scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
-                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 63) == 0,
+                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 15) == 0,
                    "slr_scene_prep: bad arguments");
     const int64_t P = H * W;
     const int groups = (int)((C + 3) / 4);

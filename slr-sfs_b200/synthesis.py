@@ -204,7 +204,7 @@ class JointSplat:
         if scene_buffer is not None:
             need = self.scene_buffer_numel(self.C, self.n_tail, self.H, self.W)
             assert scene_buffer.is_cuda and scene_buffer.dtype == torch.float32 and scene_buffer.is_contiguous() \
-                and scene_buffer.numel() >= need and scene_buffer.data_ptr() % 64 == 0
+                and scene_buffer.numel() >= need and scene_buffer.data_ptr() % 16 == 0
             self._scene = scene_buffer
             # caller-owned: same bookkeeping as a pool entry (users' events), never handed to the pool
             self._scene_entry = {"kind": "external", "last": {}, "buf": scene_buffer}
