@@ -37,6 +37,7 @@ constexpr int kCopyLenBits = 12;
 struct StageRecord {
     unsigned n_copies;
     unsigned stages;                                 // 0: does not fit -> rowgather_kernel; 1 / 2: single / double buffered
+    unsigned warp_bytes[8];                          // bytes per chunk of copies i with i % 8 == w (warp w of the gather issues those)
     unsigned copy_src[kMaxCopies];                   // first block (within a chunk plane of Q) of a row segment
     unsigned copy_dst[kMaxCopies];                   // staged block index << kCopyLenBits | blocks
 };

@@ -74,10 +74,12 @@ struct GatherParams {
     uint4* excess;             // [excess_cap]: (destination pixel, source pixel, weight, frame) beyond kListDepth
     unsigned* excess_count;    // [1], zeroed by slr_clip_plan
     unsigned excess_cap;
-    float* heavy_sums;         // [frames][3][P] (tail..., norm) sums of flagged tiles
+    float* heavy_sums;         // [frames][3][P] un-normalised (tail..., norm) sums of every destination pixel, written by
+                               // expand_kernel; flagged tiles get their excess pairs added by heavy_excess_kernel
     const char* Q;             // [chunks] planes of (P + 1) x 64 B: the staged copy of G (clip_common.cuh)
     unsigned* fallback;        // [frames][n_tiles]: 1 = stagegather_kernel left the tile to rowgather_kernel
     int only_fallback;         // rowgather_kernel: skip the tiles stagegather_kernel has done
+    int n_tail;                // scalar planes of S besides the normaliser
     int staged;                // expand_kernel: plan the staging (stagegather_kernel follows) or not (rowgather_kernel for all)
     StageRecord* records;      // [frame pairs][n_tiles] staging plans
     float* out;                // [frames][C][P]
@@ -139,6 +141,7 @@ expand_kernel(const GatherParams prm)
     __shared__ int row_block[kSets][kPlanRows];    // staged block of column 0 of a source row (hashed by row % kPlanRows)
     __shared__ int ylo[kSets], yhi[kSets];
     __shared__ unsigned stages_s;
+    __shared__ unsigned warp_bytes[8];             // bytes per chunk of the copies warp w of stagegather_kernel will issue
     static_assert(sizeof(tab) >= 2 * kSets * kPlanRows * sizeof(int), "the plan's column ranges alias the list table");
     int* xlo = reinterpret_cast<int*>(tab);        // [kSets][kPlanRows], phases A and B only
     int* xhi = xlo + kSets * kPlanRows;
@@ -157,6 +160,7 @@ expand_kernel(const GatherParams prm)
     if (prm.staged) {
         for (int i = tid; i < kSets * kPlanRows; i += TILE) { xlo[i] = 0x7fffffff; xhi[i] = -1; }
         if (tid < kSets) { ylo[tid] = 0x7fffffff; yhi[tid] = -1; }
+        if (tid < 8) warp_bytes[tid] = 0u;
         __syncthreads();
         auto note = [&](unsigned set, int y, int x0, int x1) {
             atomicMin(&ylo[set], y); atomicMax(&yhi[set], y);
@@ -220,6 +224,7 @@ expand_kernel(const GatherParams prm)
                         row_block[set][r] = at - (lo >> 1);
                         rec->copy_src[i] = (unsigned)(y * Wb + (lo >> 1));
                         rec->copy_dst[i] = (unsigned)at << kCopyLenBits | (unsigned)len;
+                        atomicAdd(&warp_bytes[i & 7], (unsigned)len * kBlockBytes);
                     }
                     total += __shfl_sync(0xffffffffu, incl, 31);
                     n_copies += __popc(m);
@@ -231,6 +236,8 @@ expand_kernel(const GatherParams prm)
                 rec->n_copies = (unsigned)n_copies;
                 rec->stages = stages_s;
             }
+            __syncwarp();
+            if (lane < 8) rec->warp_bytes[lane] = warp_bytes[lane];
         }
         __syncthreads();
         stages = stages_s;
@@ -327,12 +334,45 @@ expand_kernel(const GatherParams prm)
             const int64_t pair = pair0 + (tid >> 5);
             if ((tid & 31) == 0) prm.row_k[pair] = (unsigned)kmax;
             uint4* dst = prm.lists + pair * (kListDepth * 32) + (tid & 31);
+            // ... and, on the way, the un-normalised sums of the scalar planes (tail channels, then the
+            // normaliser e^Z) of this lane's two pixels: same products in the same order as rowgather_kernel
+            float st[3] = {0.0f, 0.0f, 0.0f}, sb[3] = {0.0f, 0.0f, 0.0f};
+            const int64_t sstride = P + 1;
+            const bool want_sums = stages != 0u;        // stagegather_kernel reads them; rowgather_kernel sums for itself
+            auto scalars = [&](const uint4& e, int k) {
+                if (!want_sums) return;
+                const unsigned p = (e.w >> 16) * (unsigned)prm.W + (e.w & 0xffffu);
+                #pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (j <= prm.n_tail) {
+                        const float sv = __ldg(prm.S + (int64_t)j * sstride + p);
+                        if (slot_role(k) != kBottomOnly) st[j] = fmaf(sv, __uint_as_float(e.y), st[j]);
+                        if (slot_role(k) != kTopOnly) sb[j] = fmaf(sv, __uint_as_float(e.z), sb[j]);
+                    }
+                }
+            };
             for (int k = 0; k < min(kmax, kSmemSlots); ++k) {
                 const bool used = k < kCanon ? (my_occ >> k & 1u) : (k - kCanon < n_ovf);
-                __stcg(dst + k * 32, used ? tab[k * kCols + tid] : none);
+                const uint4 e = used ? tab[k * kCols + tid] : none;
+                __stcg(dst + k * 32, e);
+                if (used) scalars(e, k);
             }
-            // slots past the shared table were written in place; pad this lane's unused ones
+            // slots past the shared table were written in place (by whichever thread met the pair)
+            if (want_sums)
+                for (int k = kSmemSlots; k < my_hi; ++k) scalars(__ldcg(dst + k * 32), k);
+            // pad this lane's unused ones
             for (int k = max(my_hi, kSmemSlots); k < kmax; ++k) __stcg(dst + k * 32, none);
+            const int Xc = tx * TW + (tid & 31), Yc = ty * TH + 2 * (tid >> 5);
+            if (want_sums && Xc < prm.W && Yc < prm.H) {
+                float* hs = prm.heavy_sums + (int64_t)f * 3 * P + (int64_t)Yc * prm.W + Xc;
+                #pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (j <= prm.n_tail) {
+                        hs[(int64_t)j * P] = st[j];
+                        if (Yc + 1 < prm.H) hs[(int64_t)j * P + prm.W] = sb[j];
+                    }
+                }
+            }
         }
     }
 }
@@ -568,7 +608,6 @@ rowgather_kernel(const GatherParams prm)
 // ---------------------------------------------------------------------------
 constexpr int kStageWarps = kStageFrames * kPairsPerTile;      // one warp per (frame, row pair)
 constexpr int kStageThreads = 32 * kStageWarps;
-constexpr int kTailBatch = 4;                                  // list slots beyond the registers are read this many at a time
 
 struct StageShared {
     unsigned copy_src[kMaxCopies];
@@ -580,6 +619,7 @@ struct StageCtx {
     const char* Q;            // chunk plane 0
     size_t plane_bytes;       // bytes of a chunk plane
     unsigned char* stage;     // staging area
+    tma::SharedAddr stage_addr, full_addr;     // the same and the two barriers, as the copy instruction wants them
     StageShared* sh;
     const uint4* list;        // this lane's column of the row-pair list
     float* out_top;
@@ -594,28 +634,49 @@ struct StageCtx {
 __device__ __forceinline__ void stage_issue(const StageCtx& c, int q)
 {
     const int s = c.n_stage == 2 ? (q & 1) : 0;
-    unsigned char* base = c.stage + (size_t)s * (kStageBytes / 2);
     if (tma::elect_one()) {
-        tma::arrive_expect_tx(&c.sh->full[s], c.my_bytes);
+        const tma::SharedAddr base = c.stage_addr + (tma::SharedAddr)s * (kStageBytes / 2);
+        const tma::SharedAddr bar = c.full_addr + (tma::SharedAddr)s * sizeof(tma::Barrier);
+        tma::arrive_expect_tx_at(bar, c.my_bytes);
         const char* src = c.Q + (size_t)q * c.plane_bytes;
         for (int i = c.warp; i < c.n_copies; i += kStageWarps) {
             const unsigned d = c.sh->copy_dst[i];
-            tma::load(base + (size_t)(d >> kCopyLenBits) * kBlockBytes, src + (size_t)c.sh->copy_src[i] * kBlockBytes,
-                      (d & ((1u << kCopyLenBits) - 1u)) * kBlockBytes, &c.sh->full[s]);
+            tma::load_at(base + (d >> kCopyLenBits) * kBlockBytes, src + (size_t)c.sh->copy_src[i] * kBlockBytes,
+                         (d & ((1u << kCopyLenBits) - 1u)) * kBlockBytes, bar);
         }
     }
     __syncwarp();
 }
 
+__device__ __forceinline__ void fma4(float4& a, const float4& v, float w)
+{
+    a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
+}
+
+// normalise and store 4 channels of the lane's two pixels
+__device__ __forceinline__ void stage_store(const StageCtx& c, float* og, int ch0, const float4& at, const float4& ab)
+{
+    const size_t ostride = (size_t)c.P;
+    const float rt[4] = {at.x * c.inv_t, at.y * c.inv_t, at.z * c.inv_t, at.w * c.inv_t};
+    const float rb[4] = {ab.x * c.inv_b, ab.y * c.inv_b, ab.z * c.inv_b, ab.w * c.inv_b};
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (ch0 + j < c.C) {
+            if (c.in_top) __stcs(og + j * ostride, rt[j]);
+            if (c.in_bot) __stcs(og + j * ostride + c.W, rb[j]);
+        }
+    }
+}
+
 // The chunk loop of one warp.  K = compile-time number of register-resident slots (0: a warp without
 // work -- no frame, or a whole-tile heavy tile -- that only takes part in the copies and barriers).
+// The copies of chunk 0 were issued by the caller.
 template <int NT, int K>
 __device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&pk)[kRegSlots],
                                            const float (&wt)[kRegSlots], const float (&wb)[kRegSlots])
 {
     const int n_stage = c.n_stage;
     const size_t ostride = (size_t)c.P;
-    stage_issue(c, 0);
     for (int q = 0; q < c.chunks; ++q) {
         if (n_stage == 2 && q + 1 < c.chunks) {
             // the stage chunk q+1 goes to was read for chunk q-1: every warp must be done with it
@@ -627,64 +688,59 @@ __device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&p
         if (K > 0) {
             const unsigned char* base = c.stage + (size_t)s * (kStageBytes / 2);
             float* o = c.out_top + (size_t)q * kChunkChannels * ostride;
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) {                  // the chunk's four channel groups
-                const int ch0 = q * kChunkChannels + 4 * u;
-                if (ch0 < c.C) {
-                    constexpr int B = K == 0 ? 1 : (K <= 8 ? K : K / 2);      // loads in flight (shared-memory latency is short)
-                    float4 at = make_float4(0.0f, 0.0f, 0.0f, 0.0f), ab = at;
+            constexpr int B = K == 0 ? 1 : (K <= 8 ? K : K / 2);      // loads in flight (shared-memory latency is short)
+            if (K == kRegSlots && c.kmax > kRegSlots) {
+                // Lists deeper than the registers hold (convergence zones): all four channel groups of the chunk are
+                // accumulated together, so that a deep slot's entry is fetched once per chunk (not once per group)
+                // and its four shared-memory loads overlap.  Same FMAs in the same order per accumulator.
+                float4 at[4], ab[4];
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    at[u] = ab[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     #pragma unroll
-                    for (int kb = 0; kb < K; kb += B) {
-                        float4 v[B];
+                    for (int kb = 0; kb < K; kb += 4) {
+                        float4 v[4];
                         #pragma unroll
-                        for (int k = 0; k < B; ++k)
-                            v[k] = *reinterpret_cast<const float4*>(base + (pk[kb + k] ^ ((unsigned)u << 4)));
+                        for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(base + (pk[kb + k] ^ ((unsigned)u << 4)));
                         #pragma unroll
-                        for (int k = 0; k < B; ++k) {
-                            if (slot_role(kb + k) != kBottomOnly) {
-                                at.x = fmaf(v[k].x, wt[kb + k], at.x); at.y = fmaf(v[k].y, wt[kb + k], at.y);
-                                at.z = fmaf(v[k].z, wt[kb + k], at.z); at.w = fmaf(v[k].w, wt[kb + k], at.w);
-                            }
-                            if (slot_role(kb + k) != kTopOnly) {
-                                ab.x = fmaf(v[k].x, wb[kb + k], ab.x); ab.y = fmaf(v[k].y, wb[kb + k], ab.y);
-                                ab.z = fmaf(v[k].z, wb[kb + k], ab.z); ab.w = fmaf(v[k].w, wb[kb + k], ab.w);
-                            }
+                        for (int k = 0; k < 4; ++k) {
+                            if (slot_role(kb + k) != kBottomOnly) fma4(at[u], v[k], wt[kb + k]);
+                            if (slot_role(kb + k) != kTopOnly) fma4(ab[u], v[k], wb[kb + k]);
                         }
                     }
-                    if (K == kRegSlots) {
-                        // slots beyond the registers: their entries come back from L1 (they are re-read for every
-                        // channel group), kTailBatch at a time so that the entry loads and then the shared-memory
-                        // loads of a batch overlap; same FMAs in the same order as one at a time
-                        for (int k0 = kRegSlots; k0 < c.kmax; k0 += kTailBatch) {
-                            uint4 e[kTailBatch];
-                            float4 t[kTailBatch];
+                }
+                uint4 e = __ldca(c.list + kRegSlots * 32);
+                for (int k = kRegSlots; k < c.kmax; ++k) {
+                    float4 t[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const float4*>(base + (e.x ^ ((unsigned)u << 4)));
+                    const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
+                    if (k + 1 < c.kmax) e = __ldca(c.list + (k + 1) * 32);        // the next entry flies during the FMAs
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) { fma4(at[u], t[u], w0); fma4(ab[u], t[u], w1); }
+                }
+                #pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (q * kChunkChannels + 4 * u < c.C) stage_store(c, o + (size_t)(4 * u) * ostride, q * kChunkChannels + 4 * u, at[u], ab[u]);
+            } else {
+                #pragma unroll
+                for (int u = 0; u < 4; ++u) {                  // the chunk's four channel groups
+                    const int ch0 = q * kChunkChannels + 4 * u;
+                    if (ch0 < c.C) {
+                        float4 at = make_float4(0.0f, 0.0f, 0.0f, 0.0f), ab = at;
+                        #pragma unroll
+                        for (int kb = 0; kb < K; kb += B) {
+                            float4 v[B];
                             #pragma unroll
-                            for (int j = 0; j < kTailBatch; ++j)
-                                e[j] = k0 + j < c.kmax ? __ldca(c.list + (k0 + j) * 32) : make_uint4(0u, 0u, 0u, 0u);
+                            for (int k = 0; k < B; ++k)
+                                v[k] = *reinterpret_cast<const float4*>(base + (pk[kb + k] ^ ((unsigned)u << 4)));
                             #pragma unroll
-                            for (int j = 0; j < kTailBatch; ++j)
-                                t[j] = *reinterpret_cast<const float4*>(base + (e[j].x ^ ((unsigned)u << 4)));
-                            #pragma unroll
-                            for (int j = 0; j < kTailBatch; ++j) {
-                                if (k0 + j < c.kmax) {
-                                    const float w0 = __uint_as_float(e[j].y), w1 = __uint_as_float(e[j].z);
-                                    at.x = fmaf(t[j].x, w0, at.x); at.y = fmaf(t[j].y, w0, at.y);
-                                    at.z = fmaf(t[j].z, w0, at.z); at.w = fmaf(t[j].w, w0, at.w);
-                                    ab.x = fmaf(t[j].x, w1, ab.x); ab.y = fmaf(t[j].y, w1, ab.y);
-                                    ab.z = fmaf(t[j].z, w1, ab.z); ab.w = fmaf(t[j].w, w1, ab.w);
-                                }
+                            for (int k = 0; k < B; ++k) {
+                                if (slot_role(kb + k) != kBottomOnly) fma4(at, v[k], wt[kb + k]);
+                                if (slot_role(kb + k) != kTopOnly) fma4(ab, v[k], wb[kb + k]);
                             }
                         }
-                    }
-                    float* og = o + (size_t)(4 * u) * ostride;
-                    const float rt[4] = {at.x * c.inv_t, at.y * c.inv_t, at.z * c.inv_t, at.w * c.inv_t};
-                    const float rb[4] = {ab.x * c.inv_b, ab.y * c.inv_b, ab.z * c.inv_b, ab.w * c.inv_b};
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (ch0 + j < c.C) {
-                            if (c.in_top) __stcs(og + j * ostride, rt[j]);
-                            if (c.in_bot) __stcs(og + j * ostride + c.W, rb[j]);
-                        }
+                        stage_store(c, o + (size_t)(4 * u) * ostride, ch0, at, ab);
                     }
                 }
             }
@@ -733,60 +789,40 @@ stagegather_kernel(const GatherParams prm)
     StageCtx c;
     c.Q = prm.Q; c.plane_bytes = (size_t)quilt_plane_blocks(prm.H, prm.W) * kBlockBytes;
     c.stage = stage_mem; c.sh = &sh; c.P = P; c.W = prm.W; c.C = prm.C; c.kmax = kmax;
+    c.stage_addr = tma::shared_addr(stage_mem); c.full_addr = tma::shared_addr(&sh.full[0]);
     c.chunks = (int)scene_chunks(prm.C); c.warp = warp; c.n_copies = n_copies; c.n_stage = n_stage;
+    c.my_bytes = __ldcg(rec->warp_bytes + warp);
     c.list = prm.lists + pair * (kListDepth * 32) + lane;
     c.out_top = prm.out + (int64_t)f * prm.C * P + pix;
     c.in_top = active && X < prm.W && Y < prm.H;
     c.in_bot = active && X < prm.W && Y + 1 < prm.H;
 
-    // ---- the lists: staged offsets and weights, and the scalar-plane sums (tail channels, then the normaliser)
+    __syncthreads();                      // copy list, zero blocks and barriers are in place
+    stage_issue(c, 0);                    // the first chunk's copies fly while the lists are read
+
+    // ---- the lists (staged offsets and weights) and the sums of the scalar planes expand_kernel left
     unsigned pk[kRegSlots];
     float wt[kRegSlots], wb[kRegSlots];
+    #pragma unroll
+    for (int k = 0; k < kRegSlots; ++k) {
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        if (k < kmax) e = __ldcg(c.list + k * 32);
+        pk[k] = e.x;
+        wt[k] = __uint_as_float(e.y);
+        wb[k] = __uint_as_float(e.z);
+    }
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
     {
-        unsigned sxy[kRegSlots];
+        const float* hs = prm.heavy_sums + (int64_t)f * 3 * P + pix;
         #pragma unroll
-        for (int k = 0; k < kRegSlots; ++k) {
-            uint4 e = make_uint4(0u, 0u, 0u, pack_xy(0, prm.H));
-            if (k < kmax) e = __ldcg(c.list + k * 32);
-            pk[k] = e.x; sxy[k] = e.w;
-            wt[k] = __uint_as_float(e.y);
-            wb[k] = __uint_as_float(e.z);
-        }
-        const int64_t sstride = P + 1;
-        #pragma unroll
-        for (int k = 0; k < kRegSlots; ++k) {
-            if (k < kmax) {                              // warp-uniform
-                const unsigned p = (sxy[k] >> 16) * (unsigned)prm.W + (sxy[k] & 0xffffu);
-                #pragma unroll
-                for (int t = 0; t <= NT; ++t) {
-                    const float s = __ldg(prm.S + (int64_t)t * sstride + p);
-                    if (slot_role(k) != kBottomOnly) sum_t[t] = fmaf(s, wt[k], sum_t[t]);
-                    if (slot_role(k) != kTopOnly) sum_b[t] = fmaf(s, wb[k], sum_b[t]);
-                }
-            }
-        }
-        for (int k = kRegSlots; k < kmax; ++k) {
-            const uint4 e = __ldcg(c.list + k * 32);
-            const unsigned p = (e.w >> 16) * (unsigned)prm.W + (e.w & 0xffffu);
-            #pragma unroll
-            for (int t = 0; t <= NT; ++t) {
-                const float s = __ldg(prm.S + (int64_t)t * sstride + p);
-                sum_t[t] = fmaf(s, __uint_as_float(e.y), sum_t[t]);
-                sum_b[t] = fmaf(s, __uint_as_float(e.z), sum_b[t]);
-            }
+        for (int j = 0; j <= NT; ++j) {
+            if (c.in_top) sum_t[j] = __ldcg(hs + (int64_t)j * P);
+            if (c.in_bot) sum_b[j] = __ldcg(hs + (int64_t)j * P + prm.W);
         }
     }
-    const bool raw = flag == 1u;          // flagged tile: un-normalised sums, heavy_finish_kernel divides
+    const bool raw = flag == 1u;          // flagged tile: un-normalised outputs, heavy_excess / heavy_finish complete them
     c.inv_t = raw ? 1.0f : 1.0f / fmaxf(sum_t[NT], prm.eps);
     c.inv_b = raw ? 1.0f : 1.0f / fmaxf(sum_b[NT], prm.eps);
-
-    __syncthreads();                      // copy list, zero blocks and barriers are in place
-    {
-        unsigned bytes = 0;
-        for (int i = warp; i < n_copies; i += kStageWarps) bytes += (sh.copy_dst[i] & ((1u << kCopyLenBits) - 1u)) * kBlockBytes;
-        c.my_bytes = bytes;
-    }
 
     // the list length is warp-uniform: pick the unroll that fits
     if (!active) stage_rows<NT, 0>(c, pk, wt, wb);
@@ -797,17 +833,12 @@ stagegather_kernel(const GatherParams prm)
     else if (kmax <= 12) stage_rows<NT, 12>(c, pk, wt, wb);
     else stage_rows<NT, 16>(c, pk, wt, wb);
 
+    if (raw) return;                      // sums stay where they are for heavy_excess_kernel / heavy_finish_kernel
     #pragma unroll
     for (int r = 0; r < 2; ++r) {
         if (!(r ? c.in_bot : c.in_top)) continue;
         const float* sum = r ? sum_b : sum_t;
         const int64_t px = pix + (r ? prm.W : 0);
-        if (raw) {          // the excess pairs are still to come: leave the sums for heavy_finish_kernel
-            float* hs = prm.heavy_sums + (int64_t)f * 3 * P + px;
-            #pragma unroll
-            for (int j = 0; j <= NT; ++j) hs[(int64_t)j * P] = sum[j];
-            continue;
-        }
         if (prm.aux) {
             float* a = prm.aux + (int64_t)f * (NT + 1) * P + px;
             #pragma unroll
@@ -1042,6 +1073,7 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     prm.fallback = ws.fallback;
     prm.only_fallback = 0;
     prm.records = ws.records;
+    prm.n_tail = n_tail;
     // the plan packs a source row into 14 bits and a column into 16 (plan_key)
     prm.staged = gather_staged() && H <= 16384 && W <= 65535 ? 1 : 0;
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;

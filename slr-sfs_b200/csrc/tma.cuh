@@ -55,12 +55,22 @@ inline void load(void* dst_shared, const void* src_global, unsigned bytes, Barri
     emu_update(b, 0, -(int32_t)bytes);
 }
 inline bool elect_one() { __syncwarp(); return (threadIdx.x & 31u) == 0u; }
+// shared-memory addresses in the form the copy instruction takes them (computed once, then offset)
+typedef uintptr_t SharedAddr;
+inline SharedAddr shared_addr(const void* p) { return (SharedAddr)p; }
+inline void load_at(SharedAddr dst, const void* src_global, unsigned bytes, SharedAddr barrier)
+{
+    load((void*)dst, src_global, bytes, (Barrier*)barrier);
+}
+inline void arrive_expect_tx_at(SharedAddr barrier, unsigned bytes) { arrive_expect_tx((Barrier*)barrier, bytes); }
 
 #else
 
 typedef uint64_t Barrier;
+// shared-memory addresses in the form the copy instruction takes them (computed once, then offset)
+typedef uint32_t SharedAddr;
 
-__device__ __forceinline__ uint32_t shared_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ SharedAddr shared_addr(const void* p) { return (SharedAddr)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void init(Barrier* b, unsigned count)
 {
@@ -97,6 +107,15 @@ __device__ __forceinline__ void load(void* dst_shared, const void* src_global, u
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(shared_addr(dst_shared)), "l"(src_global), "r"(bytes), "r"(shared_addr(b)) : "memory");
+}
+__device__ __forceinline__ void load_at(SharedAddr dst, const void* src_global, unsigned bytes, SharedAddr barrier)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src_global), "r"(bytes), "r"(barrier) : "memory");
+}
+__device__ __forceinline__ void arrive_expect_tx_at(SharedAddr barrier, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(barrier), "r"(bytes) : "memory");
 }
 // true in exactly one lane of a converged warp; ptxas then keeps the operands of the copies issued
 // under it in uniform registers (no per-lane serialisation loop around UBLKCP)
