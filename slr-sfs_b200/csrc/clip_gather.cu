@@ -147,7 +147,9 @@ expand_kernel(const GatherParams prm)
     int* xhi = xlo + kSets * kPlanRows;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_fg = (prm.n_frames + kStageFrames - 1) / kStageFrames;
+    // staged: a CTA plans and expands the kStageFrames frames that share a staged region; otherwise one frame per CTA
+    const int per_cta = prm.staged ? kStageFrames : 1;
+    const int n_fg = (prm.n_frames + per_cta - 1) / per_cta;
     const int fg = (int)(blockIdx.x % (unsigned)n_fg), tile = (int)(blockIdx.x / (unsigned)n_fg);
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
     const int64_t P = prm.P;
@@ -250,8 +252,8 @@ expand_kernel(const GatherParams prm)
     // unused slots: the all-zero pixel, weights 0 (its (row, column) = (H, 0) is pixel P of the scalar planes)
     const uint4 none = make_uint4(stages == 0u ? (unsigned)P : 0u, 0u, 0u, pack_xy(0, prm.H));
 
-    for (int fi = 0; fi < kStageFrames; ++fi) {
-        const int f = fg * kStageFrames + fi;
+    for (int fi = 0; fi < per_cta; ++fi) {
+        const int f = fg * per_cta + fi;
         if (f >= prm.n_frames) break;
         const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
         const unsigned* off = prm.offsets + (int64_t)f * (prm.n_tiles + 1);
@@ -1045,12 +1047,14 @@ using slr_host::Workspace;
 
 namespace {
 
-// SLR_GATHER_MODE=ldg: rowgather_kernel for every tile (the round-1 path, kept for A/B runs and as the
-// fallback of the staged path); default: stagegather_kernel first.
+// Which gather runs: "ldg" (default) = rowgather_kernel for every tile; "staged" = stagegather_kernel (sources staged in
+// shared memory by the TMA unit) with rowgather_kernel for the tiles that do not fit.  Measured on B200 at
+// 768x1024x64, motion A (profiles/r02): the staged gather's main loop is ~30 % faster, but the staging plan (in
+// expand_kernel), the copy issue and the per-chunk synchronisation cost more than that saves; see DESIGN.md 4.2.
 bool gather_staged()
 {
     const char* e = getenv("SLR_GATHER_MODE");
-    return !(e && strcmp(e, "ldg") == 0);
+    return e && strcmp(e, "staged") == 0;
 }
 
 // Fills the kernel parameters shared by slr_clip_expand and slr_clip_gather.
@@ -1137,7 +1141,8 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                                nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
-    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + kStageFrames - 1) / kStageFrames);
+    const int per_cta = prm.staged ? kStageFrames : 1;
+    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + per_cta - 1) / per_cta);
     expand_kernel<<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
     return SLR_LAUNCH_STATUS();
 }

@@ -277,7 +277,7 @@ def _both_modes(monkeypatch, make):
     sc = make()
     ldg = sc.frames(0, sc.N - 1, 0, sc.N, want_aux=True, want_mask=True)
     assert sc.stats["fallback"] == 0
-    monkeypatch.delenv("SLR_GATHER_MODE")
+    monkeypatch.setenv("SLR_GATHER_MODE", "staged")
     sc = make()
     staged = sc.frames(0, sc.N - 1, 0, sc.N, want_aux=True, want_mask=True)
     return ldg, staged, sc.stats
@@ -332,7 +332,7 @@ def test_emu_staged_gather_incoherent_flow_falls_back(monkeypatch):
     monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
     sc = make()
     ldg = sc.frames(0, N - 1, 5, 4)
-    monkeypatch.delenv("SLR_GATHER_MODE")
+    monkeypatch.setenv("SLR_GATHER_MODE", "staged")
     sc = make()
     staged = sc.frames(0, N - 1, 5, 4)
     assert sc.stats["fallback"] > 0
@@ -347,7 +347,7 @@ def test_emu_staged_gather_deep_lists_and_heavy_tiles(monkeypatch):
     for m in (sink, squeeze):
         monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
         ldg = emu.Scene(feat, Z, m).frames(0, N - 1, 1, 2)
-        monkeypatch.delenv("SLR_GATHER_MODE")
+        monkeypatch.setenv("SLR_GATHER_MODE", "staged")
         sc = emu.Scene(feat, Z, m)
         staged = sc.frames(0, N - 1, 1, 2)
         assert sc.stats["fallback"] < sc.stats["tiles"]
@@ -364,7 +364,7 @@ def test_emu_staged_gather_single_stage_and_capacity_fallback(monkeypatch):
     feat, Z, motion = _scene(H, W, C, "A", 23)
     monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
     ldg = emu.Scene(feat, Z, motion).frames(0, N - 1, 0, N)
-    monkeypatch.delenv("SLR_GATHER_MODE")
+    monkeypatch.setenv("SLR_GATHER_MODE", "staged")
     seen = []
     for nbytes in (64 * 1024, 40 * 1024, 24 * 1024):
         with emu.variant("stage%d" % nbytes, ["-DSLR_STAGE_BYTES=%d" % nbytes]):
