@@ -114,6 +114,16 @@ int slr_joint_scatter(const float* feat, const float* z, const float* zsub,
                       const float* disp_f, const float* disp_b, float alpha,
                       float* acc, int64_t C, int64_t H, int64_t W, slr_stream_t stream);
 
+/* The same with the two directions' blend weights given separately (a_fwd = w_fwd, a_bwd = w_bwd)
+ * instead of (alpha, 1 - alpha): AnimatingSoftmaxSplating.warp_flow
+ * (models/animating_softmax_splating.py:1064-1138) splats an RGB image with Z = 1, weights the forward
+ * direction by e^(Z - max) * alpha and the backward one by e^Z * (1 - alpha), alpha without the "+ 1"
+ * of forward_flow (:1064), and takes precomputed displacement fields. */
+int slr_joint_scatter_weights(const float* feat, const float* z, const float* zsub,
+                              const float* tail, int n_tail,
+                              const float* disp_f, const float* disp_b, float w_fwd, float w_bwd,
+                              float* acc, int64_t C, int64_t H, int64_t W, slr_stream_t stream);
+
 /* Normalise-and-blend: out[c] = acc[c] / max(acc[norm_ch], eps) for c < n_out
  * (animating_softmax_splating.py:923-924; eps = 1e-8).  mask (optional, [H,W]) =
  * acc[norm_ch] > eps (2layers...py:1039).  Exact-zero holes stay exactly 0. */

@@ -302,3 +302,22 @@ def joint_splat_2layer(feat, Z, a_fluid, a_bg_sigmoid, motion, index, alpha0=Tru
     else:
         alpha_fluid = alpha_fluid / norm                                  # :1045
     return gen, alpha_fluid, mask
+
+
+def warp_flow_block(image, forward_flow, backward_flow, index, splat=softsplat_sum):
+    """AnimatingSoftmaxSplating.warp_flow, animating_softmax_splating.py:1064-1138: the RGB twin of the
+    joint block with Z = 1, alpha without the "+ 1" (:1064), precomputed flows, e^(Z - max) forward
+    and e^Z backward (:1067, :1103).  Returns PredImg."""
+    image = _c(image)
+    start, mid, end = [int(v) for v in index]
+    alpha = np.float32(1.0) - np.float32(mid - start) / np.float32(end - start)          # :1064
+    Z = np.ones_like(image[:, :1])                                                       # :1066
+    Zn = Z - Z.max()                                                                     # :1067
+    in_f = np.concatenate([image * np.exp(Zn) * alpha, np.exp(Zn) * alpha], 1)           # :1068
+    acc = splat(in_f, _c(forward_flow))                                                  # :1094
+    one_m = np.float32(1.0) - alpha
+    in_p = np.concatenate([image * np.exp(Z) * one_m, np.exp(Z) * one_m], 1)             # :1103
+    acc_p = splat(in_p, _c(backward_flow))                                               # :1128
+    gen = acc[:, :-1] + acc_p[:, :-1]                                                    # :1133
+    norm = np.maximum(acc[:, -1:] + acc_p[:, -1:], np.float32(1e-8))                     # :1134-1137
+    return gen / norm                                                                    # :1138

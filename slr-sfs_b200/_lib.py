@@ -29,6 +29,7 @@ SIGNATURES = {
     "slr_euler_grad_motion": [_f32p, _flt, _int, _f32p, _f32p, _i64, _i64, _strm],
     "slr_reduce_max": [_f32p, _i64, _f32p, _strm],
     "slr_joint_scatter": [_f32p, _f32p, _f32p, _f32p, _int, _f32p, _f32p, _flt, _f32p, _i64, _i64, _i64, _strm],
+    "slr_joint_scatter_weights": [_f32p, _f32p, _f32p, _f32p, _int, _f32p, _f32p, _flt, _flt, _f32p, _i64, _i64, _i64, _strm],
     "slr_normalize": [_f32p, _f32p, _f32p, _i64, _i64, _i64, _flt, _i64, _i64, _strm],
     "slr_scene_bytes": [_i64, _int, _i64, _i64],
     "slr_scene_core_bytes": [_i64, _int, _i64, _i64],
@@ -112,7 +113,7 @@ def current_stream(device):
 KERNELS_PER_CALL = {
     "slr_softsplat_sum_fwd": 1, "slr_softsplat_grad_input": 1, "slr_softsplat_grad_flow": 1,
     "slr_maxsplat_fwd": 2, "slr_maxwarpnorm": 3, "slr_euler": 1, "slr_euler_grad_motion": 1, "slr_reduce_max": 2,
-    "slr_joint_scatter": 1, "slr_normalize": 1, "slr_scene_prep": 2, "slr_scene_quilt": 1, "slr_clip_frames": 9,
+    "slr_joint_scatter": 1, "slr_joint_scatter_weights": 1, "slr_normalize": 1, "slr_scene_prep": 2, "slr_scene_quilt": 1, "slr_clip_frames": 9,
     "slr_clip_plan": 3, "slr_clip_table": 2, "slr_clip_bin": 1, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 4,
 }
 _launches = 0

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kBlock)
 joint_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ z,
                      const float* __restrict__ zsub, const float* __restrict__ tail, int n_tail,
                      const float* __restrict__ disp_f, const float* __restrict__ disp_b,
-                     float alpha, float* __restrict__ acc, int C, int H, int W, int c_per_block)
+                     float a_f, float a_b, float* __restrict__ acc, int C, int H, int W, int c_per_block)
 {
     const int64_t P = (int64_t)H * W;
     const int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -284,7 +284,6 @@ joint_scatter_kernel(const float* __restrict__ feat, const float* __restrict__ z
     const Footprint ff = landing(x, y, disp_f[p], disp_f[P + p], H, W);
     const Footprint fb = landing(x, y, disp_b[p], disp_b[P + p], H, W);
     if ((ff.ok | fb.ok) == 0u) return;
-    const float a_f = alpha, a_b = 1.0f - alpha;
     const float ez = expf(z[p] - (zsub ? *zsub : 0.0f));
     const int64_t qf = (int64_t)ff.y0 * W + ff.x0, qb = (int64_t)fb.y0 * W + fb.x0;
 
@@ -441,10 +440,10 @@ extern "C" int slr_reduce_max(const float* x, int64_t n, float* out_scalar, slr_
     return SLR_LAUNCH_STATUS();
 }
 
-extern "C" int slr_joint_scatter(const float* feat, const float* z, const float* zsub,
-                                 const float* tail, int n_tail,
-                                 const float* disp_f, const float* disp_b, float alpha,
-                                 float* acc, int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
+extern "C" int slr_joint_scatter_weights(const float* feat, const float* z, const float* zsub,
+                                         const float* tail, int n_tail,
+                                         const float* disp_f, const float* disp_b, float w_fwd, float w_bwd,
+                                         float* acc, int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(feat && z && disp_f && disp_b && acc && C > 0 && H > 0 && W > 0 && H * W < (1ll << 31) &&
                    n_tail >= 0 && (n_tail == 0 || tail), "slr_joint_scatter: bad arguments");
@@ -453,9 +452,17 @@ extern "C" int slr_joint_scatter(const float* feat, const float* z, const float*
     const int chunks = channel_chunks(blocks_for(H * W), C);
     const int per = (int)((C + chunks - 1) / chunks);
     dim3 grid(blocks_for(H * W), (unsigned)((C + per - 1) / per), 1);
-    joint_scatter_kernel<<<grid, kBlock, 0, s>>>(feat, z, zsub, tail, n_tail, disp_f, disp_b, alpha, acc,
+    joint_scatter_kernel<<<grid, kBlock, 0, s>>>(feat, z, zsub, tail, n_tail, disp_f, disp_b, w_fwd, w_bwd, acc,
                                                  (int)C, (int)H, (int)W, per);
     return SLR_LAUNCH_STATUS();
+}
+
+extern "C" int slr_joint_scatter(const float* feat, const float* z, const float* zsub,
+                                 const float* tail, int n_tail,
+                                 const float* disp_f, const float* disp_b, float alpha,
+                                 float* acc, int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
+{
+    return slr_joint_scatter_weights(feat, z, zsub, tail, n_tail, disp_f, disp_b, alpha, 1.0f - alpha, acc, C, H, W, stream_);
 }
 
 extern "C" int slr_normalize(const float* acc, float* out, float* mask, int64_t n_out, int64_t norm_ch,

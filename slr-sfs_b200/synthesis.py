@@ -438,3 +438,38 @@ class JointSplat:
     def frame_scatter(self, index, alpha=None):
         """gen_fs [1,C,H,W] for index = (start, t, end)."""
         return self.normalize(self.accumulate_scatter(index, alpha))
+
+
+def warp_flow_block(image, forward_flow, backward_flow, index):
+    """The RGB twin of the joint block: ``AnimatingSoftmaxSplating.warp_flow``
+    (models/animating_softmax_splating.py:1064-1138).  ``image`` [1,3,H,W] is splatted with the
+    PRECOMPUTED displacement fields ``forward_flow`` = flow_f[mid - start] and ``backward_flow`` =
+    flow_p[end - mid] ([1,2,H,W] each), Z = 1 everywhere:
+
+        alpha = 1 - (mid - start) / (end - start)                       no "+ 1" here (:1064)
+        acc   = splat([img * e^(Z - Z.max()) * alpha, e^(Z - Z.max()) * alpha], forward_flow)
+              + splat([img * e^Z * (1 - alpha),        e^Z * (1 - alpha)],        backward_flow)   (:1067, :1103)
+        out   = acc[:, :3] / clamp(acc[:, 3:], 1e-8)
+
+    The forward direction carries e^0, the backward one e^1 -- the reference's own asymmetry, kept.
+    One fused scatter (slr_joint_scatter_weights) + slr_normalize; returns PredImg [1,3,H,W]."""
+    start, mid, end = _index_triplet(index)
+    image = _req(image.detach(), "image")
+    assert image.dim() == 4 and image.shape[0] == 1
+    C, H, W = image.shape[1:]
+    fwd = _req(forward_flow.detach().reshape(2, H, W), "forward_flow")
+    bwd = _req(backward_flow.detach().reshape(2, H, W), "backward_flow")
+    alpha = np.float32(1.0) - np.float32(mid - start) / np.float32(end - start)
+    w_fwd = float(alpha)                                                  # e^(1 - 1) * alpha
+    w_bwd = float(np.exp(np.float32(1.0)) * (np.float32(1.0) - alpha))    # e^1 * (1 - alpha)
+    dev = image.device
+    ones = torch.ones(1, 1, H, W, dtype=torch.float32, device=dev)
+    zmax = torch.ones(1, dtype=torch.float32, device=dev)
+    acc = torch.empty(1, C + 1, H, W, dtype=torch.float32, device=dev)
+    out = torch.empty(1, C, H, W, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        s = _lib.current_stream(dev)
+        _lib.call("slr_joint_scatter_weights", _lib.ptr(image), _lib.ptr(ones), _lib.ptr(zmax), None, 0,
+                  _lib.ptr(fwd), _lib.ptr(bwd), w_fwd, w_bwd, _lib.ptr(acc), C, H, W, s)
+        _lib.call("slr_normalize", _lib.ptr(acc), _lib.ptr(out), None, C, C, C + 1, EPS, H, W, s)
+    return out

@@ -63,3 +63,8 @@ if _TESTS not in sys.path:
 @pytest.fixture(scope="session")
 def golden_euler_grad():
     return load_golden("euler_grad_ref")
+
+
+@pytest.fixture(scope="session")
+def golden_warp_flow():
+    return load_golden("warp_flow_ref")

@@ -254,6 +254,27 @@ def make_joint(rng, base, two):
     return out
 
 
+def make_warp_flow(rng, base, eul):
+    """AnimatingSoftmaxSplating.warp_flow (animating_softmax_splating.py:983-1140) imported unmodified:
+    RGB image, Z = 1, precomputed flow lists (here: the reference's own euler_integration per step)."""
+    out = {}
+    W, N = 20, 8
+    img = rng.standard_normal((1, 3, W, W)).astype(np.float32)
+    motion = motion_fields(rng, W, W)["smooth"]
+    with cpu_as_cuda(), torch.no_grad():
+        flow_f = torch.cat([eul.euler_integration(torch.from_numpy(motion), t)[0] for t in range(N + 1)], 0)
+        flow_p = torch.cat([eul.euler_integration(torch.from_numpy(-motion), t)[0] for t in range(N + 1)], 0)
+    out.update(img=img, flow_f=flow_f.numpy(), flow_p=flow_p.numpy(), N=np.int64(N))
+    for t in [0, 3, N - 2]:
+        opt = argparse.Namespace(W=W)
+        me = types.SimpleNamespace(opt=opt, softsplater=RefSplat())
+        batch = {"images": [torch.from_numpy(img)], "motions": [flow_f, flow_p], "index": torch.tensor([[0, t, N - 1]])}
+        with cpu_as_cuda(), torch.no_grad():
+            pred = base.AnimatingSoftmaxSplating.warp_flow(me, batch)
+        out[f"t{t}/PredImg"] = pred["PredImg"].numpy()
+    return out
+
+
 def main():
     assert oracle.ref_available(), "build oracle/_ref first (python oracle/build.py)"
     rng = np.random.default_rng(20261017)
@@ -261,7 +282,8 @@ def main():
     only = set(sys.argv[1:])       # e.g. `make_golden.py euler_grad_ref`: regenerate just that file
     makers = [("softsplat_ref", lambda: make_softsplat(rng)), ("euler_ref", lambda: make_euler(rng, eul)),
               ("joint_ref", lambda: make_joint(rng, base, two)),
-              ("euler_grad_ref", lambda: make_euler_grad(np.random.default_rng(20261018), eul))]
+              ("euler_grad_ref", lambda: make_euler_grad(np.random.default_rng(20261018), eul)),
+              ("warp_flow_ref", lambda: make_warp_flow(np.random.default_rng(20261019), base, eul))]
     for name, make in makers:
         if only and name not in only:
             continue

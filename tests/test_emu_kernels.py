@@ -373,3 +373,23 @@ def test_emu_staged_gather_single_stage_and_capacity_fallback(monkeypatch):
             seen.append(sc.stats["fallback"])
         assert np.array_equal(got, ldg), nbytes
     assert seen[0] <= seen[1] <= seen[2] and seen[2] > 0 and seen[0] < sc.stats["tiles"]
+
+
+def test_emu_warp_flow_twin_vs_reference_model_golden(golden_warp_flow):
+    """slr_joint_scatter_weights + slr_normalize as synthesis.warp_flow_block drives them, against the
+    reference's warp_flow (RGB, Z = 1, separate direction weights, alpha without the + 1)."""
+    g = golden_warp_flow
+    N = int(g["N"])
+    img = emu.f32(g["img"])
+    _, C, H, W = img.shape
+    ones = np.ones((1, 1, H, W), np.float32)
+    zmax = np.ones(1, np.float32)
+    for t in (0, 3, N - 2):
+        fwd, bwd = emu.f32(g["flow_f"][t]), emu.f32(g["flow_p"][N - 1 - t])
+        alpha = np.float32(1.0) - np.float32(t) / np.float32(N - 1)
+        acc = np.full((1, C + 1, H, W), np.nan, np.float32)
+        out = np.full((1, C, H, W), np.nan, np.float32)
+        emu.call("slr_joint_scatter_weights", emu.p(img), emu.p(ones), emu.p(zmax), None, 0, emu.p(fwd), emu.p(bwd),
+                 float(alpha), float(np.exp(np.float32(1.0)) * (np.float32(1.0) - alpha)), emu.p(acc), C, H, W, None)
+        emu.call("slr_normalize", emu.p(acc), emu.p(out), None, C, C, C + 1, 1e-8, H, W, None)
+        assert rel_err(out, g[f"t{t}/PredImg"]) <= TOL, t

@@ -316,3 +316,14 @@ def test_staged_gather_mode_two_layer_and_ragged(pkg, golden_joint, monkeypatch)
         alpha_fluid = aux[t:t + 1, 0:1] / torch.clamp(aux[t:t + 1, 1:2], min=1e-8)
         assert rel_err(alpha_fluid.cpu().numpy(), w_alpha) <= TOL
         assert np.mean(mask[t:t + 1].cpu().numpy() != w_mask) < 1e-4
+
+
+def test_warp_flow_twin_vs_reference_model_golden(pkg, golden_warp_flow):
+    """synthesis.warp_flow_block against AnimatingSoftmaxSplating.warp_flow (imported unmodified by
+    tests/golden/make_golden.py): animating_softmax_splating.py:1064-1138."""
+    from slr_sfs_b200.synthesis import warp_flow_block
+    g = golden_warp_flow
+    N = int(g["N"])
+    for t in (0, 3, N - 2):
+        got = warp_flow_block(cu(g["img"]), cu(g["flow_f"][t:t + 1]), cu(g["flow_p"][N - 1 - t:N - t]), (0, t, N - 1))
+        assert rel_err(got.cpu().numpy(), g[f"t{t}/PredImg"]) <= TOL, t

@@ -231,3 +231,14 @@ def test_euler_grad_matches_reference_autograd(golden_euler_grad):
         assert np.array_equal(got == 0.0, want == 0.0), key
         nonzero += int(np.any(want != 0.0))
     assert nonzero >= 30
+
+
+def test_warp_flow_block_matches_reference_model(golden_warp_flow):
+    """oracle.warp_flow_block against AnimatingSoftmaxSplating.warp_flow imported unmodified
+    (tests/golden/make_golden.py::make_warp_flow)."""
+    g = golden_warp_flow
+    N = int(g["N"])
+    for t in (0, 3, N - 2):
+        got = oracle.warp_flow_block(g["img"], g["flow_f"][t:t + 1], g["flow_p"][N - 1 - t:N - t], (0, t, N - 1),
+                                     splat=oracle.ref_softsplat_sum if oracle.ref_available() else oracle.softsplat_sum)
+        assert rel_err(got, g[f"t{t}/PredImg"]) <= 2e-6, t
