@@ -238,7 +238,11 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
     #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
         const float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
-        const float ox = __ldcs(l), oy = __ldcs(l + P);
+        const float ox = __ldcs(l);
+        // static pixels carry the marker in every frame and direction: a warp of them (about half of the
+        // warps of a scene with a still background) has nothing to bin
+        if (__all_sync(0xffffffffu, !active || ox == kStaticLand)) break;
+        const float oy = __ldcs(l + P);
         int tiles[4];
         if (active) {
             const Footprint fp = footprint_at(ox, oy, H, W);
