@@ -172,6 +172,11 @@ size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames);
  *   aux  [n_frames, n_tail + 1, H, W] or NULL: raw sums of the tail channels and
  *        the norm (the 2-layer model divides them itself, 2layers...py:1038-1045)
  *   mask [n_frames, H, W] or NULL: norm > 1e-8                      (2layers...py:1039)
+ *   nnz  [n_frames, H, W] or NULL: number of channels of `out` that are != 0 at the pixel.  The
+ *        decoder starts with mask = (x != 0) over all channels (networks/architectures.py:369) and its
+ *        first partial convolution only ever uses that mask summed over the channels and the window
+ *        (layers/partialconv2d.py:61-66): nnz is exactly the per-pixel channel sum, so neither the
+ *        per-element mask nor the all-ones mask convolution over C channels has to be materialised
  * workspace: slr_clip_workspace_bytes(H, W, n_frames) bytes, 16-byte aligned.
  * slr_clip_frames = slr_clip_plan (Euler chains, landing table, destination-tile
  * bins; depends on the motion only), slr_clip_expand (per-lane source lists of every
@@ -190,15 +195,15 @@ int slr_clip_expand(const void* scene, const float* motion, int64_t C, int n_tai
                     void* workspace, size_t workspace_bytes, slr_stream_t stream);
 int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
                     int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
-                    float* out, float* aux, float* mask,
+                    float* out, float* aux, float* mask, float* nnz,
                     const void* workspace, size_t workspace_bytes, slr_stream_t stream);
 int slr_clip_heavy(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
                    int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
-                   float* out, float* aux, float* mask,
+                   float* out, float* aux, float* mask, float* nnz,
                    const void* workspace, size_t workspace_bytes, slr_stream_t stream);
 int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tail,
                     int64_t H, int64_t W, int start, int end, int t0, int n_frames,
-                    float alpha_lo, float alpha_hi, float* out, float* aux, float* mask,
+                    float alpha_lo, float alpha_hi, float* out, float* aux, float* mask, float* nnz,
                     void* workspace, size_t workspace_bytes, slr_stream_t stream);
 
 /* Clip table: slr_clip_plan split in two, so that the part that depends on the motion only --

@@ -17,6 +17,7 @@ from . import synthesis
 from . import sharding
 from . import clip
 from . import level0
+from . import decoder_entry
 from .softsplat import (FunctionSoftsplat, ModuleSoftsplat, ModuleMaximumsplat,
                         ModuleMaximumWarpNormsplat)
 from .euler_integration_manipulator import EulerIntegration, euler_integration

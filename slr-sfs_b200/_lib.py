@@ -40,11 +40,11 @@ SIGNATURES = {
     "slr_clip_expand": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
                         _f32p, ctypes.c_size_t, _strm],
     "slr_clip_gather": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
-                        _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
+                        _f32p, _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_heavy": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
-                       _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
+                       _f32p, _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_frames": [_f32p, _f32p, _i64, _int, _i64, _i64, _int, _int, _int, _int, _flt, _flt,
-                        _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
+                        _f32p, _f32p, _f32p, _f32p, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_table_bytes": [_i64, _i64, _int],
     "slr_clip_table": [_f32p, _i64, _i64, _int, _int, _int, _int, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_bin": [_f32p, ctypes.c_size_t, _i64, _i64, _int, _int, _int, _f32p, ctypes.c_size_t, _strm],

@@ -85,6 +85,9 @@ struct GatherParams {
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
+    float* nnz;                // [frames][P] number of non-zero output channels of the pixel, or NULL: all the decoder's
+                               // per-element hole mask (x != 0, networks/architectures.py:369) contributes to its first
+                               // partial convolution's mask update (layers/partialconv2d.py:61)
     int C, groups, H, W, tiles_x, n_tiles, n_frames;
     int64_t P, cap;
     float eps;
@@ -398,6 +401,7 @@ struct RowCtx {
     float eps;
     bool in_top, in_bot;
     bool raw;             // flagged tile: write un-normalised sums, heavy_finish_kernel divides
+    bool count_nz;        // count the non-zero outputs of the lane's two pixels (GatherParams::nnz)
 };
 
 // K  = compile-time number of register-resident slots (the warp's list length rounded up);
@@ -406,7 +410,7 @@ struct RowCtx {
 template <int NT, int K, int GI>
 __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk)[kRegSlots],
                                             const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
-                                            float (&sum_t)[NT + 1], float (&sum_b)[NT + 1])
+                                            float (&sum_t)[NT + 1], float (&sum_b)[NT + 1], int (&nz)[2])
 {
     const int64_t sstride = c.P + 1;
     // scalar planes: tail channels, then the e^Z weight (the normaliser)
@@ -497,6 +501,7 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
                 if (4 * (g + gi) + j < c.C) {
                     if (c.in_top) __stcs(og + j * ostride, rt[j]);
                     if (c.in_bot) __stcs(og + j * ostride + c.W, rb[j]);
+                    if (c.count_nz) { nz[0] += rt[j] != 0.0f; nz[1] += rb[j] != 0.0f; }
                 }
             }
         }
@@ -506,11 +511,11 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
 template <int NT, int K>
 __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsigned (&pk)[kRegSlots],
                                                      const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
-                                                     float (&sum_t)[NT + 1], float (&sum_b)[NT + 1])
+                                                     float (&sum_t)[NT + 1], float (&sum_b)[NT + 1], int (&nz)[2])
 {
     constexpr int GI = K <= 2 ? 4 : K <= 6 ? 2 : 1;
-    if (c.groups % GI == 0) gather_rows<NT, K, GI>(c, pk, wt, wb, sum_t, sum_b);
-    else gather_rows<NT, K, 1>(c, pk, wt, wb, sum_t, sum_b);
+    if (c.groups % GI == 0) gather_rows<NT, K, GI>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else gather_rows<NT, K, 1>(c, pk, wt, wb, sum_t, sum_b, nz);
 }
 
 
@@ -560,13 +565,15 @@ rowgather_kernel(const GatherParams prm)
         wb[k] = __uint_as_float(e.z);
     }
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
+    int nz[2] = {0, 0};
+    c.count_nz = prm.nnz != nullptr && !c.raw;
     // the list length is warp-uniform: pick the unroll that fits
-    if (kmax <= 2) gather_rows_dispatch<NT, 2>(c, pk, wt, wb, sum_t, sum_b);
-    else if (kmax <= 4) gather_rows_dispatch<NT, 4>(c, pk, wt, wb, sum_t, sum_b);
-    else if (kmax <= 6) gather_rows_dispatch<NT, 6>(c, pk, wt, wb, sum_t, sum_b);
-    else if (kmax <= 8) gather_rows_dispatch<NT, 8>(c, pk, wt, wb, sum_t, sum_b);
-    else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b);
-    else gather_rows_dispatch<NT, 16>(c, pk, wt, wb, sum_t, sum_b);
+    if (kmax <= 2) gather_rows_dispatch<NT, 2>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 4) gather_rows_dispatch<NT, 4>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 6) gather_rows_dispatch<NT, 6>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 8) gather_rows_dispatch<NT, 8>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else gather_rows_dispatch<NT, 16>(c, pk, wt, wb, sum_t, sum_b, nz);
 
     #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -585,6 +592,7 @@ rowgather_kernel(const GatherParams prm)
             for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sum[j];
         }
         if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
+        if (prm.nnz) prm.nnz[(int64_t)f * P + px] = (float)nz[r];
     }
 }
 
@@ -630,6 +638,7 @@ struct StageCtx {
     unsigned my_bytes;        // bytes per chunk of the copies this warp issues
     float inv_t, inv_b;
     bool in_top, in_bot;
+    bool count_nz;            // count the non-zero outputs of the lane's two pixels (GatherParams::nnz)
 };
 
 // Issues this warp's share of the copies of chunk q into its stage and announces their bytes.
@@ -656,7 +665,7 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float w)
 }
 
 // normalise and store 4 channels of the lane's two pixels
-__device__ __forceinline__ void stage_store(const StageCtx& c, float* og, int ch0, const float4& at, const float4& ab)
+__device__ __forceinline__ void stage_store(const StageCtx& c, float* og, int ch0, const float4& at, const float4& ab, int (&nz)[2])
 {
     const size_t ostride = (size_t)c.P;
     const float rt[4] = {at.x * c.inv_t, at.y * c.inv_t, at.z * c.inv_t, at.w * c.inv_t};
@@ -666,6 +675,7 @@ __device__ __forceinline__ void stage_store(const StageCtx& c, float* og, int ch
         if (ch0 + j < c.C) {
             if (c.in_top) __stcs(og + j * ostride, rt[j]);
             if (c.in_bot) __stcs(og + j * ostride + c.W, rb[j]);
+            if (c.count_nz) { nz[0] += rt[j] != 0.0f; nz[1] += rb[j] != 0.0f; }
         }
     }
 }
@@ -675,7 +685,7 @@ __device__ __forceinline__ void stage_store(const StageCtx& c, float* og, int ch
 // The copies of chunk 0 were issued by the caller.
 template <int NT, int K>
 __device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&pk)[kRegSlots],
-                                           const float (&wt)[kRegSlots], const float (&wb)[kRegSlots])
+                                           const float (&wt)[kRegSlots], const float (&wb)[kRegSlots], int (&nz)[2])
 {
     const int n_stage = c.n_stage;
     const size_t ostride = (size_t)c.P;
@@ -723,7 +733,7 @@ __device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&p
                 }
                 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (q * kChunkChannels + 4 * u < c.C) stage_store(c, o + (size_t)(4 * u) * ostride, q * kChunkChannels + 4 * u, at[u], ab[u]);
+                    if (q * kChunkChannels + 4 * u < c.C) stage_store(c, o + (size_t)(4 * u) * ostride, q * kChunkChannels + 4 * u, at[u], ab[u], nz);
             } else {
                 #pragma unroll
                 for (int u = 0; u < 4; ++u) {                  // the chunk's four channel groups
@@ -742,7 +752,7 @@ __device__ __forceinline__ void stage_rows(const StageCtx& c, const unsigned (&p
                                 if (slot_role(kb + k) != kTopOnly) fma4(ab, v[k], wb[kb + k]);
                             }
                         }
-                        stage_store(c, o + (size_t)(4 * u) * ostride, ch0, at, ab);
+                        stage_store(c, o + (size_t)(4 * u) * ostride, ch0, at, ab, nz);
                     }
                 }
             }
@@ -827,13 +837,15 @@ stagegather_kernel(const GatherParams prm)
     c.inv_b = raw ? 1.0f : 1.0f / fmaxf(sum_b[NT], prm.eps);
 
     // the list length is warp-uniform: pick the unroll that fits
-    if (!active) stage_rows<NT, 0>(c, pk, wt, wb);
-    else if (kmax <= 2) stage_rows<NT, 2>(c, pk, wt, wb);
-    else if (kmax <= 4) stage_rows<NT, 4>(c, pk, wt, wb);
-    else if (kmax <= 6) stage_rows<NT, 6>(c, pk, wt, wb);
-    else if (kmax <= 8) stage_rows<NT, 8>(c, pk, wt, wb);
-    else if (kmax <= 12) stage_rows<NT, 12>(c, pk, wt, wb);
-    else stage_rows<NT, 16>(c, pk, wt, wb);
+    int nz[2] = {0, 0};
+    c.count_nz = prm.nnz != nullptr && !raw;
+    if (!active) stage_rows<NT, 0>(c, pk, wt, wb, nz);
+    else if (kmax <= 2) stage_rows<NT, 2>(c, pk, wt, wb, nz);
+    else if (kmax <= 4) stage_rows<NT, 4>(c, pk, wt, wb, nz);
+    else if (kmax <= 6) stage_rows<NT, 6>(c, pk, wt, wb, nz);
+    else if (kmax <= 8) stage_rows<NT, 8>(c, pk, wt, wb, nz);
+    else if (kmax <= 12) stage_rows<NT, 12>(c, pk, wt, wb, nz);
+    else stage_rows<NT, 16>(c, pk, wt, wb, nz);
 
     if (raw) return;                      // sums stay where they are for heavy_excess_kernel / heavy_finish_kernel
     #pragma unroll
@@ -847,6 +859,7 @@ stagegather_kernel(const GatherParams prm)
             for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sum[j];
         }
         if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
+        if (prm.nnz) prm.nnz[(int64_t)f * P + px] = (float)nz[r];
     }
 }
 
@@ -1017,6 +1030,7 @@ heavy_finish_kernel(const GatherParams prm)
         const float nrm = __ldcg(sums + (int64_t)NT * P);
         const float inv = 1.0f / fmaxf(nrm, prm.eps);
         float* out = prm.out + (int64_t)t.f * prm.C * P + t.pix;
+        int nz = 0;
         // eight independent loads in flight per thread (one load -> store chain per channel is a
         // full memory latency each: 64 of them made this kernel 33 us whatever the tile count)
         for (int c0 = 0; c0 < prm.C; c0 += 8) {
@@ -1024,9 +1038,15 @@ heavy_finish_kernel(const GatherParams prm)
             #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = c0 + j < prm.C ? __ldcg(out + (int64_t)(c0 + j) * P) : 0.0f;
             #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (c0 + j < prm.C) out[(int64_t)(c0 + j) * P] = v[j] * inv;
+            for (int j = 0; j < 8; ++j) {
+                if (c0 + j < prm.C) {
+                    const float r = v[j] * inv;
+                    out[(int64_t)(c0 + j) * P] = r;
+                    nz += r != 0.0f;
+                }
+            }
         }
+        if (prm.nnz) prm.nnz[(int64_t)t.f * P + t.pix] = (float)nz;
         if (prm.aux) {
             float* a = prm.aux + (int64_t)t.f * (NT + 1) * P + t.pix;
             #pragma unroll
@@ -1060,7 +1080,7 @@ bool gather_staged()
 // Fills the kernel parameters shared by slr_clip_expand and slr_clip_gather.
 int make_params(GatherParams& prm, const void* scene, const float* motion, int64_t C, int n_tail,
                 int64_t H, int64_t W, int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
-                float* out, float* aux, float* mask, const void* workspace, size_t workspace_bytes)
+                float* out, float* aux, float* mask, float* nnz, const void* workspace, size_t workspace_bytes)
 {
     SLR_CHECK_ARGS(scene && motion && workspace && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
                    n_tail >= 0 && n_tail <= 2 && n_frames > 0 && n_frames <= kMaxFrames &&
@@ -1084,7 +1104,7 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;
     prm.excess = ws.excess; prm.excess_count = ws.excess_count; prm.excess_cap = ws.excess_cap;
-    prm.out = out; prm.aux = aux; prm.mask = mask;
+    prm.out = out; prm.aux = aux; prm.mask = mask; prm.nnz = nnz;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = tiles_x * tiles_y; prm.n_frames = n_frames;
     prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
@@ -1139,7 +1159,7 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
 {
     GatherParams prm;
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
-                               nullptr, nullptr, nullptr, workspace, workspace_bytes);
+                               nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
     const int per_cta = prm.staged ? kStageFrames : 1;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + per_cta - 1) / per_cta);
@@ -1149,13 +1169,13 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
 
 extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
                                int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
-                               float* out, float* aux, float* mask,
+                               float* out, float* aux, float* mask, float* nnz,
                                const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(out, "slr_clip_gather: bad arguments");
     GatherParams prm;
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
-                               out, aux, mask, workspace, workspace_bytes);
+                               out, aux, mask, nnz, workspace, workspace_bytes);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream_;
     if (prm.staged) {
@@ -1176,13 +1196,13 @@ extern "C" int slr_clip_gather(const void* scene, const float* motion, int64_t C
 
 extern "C" int slr_clip_heavy(const void* scene, const float* motion, int64_t C, int n_tail, int64_t H, int64_t W,
                               int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
-                              float* out, float* aux, float* mask,
+                              float* out, float* aux, float* mask, float* nnz,
                               const void* workspace, size_t workspace_bytes, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(out, "slr_clip_heavy: bad arguments");
     GatherParams prm;
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
-                               out, aux, mask, workspace, workspace_bytes);
+                               out, aux, mask, nnz, workspace, workspace_bytes);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream_;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
@@ -1207,7 +1227,7 @@ extern "C" int slr_clip_heavy(const void* scene, const float* motion, int64_t C,
 extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tail,
                                int64_t H, int64_t W, int start, int end, int t0, int n_frames,
                                float alpha_lo, float alpha_hi,
-                               float* out, float* aux, float* mask,
+                               float* out, float* aux, float* mask, float* nnz,
                                void* workspace, size_t workspace_bytes, slr_stream_t stream_)
 {
     int rc = slr_clip_plan(motion, H, W, start, end, t0, n_frames, workspace, workspace_bytes, stream_);
@@ -1216,10 +1236,10 @@ extern "C" int slr_clip_frames(const void* scene, const float* motion, int64_t C
                          workspace, workspace_bytes, stream_);
     if (rc) return rc;
     rc = slr_clip_gather(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
-                         out, aux, mask, workspace, workspace_bytes, stream_);
+                         out, aux, mask, nnz, workspace, workspace_bytes, stream_);
     if (rc) return rc;
     return slr_clip_heavy(scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
-                          out, aux, mask, workspace, workspace_bytes, stream_);
+                          out, aux, mask, nnz, workspace, workspace_bytes, stream_);
 }
 
 extern "C" int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,

@@ -336,9 +336,10 @@ class JointSplat:
             side = st["side"] if self.pipeline else torch.cuda.current_stream(self.device)
             self._clip_table(start, end, t0, n, side)
 
-    def frames(self, start, end, t0, n, out=None, want_aux=False, want_mask=False, alpha_clamp=(0.0, 1.0)):
+    def frames(self, start, end, t0, n, out=None, want_aux=False, want_mask=False, alpha_clamp=(0.0, 1.0), want_nnz=False):
         """Frames t0..t0+n-1 of the clip [start, end]: gen_fs [n,C,H,W]
-        (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W]).  Asynchronous like any
+        (+ aux [n,n_tail+1,H,W] raw tail/norm sums, + mask [n,1,H,W], + nnz [n,1,H,W]: the number of
+        non-zero channels of gen_fs per pixel, see decoder_entry).  Asynchronous like any
         torch op: results are ordered on the current stream.
 
         The Euler chains of the requested range are integrated once (slr_clip_table, cached: see
@@ -352,6 +353,7 @@ class JointSplat:
         assert out.shape == (n, C, H, W) and out.is_contiguous() and out.device == self.device
         aux = torch.empty(n, self.n_tail + 1, H, W, dtype=torch.float32, device=self.device) if want_aux else None
         mask = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_mask else None
+        nnz = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_nnz else None
         batches = [(b0, min(self.batch, n - b0)) for b0 in range(0, n, self.batch)]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
@@ -383,7 +385,8 @@ class JointSplat:
                 for entry in ("slr_clip_gather", "slr_clip_heavy"):
                     _lib.call(entry, _lib.ptr(scene), _lib.ptr(self.motion), *args, _lib.ptr(out[b0:]),
                               None if aux is None else _lib.ptr(aux[b0:]),
-                              None if mask is None else _lib.ptr(mask[b0:]), _lib.ptr(ws), ws_bytes,
+                              None if mask is None else _lib.ptr(mask[b0:]),
+                              None if nnz is None else _lib.ptr(nnz[b0:]), _lib.ptr(ws), ws_bytes,
                               _lib.current_stream(self.device))
                 done = torch.cuda.Event()
                 done.record(main)
@@ -391,7 +394,7 @@ class JointSplat:
                 # the batch's side-stream work precedes `ready`, which main waited for: `done` covers both
                 _BufferPool.used(self._scene_entry, main, done)
                 _BufferPool.used(tb["entry"], main, done)
-        res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
+        res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ()) + ((nnz,) if want_nnz else ())
         return res if len(res) > 1 else out
 
     def frame(self, index, **kw):

@@ -92,10 +92,10 @@ def clip_table_bin_stats(be, H=40, W=72, C=6, start=1, end=12, t0=2, n_table=9, 
         be.call("slr_clip_bin", be.ptr(table), tb_bytes, H, W, n_table, b0 - t0, n, be.ptr(ws), ws_bytes, s)
         be.call("slr_clip_expand", be.ptr(scene), be.ptr(d_m), *args, be.ptr(ws), ws_bytes, s)
         for entry in ("slr_clip_gather", "slr_clip_heavy"):
-            be.call(entry, be.ptr(scene), be.ptr(d_m), *args, be.ptr(out), None, be.ptr(mask), be.ptr(ws), ws_bytes, s)
+            be.call(entry, be.ptr(scene), be.ptr(d_m), *args, be.ptr(out), None, be.ptr(mask), None, be.ptr(ws), ws_bytes, s)
         ref = be.empty(n, C, H, W)
         ws2 = be.scratch(ws_bytes)
-        be.call("slr_clip_frames", be.ptr(scene), be.ptr(d_m), *args, be.ptr(ref), None, None, be.ptr(ws2), ws_bytes, s)
+        be.call("slr_clip_frames", be.ptr(scene), be.ptr(d_m), *args, be.ptr(ref), None, None, None, be.ptr(ws2), ws_bytes, s)
         be.sync()
         got, ref = be.host(out), be.host(ref)
         assert rel_err(got, ref) <= 1e-5, (b0, n)              # same chains, continued instead of restarted
@@ -123,7 +123,7 @@ def clip_table_bin_stats(be, H=40, W=72, C=6, start=1, end=12, t0=2, n_table=9, 
     ws = be.scratch(ws_bytes)
     out = be.empty(1, C, H, W)
     be.call("slr_clip_frames", be.ptr(scene), be.ptr(d_sink), C, 0, H, W, 0, 2, 1, 1, 0.0, 1.0,
-            be.ptr(out), None, None, be.ptr(ws), ws_bytes, s)
+            be.ptr(out), None, None, None, be.ptr(ws), ws_bytes, s)
     stats = (ctypes.c_uint32 * 6)()
     be.call("slr_clip_stats_host", be.ptr(ws), ws_bytes, H, W, 1, stats, s)
     assert stats[0] >= 1 and stats[1] >= 1 and stats[2] > stats[3] == 2 * H * W and stats[5] == 5 * 3

@@ -103,11 +103,12 @@ class Scene:
         return dict(buf=buf, bytes=nb, t0=t0, n=n, start=start, end=end)
 
     def frames(self, start, end, t0, n, alpha_clamp=(0.0, 1.0), want_aux=False, want_mask=False, split=False,
-               table=None):
+               table=None, want_nnz=False):
         C, H, W = self.C, self.H, self.W
         out = np.full((n, C, H, W), np.nan, dtype=np.float32)
         aux = np.full((n, self.n_tail + 1, H, W), np.nan, dtype=np.float32) if want_aux else None
         mask = np.full((n, 1, H, W), np.nan, dtype=np.float32) if want_mask else None
+        nnz = np.full((n, 1, H, W), np.nan, dtype=np.float32) if want_nnz else None
         nb = lib().slr_clip_workspace_bytes(H, W, n)
         ws = aligned(nb)
         ws[:] = 0xA5          # the library must not rely on a zeroed workspace
@@ -120,11 +121,11 @@ class Scene:
                 call("slr_clip_plan", p(self.motion), H, W, start, end, t0, n, p(ws), nb, None)
             call("slr_clip_expand", p(self.scene), p(self.motion), *args, p(ws), nb, None)
             for entry in ("slr_clip_gather", "slr_clip_heavy"):
-                call(entry, p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)
+                call(entry, p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(nnz), p(ws), nb, None)
         else:
-            call("slr_clip_frames", p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(ws), nb, None)
+            call("slr_clip_frames", p(self.scene), p(self.motion), *args, p(out), p(aux), p(mask), p(nnz), p(ws), nb, None)
         st = (ctypes.c_uint32 * 6)()
         call("slr_clip_stats_host", p(ws), nb, H, W, n, st, None)
         self.stats = dict(flagged=st[0], full=st[1], excess=st[2], excess_cap=st[3], fallback=st[4], tiles=st[5])
-        res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ())
+        res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ()) + ((nnz,) if want_nnz else ())
         return res if len(res) > 1 else out

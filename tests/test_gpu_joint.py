@@ -262,10 +262,11 @@ def test_c_abi_clip_frames_single_call(pkg):
     ws = torch.empty((ws_bytes + 3) // 4, device="cuda")
     out = torch.empty(4, C, H, W, device="cuda")
     mask = torch.empty(4, 1, H, W, device="cuda")
+    nnz = torch.empty(4, 1, H, W, device="cuda")
     _lib.call("slr_reduce_max", _lib.ptr(Z), Z.numel(), _lib.ptr(zmax), s)
     _lib.call("slr_scene_prep", _lib.ptr(feat), _lib.ptr(Z), _lib.ptr(zmax), None, 0, _lib.ptr(scene), C, H, W, s)
     _lib.call("slr_clip_frames", _lib.ptr(scene), _lib.ptr(m), C, 0, H, W, 0, N - 1, 3, 4, 0.0, 1.0,
-              _lib.ptr(out), None, _lib.ptr(mask), _lib.ptr(ws), ws_bytes, s)
+              _lib.ptr(out), None, _lib.ptr(mask), _lib.ptr(nnz), _lib.ptr(ws), ws_bytes, s)
     torch.cuda.synchronize()
     for i, t in enumerate(range(3, 7)):
         want = oracle.joint_splat_baseline(feat.cpu().numpy(), Z.cpu().numpy(), m.cpu().numpy(), (0, t, N - 1))
@@ -274,9 +275,11 @@ def test_c_abi_clip_frames_single_call(pkg):
         # the mask is exactly the decoder's hole test (networks/architectures.py:369) on the norm
         covered = (np.abs(want).sum(1, keepdims=True) != 0)
         assert np.mean(mask[i:i + 1].cpu().numpy().astype(bool) != covered) < 1e-3
+        # nnz is exactly the channel sum of the decoder's per-element mask (x != 0) on what was written
+        assert torch.equal(nnz[i:i + 1], (out[i:i + 1] != 0).float().sum(1, keepdim=True))
     with pytest.raises(_lib.SlrError):          # workspace too small is an argument error, not a crash
         _lib.call("slr_clip_frames", _lib.ptr(scene), _lib.ptr(m), C, 0, H, W, 0, N - 1, 3, 4, 0.0, 1.0,
-                  _lib.ptr(out), None, None, _lib.ptr(ws), 1024, s)
+                  _lib.ptr(out), None, None, None, _lib.ptr(ws), 1024, s)
 
 
 @pytest.mark.parametrize("motion", ["A", "B"])
