@@ -233,6 +233,16 @@ int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, int64_t W, in
 int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,
                         uint32_t stats[6], slr_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Frame sink (after the decoder): what test_animating/test_v1_4eval_rawsize.py:240-242,284-286 does per
+ * frame on the host -- bilinear resize to the raw size (align_corners=False), (x * mul + add) * 255
+ * (mul = add = 0.5 for images in [-1, 1]; mul = 1, add = 0 for alpha maps, :245), round to nearest even,
+ * saturate to 0..255, RGB -> BGR (swap_rb) and interleave -- as one kernel: frames [n,3,H,W] fp32 ->
+ * out [n,out_H,out_W,3] uint8.  3 bytes per pixel leave the device instead of 12.
+ * ------------------------------------------------------------------------- */
+int slr_frame_sink_u8(const float* frames, uint8_t* out, int64_t n, int64_t H, int64_t W,
+                      int64_t out_H, int64_t out_W, float mul, float add, int swap_rb, slr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

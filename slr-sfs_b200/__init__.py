@@ -18,11 +18,13 @@ from . import sharding
 from . import clip
 from . import level0
 from . import decoder_entry
+from . import frame_sink
 from .softsplat import (FunctionSoftsplat, ModuleSoftsplat, ModuleMaximumsplat,
                         ModuleMaximumWarpNormsplat)
 from .euler_integration_manipulator import EulerIntegration, euler_integration
 from .synthesis import JointSplat
 from .clip import ClipRunner
+from .frame_sink import FrameSink
 
 __all__ = ["FunctionSoftsplat", "ModuleSoftsplat", "ModuleMaximumsplat", "ModuleMaximumWarpNormsplat",
            "EulerIntegration", "euler_integration", "JointSplat", "ClipRunner", "install_as_reference_modules"]

@@ -48,6 +48,7 @@ SIGNATURES = {
     "slr_clip_table_bytes": [_i64, _i64, _int],
     "slr_clip_table": [_f32p, _i64, _i64, _int, _int, _int, _int, _f32p, ctypes.c_size_t, _strm],
     "slr_clip_bin": [_f32p, ctypes.c_size_t, _i64, _i64, _int, _int, _int, _f32p, ctypes.c_size_t, _strm],
+    "slr_frame_sink_u8": [_f32p, _f32p, _i64, _i64, _i64, _i64, _i64, _flt, _flt, _int, _strm],
     "slr_clip_stats_host": [_f32p, ctypes.c_size_t, _i64, _i64, _int, ctypes.POINTER(ctypes.c_uint32), _strm],
 }
 _OTHER_RESTYPE = {"slr_last_error_string": ctypes.c_char_p, "slr_scene_bytes": ctypes.c_size_t, "slr_scene_core_bytes": ctypes.c_size_t,
@@ -114,7 +115,7 @@ KERNELS_PER_CALL = {
     "slr_softsplat_sum_fwd": 1, "slr_softsplat_grad_input": 1, "slr_softsplat_grad_flow": 1,
     "slr_maxsplat_fwd": 2, "slr_maxwarpnorm": 3, "slr_euler": 1, "slr_euler_grad_motion": 1, "slr_reduce_max": 2,
     "slr_joint_scatter": 1, "slr_joint_scatter_weights": 1, "slr_normalize": 1, "slr_scene_prep": 2, "slr_scene_quilt": 1, "slr_clip_frames": 9,
-    "slr_clip_plan": 3, "slr_clip_table": 2, "slr_clip_bin": 1, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 4,
+    "slr_clip_plan": 3, "slr_clip_table": 2, "slr_clip_bin": 1, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 4, "slr_frame_sink_u8": 1,
 }
 _launches = 0
 _timing = None          # None, or list of (name, start_event, end_event)
