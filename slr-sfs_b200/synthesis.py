@@ -119,7 +119,9 @@ def _release_all(pool, entries):
 class JointSplat:
     """Frame synthesiser for one scene: features [1,C,H,W], importance Z [1,1,H,W]
     and Eulerian motion [1,2,H,W] are fixed, frames t = start..end are produced on
-    demand.  ``z_mode``: 'max' (Z - Z.max(), :855), 'v1' (Z as is, :853).
+    demand.  ``z_mode``: 'max' (Z - Z.max(), :855), 'v1' (Z as is, :853), 'v2' (use_softmax_splatter_v2,
+    :849-851: Z - maximum_warp_norm_splater(Z, forward flow of the frame) -- the importance then depends
+    on the frame, so the scene buffer is rebuilt per frame: correct, not fast; no shipped script sets it).
 
     ``tail`` ([1,n_tail,H,W], optional) carries the 2-layer model's extra
     pre-weighted channels (a_f*e^A, e^A with use_alpha0_as_blending_weight,
@@ -151,7 +153,7 @@ class JointSplat:
         self.Z = _req(Z.detach().reshape(1, 1, self.H, self.W), "Z")
         self.tail = None if tail is None else _req(tail.detach(), "tail")
         self.n_tail = 0 if tail is None else tail.shape[1]
-        assert z_mode in ("max", "v1")
+        assert z_mode in ("max", "v1", "v2")
         self.z_mode = z_mode
         self._init_common(motion, inputs_event, scene_buffer)
 
@@ -351,6 +353,8 @@ class JointSplat:
         if out is None:
             out = torch.empty(n, C, H, W, dtype=torch.float32, device=self.device)
         assert out.shape == (n, C, H, W) and out.is_contiguous() and out.device == self.device
+        if self.z_mode == "v2":
+            return self._frames_v2(start, end, t0, n, out, want_aux, want_mask, alpha_clamp, want_nnz)
         aux = torch.empty(n, self.n_tail + 1, H, W, dtype=torch.float32, device=self.device) if want_aux else None
         mask = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_mask else None
         nnz = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_nnz else None
@@ -397,6 +401,60 @@ class JointSplat:
         res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ()) + ((nnz,) if want_nnz else ())
         return res if len(res) > 1 else out
 
+    def _z_minus_warped_max(self, steps):
+        """Z - maximum_warp_norm_splater(Z, euler_integration(motion, steps)) on the current stream
+        (animating_softmax_splating.py:849-851; softsplat.py:576-624)."""
+        H, W, dev = self.H, self.W, self.device
+        disp = torch.empty(1, 2, H, W, dtype=torch.float32, device=dev)
+        scratch = torch.empty(1, 1, H, W, dtype=torch.float32, device=dev)
+        zmax = torch.empty(1, 1, H, W, dtype=torch.float32, device=dev)
+        s = _lib.current_stream(dev)
+        _lib.call("slr_euler", _lib.ptr(self.motion), 1.0, steps, _lib.ptr(disp), None, H, W, s)
+        _lib.call("slr_maxwarpnorm", _lib.ptr(self.Z), _lib.ptr(disp), _lib.ptr(scratch), _lib.ptr(zmax), 1, 1, H, W, s)
+        return self.Z - zmax
+
+    def _frames_v2(self, start, end, t0, n, out, want_aux, want_mask, alpha_clamp, want_nnz):
+        """use_softmax_splatter_v2: the scene buffer depends on the frame (see the class docstring).
+        Frame by frame on the current stream: warped max of Z, scene prep, one-frame batch cut from
+        the shared clip table."""
+        H, W, C, dev = self.H, self.W, self.C, self.device
+        aux = torch.empty(n, self.n_tail + 1, H, W, dtype=torch.float32, device=dev) if want_aux else None
+        mask = torch.empty(n, 1, H, W, dtype=torch.float32, device=dev) if want_mask else None
+        nnz = torch.empty(n, 1, H, W, dtype=torch.float32, device=dev) if want_nnz else None
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            st = self._shared_state()
+            self._wait_inputs(main)
+            if self._scene is None:
+                nbytes = _lib.load().slr_scene_bytes(C, self.n_tail, H, W)
+                self._scene_entry = self._from_pool("scene", nbytes)
+                self._scene = self._scene_entry["buf"]
+            _BufferPool.take_over(self._scene_entry, main)
+            tb = self._clip_table(start, end, t0, n, main)
+            main.wait_event(tb["ready"])
+            ws, ws_bytes = self._scratch(st, 1, "v2", main)
+            for ev in st["free"].get("v2", ()):
+                main.wait_event(ev)
+            s = _lib.current_stream(dev)
+            for i in range(n):
+                t = t0 + i
+                z_eff = self._z_minus_warped_max(t - start)
+                _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(z_eff), None, _lib.ptr(self.tail), self.n_tail,
+                          _lib.ptr(self._scene), C, H, W, s)
+                args = (C, self.n_tail, H, W, start, end, t, 1, alpha_clamp[0], alpha_clamp[1])
+                _lib.call("slr_clip_bin", _lib.ptr(tb["buf"]), tb["bytes"], H, W, tb["n"], t - tb["t0"], 1, _lib.ptr(ws), ws_bytes, s)
+                _lib.call("slr_clip_expand", _lib.ptr(self._scene), _lib.ptr(self.motion), *args, _lib.ptr(ws), ws_bytes, s)
+                for entry in ("slr_clip_gather", "slr_clip_heavy"):
+                    _lib.call(entry, _lib.ptr(self._scene), _lib.ptr(self.motion), *args, _lib.ptr(out[i:]),
+                              None if aux is None else _lib.ptr(aux[i:]), None if mask is None else _lib.ptr(mask[i:]),
+                              None if nnz is None else _lib.ptr(nnz[i:]), _lib.ptr(ws), ws_bytes, s)
+            done = _event_now(dev)
+            st["free"]["v2"] = (done,)
+            _BufferPool.used(self._scene_entry, main, done)
+            _BufferPool.used(tb["entry"], main, done)
+        res = (out,) + ((aux,) if want_aux else ()) + ((mask,) if want_mask else ()) + ((nnz,) if want_nnz else ())
+        return res if len(res) > 1 else out
+
     def frame(self, index, **kw):
         """gen_fs [1,C,H,W] for index = (start, t, end) -- the per-frame call of the
         reference's loop (test_v1_4eval_rawsize.py:233-239)."""
@@ -422,7 +480,11 @@ class JointSplat:
             s = _lib.current_stream(dev)
             _lib.call("slr_euler", _lib.ptr(self.motion), 1.0, mid - start, _lib.ptr(disp[0]), None, H, W, s)
             _lib.call("slr_euler", _lib.ptr(self.motion), -1.0, end - mid + 1, _lib.ptr(disp[1]), None, H, W, s)
-            _lib.call("slr_joint_scatter", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self.zsub),
+            z, zsub = self.Z, self.zsub
+            if self.z_mode == "v2":
+                self._wait_inputs(torch.cuda.current_stream(dev))
+                z, zsub = self._z_minus_warped_max(mid - start), None
+            _lib.call("slr_joint_scatter", _lib.ptr(self.feat), _lib.ptr(z), _lib.ptr(zsub),
                       _lib.ptr(self.tail), self.n_tail, _lib.ptr(disp[0]), _lib.ptr(disp[1]), alpha,
                       _lib.ptr(acc), C, H, W, s)
         return acc

@@ -159,3 +159,18 @@ def test_scene_and_table_buffers_are_recycled_between_scenes(host_pkg):
     first = js._table["buf"].data_ptr()
     js.frames(0, N, 0, 2)
     assert js._table["buf"].data_ptr() == first and len(js._pooled) == 2
+
+
+def test_v2_importance_through_the_python_layer(host_pkg, golden_joint):
+    """use_softmax_splatter_v2 (Z - maximum_warp_norm_splater(Z, forward flow), animating_softmax_splating.py:849-851)
+    through JointSplat(z_mode='v2'): gather and scatter paths against the reference model's golden frames."""
+    j = golden_joint
+    N = int(j["N"])
+    js = host_pkg.JointSplat(torch.from_numpy(j["feat"]), torch.from_numpy(j["Z"]), torch.from_numpy(j["motion"]), z_mode="v2")
+    all_frames = js.frames(0, N - 1, 0, N).numpy()
+    for t in (0, 3, N - 1):
+        want = j[f"baseline/v2/t{t}/gen_fs"]
+        assert rel_err(all_frames[t:t + 1], want) <= TOL, t
+        assert rel_err(js.frame((0, t, N - 1)).numpy(), want) <= TOL, t
+        assert rel_err(js.frame_scatter((0, t, N - 1)).numpy(), want) <= TOL, t
+    assert host_pkg.calls.count("slr_clip_table") == 1 and host_pkg.calls.count("slr_maxwarpnorm") >= N

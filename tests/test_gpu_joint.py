@@ -33,7 +33,7 @@ def paths(js):
 def test_baseline_joint_vs_reference_model_golden(pkg, golden_joint):
     j = golden_joint
     N = int(j["N"])
-    for z_mode in ("max", "v1"):
+    for z_mode in ("max", "v1", "v2"):
         js = pkg.JointSplat(cu(j["feat"]), cu(j["Z"]), cu(j["motion"]), z_mode=z_mode)
         for t in (0, 3, N - 1):
             want = j[f"baseline/{z_mode}/t{t}/gen_fs"]
