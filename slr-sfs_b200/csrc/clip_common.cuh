@@ -53,7 +53,10 @@ enum SourceSet { kSetForward = 0, kSetBackward = 1, kSetSelf = 2, kSets = 3 };  
 __host__ __device__ __forceinline__ unsigned pack_xy(int x, int y) { return (unsigned)y << 16 | (unsigned)x; }
 
 // Scene buffer (slr_scene_prep), three regions:
-//   G4  [groups][P + 1] float4   channel groups of 4, pre-weighted by e^(Z - zsub); pixel P is all-zero
+//   G8  [groups8][P + 1] x 32 B  channel groups of 8, pre-weighted by e^(Z - zsub); pixel P is all-zero.  One 256-bit
+//                                load (LDG.E.256, sm_100) fetches 8 channels of a source pixel: for runs of 32 pixels
+//                                starting anywhere, L1 delivers 95 B/clk/SM that way against 63 with 128-bit loads of a
+//                                16-byte layout (profiles/microbench/ldg_width.cu)
 //   S   [n_tail + 1][P + 1] float  scalar planes (2-layer tail channels, then e^(Z - zsub))
 //   Q   [chunks][H * Wb + 1] x 128 B   the same features in chunks of 16 channels, pixel-PAIR-major: a block
 //                                holds the 2 x 4 float4 units of the horizontally adjacent pixels (2b, y) and
@@ -71,9 +74,12 @@ __host__ __device__ __forceinline__ unsigned quilt_offset(unsigned row_block, un
 }
 __host__ __device__ __forceinline__ int64_t quilt_row_blocks(int64_t W) { return (W + 1) / 2; }
 __host__ __device__ __forceinline__ int64_t quilt_plane_blocks(int64_t H, int64_t W) { return H * quilt_row_blocks(W) + 1; }
+constexpr int kGroupChannels = 8;
+constexpr int kGroupBytes = 32;                      // per pixel and group of G8
+__host__ __device__ __forceinline__ int64_t scene_groups8(int64_t C) { return (C + kGroupChannels - 1) / kGroupChannels; }
 __host__ __device__ __forceinline__ int64_t scene_core_floats(int64_t C, int n_tail, int64_t P)
 {
-    return (((C + 3) / 4) * 4 + n_tail + 1) * (P + 1);
+    return (scene_groups8(C) * kGroupChannels + n_tail + 1) * (P + 1);
 }
 __host__ __device__ __forceinline__ int64_t scene_quilt_offset_floats(int64_t C, int n_tail, int64_t P)
 {
@@ -119,16 +125,40 @@ __device__ __forceinline__ unsigned warp_reserve(unsigned* counters, int key)
 }
 
 
-// address of pixel `p` in a float4 plane: one IMAD.WIDE
-__device__ __forceinline__ const float4* px16(const char* plane, unsigned p)
+// 8 channels of a source pixel
+struct alignas(32) float8 { float4 lo, hi; };
+
+// address of pixel `p` in a plane of G8: one IMAD.WIDE
+__device__ __forceinline__ const float8* px32(const char* plane, unsigned p)
 {
 #if defined(SLR_CPU_EMULATION)      // tests/emu: the same sources compiled for the CPU
-    return reinterpret_cast<const float4*>(plane + (size_t)p * 16);
+    return reinterpret_cast<const float8*>(plane + (size_t)p * kGroupBytes);
 #else
     unsigned long long a;
-    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(a) : "r"(p), "l"(plane));
-    return reinterpret_cast<const float4*>(a);
+    asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(a) : "r"(p), "l"(plane));
+    return reinterpret_cast<const float8*>(a);
 #endif
+}
+
+// one 256-bit read-only load (LDG.E.256.CONSTANT)
+__device__ __forceinline__ float8 ldg256(const float8* p)
+{
+#if defined(SLR_CPU_EMULATION)
+    emu::check(p);
+    return *p;
+#else
+    float8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+    return r;
+#endif
+}
+
+// the 4 channels 4 * g4 .. 4 * g4 + 3 of pixel p (heavy kernels, scene_quilt: per group of FOUR)
+__device__ __forceinline__ float4 ldg_group4(const char* G, int64_t P, int g4, unsigned p)
+{
+    const char* a = G + ((size_t)(g4 >> 1) * (size_t)(P + 1) + p) * kGroupBytes + (g4 & 1) * 16;
+    return __ldg(reinterpret_cast<const float4*>(a));
 }
 
 }  // namespace slr

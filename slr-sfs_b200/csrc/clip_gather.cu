@@ -60,7 +60,7 @@ constexpr int kStageBlocks1 = kStageBytes / kBlockBytes - 1;           // one st
 constexpr int kStageBlocks2 = kStageBytes / 2 / kBlockBytes - 1;       // two stages (double buffered)
 
 struct GatherParams {
-    const char* G;             // [groups] planes of (P + 1) float4; pixel P of every plane is all-zero
+    const char* G;             // [groups] planes of (P + 1) x 32 bytes (8 channels per pixel); pixel P of every plane is all-zero
     const float* S;            // [n_tail + 1] planes of (P + 1) float (last plane = e^Z)
     const float4* ent;         // [frames][cap] bin entries
     const float* motion;       // [2][P]: a destination pixel with zero motion contributes to itself
@@ -134,6 +134,8 @@ __device__ __forceinline__ unsigned plan_key(unsigned set, unsigned xy)      // 
     return set << 30 | (xy >> 16 & 0x3fffu) << 16 | (xy & 0xffffu);
 }
 
+// STAGED: with the staging plan (stagegather_kernel follows); otherwise lists only, one frame per CTA (rowgather_kernel follows).
+template <bool STAGED>
 __global__ void __launch_bounds__(TILE, SLR_EXPAND_MINBLOCKS)
 expand_kernel(const GatherParams prm)
 {
@@ -141,7 +143,7 @@ expand_kernel(const GatherParams prm)
     __shared__ unsigned occ[kCols];                // used canonical slots (bit mask)
     __shared__ unsigned ovf[kCols];                // overflow slots in use (kCanon, kCanon + 1, ...)
     __shared__ unsigned excess_full;               // the global excess list ran out of room
-    __shared__ int row_block[kSets][kPlanRows];    // staged block of column 0 of a source row (hashed by row % kPlanRows)
+    __shared__ int row_block[STAGED ? kSets : 1][STAGED ? kPlanRows : 1];    // staged block of column 0 of a source row (hashed by row % kPlanRows)
     __shared__ int ylo[kSets], yhi[kSets];
     __shared__ unsigned stages_s;
     __shared__ unsigned warp_bytes[8];             // bytes per chunk of the copies warp w of stagegather_kernel will issue
@@ -151,7 +153,7 @@ expand_kernel(const GatherParams prm)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // staged: a CTA plans and expands the kStageFrames frames that share a staged region; otherwise one frame per CTA
-    const int per_cta = prm.staged ? kStageFrames : 1;
+    constexpr int per_cta = STAGED ? kStageFrames : 1;
     const int n_fg = (prm.n_frames + per_cta - 1) / per_cta;
     const int fg = (int)(blockIdx.x % (unsigned)n_fg), tile = (int)(blockIdx.x / (unsigned)n_fg);
     const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
@@ -162,7 +164,7 @@ expand_kernel(const GatherParams prm)
     const bool still = inside && __ldg(prm.motion + pix) == 0.0f && __ldg(prm.motion + P + pix) == 0.0f;
 
     unsigned stages = 0u;
-    if (prm.staged) {
+    if (STAGED) {
         for (int i = tid; i < kSets * kPlanRows; i += TILE) { xlo[i] = 0x7fffffff; xhi[i] = -1; }
         if (tid < kSets) { ylo[tid] = 0x7fffffff; yhi[tid] = -1; }
         if (tid < 8) warp_bytes[tid] = 0u;
@@ -249,7 +251,7 @@ expand_kernel(const GatherParams prm)
     }
     // the source field of a list entry: staged byte offset, or global pixel | set
     auto source_field = [&](unsigned set, unsigned p, unsigned xy) -> unsigned {
-        if (stages == 0u) return p | set << kSetShift;
+        if (!STAGED || stages == 0u) return p | set << kSetShift;
         return quilt_offset((unsigned)row_block[set][xy >> 16 & (kPlanRows - 1)], xy & 0xffffu);
     };
     // unused slots: the all-zero pixel, weights 0 (its (row, column) = (H, 0) is pixel P of the scalar planes)
@@ -327,7 +329,7 @@ expand_kernel(const GatherParams prm)
         const unsigned flag = excess_full ? 2u : (any_deep ? 1u : 0u);
         if (tid == 0) {
             prm.tile_flag[(int64_t)f * prm.n_tiles + tile] = flag;
-            prm.fallback[(int64_t)f * prm.n_tiles + tile] = prm.staged && stages == 0u ? 1u : 0u;
+            prm.fallback[(int64_t)f * prm.n_tiles + tile] = STAGED && stages == 0u ? 1u : 0u;
             if (flag) prm.flag_list[atomicAdd(prm.flag_count, 1u)] = (unsigned)(tile * prm.n_frames + f);
         }
         if (flag != 2u && tid < kCols) {
@@ -343,7 +345,7 @@ expand_kernel(const GatherParams prm)
             // normaliser e^Z) of this lane's two pixels: same products in the same order as rowgather_kernel
             float st[3] = {0.0f, 0.0f, 0.0f}, sb[3] = {0.0f, 0.0f, 0.0f};
             const int64_t sstride = P + 1;
-            const bool want_sums = stages != 0u;        // stagegather_kernel reads them; rowgather_kernel sums for itself
+            const bool want_sums = STAGED && stages != 0u;        // stagegather_kernel reads them; rowgather_kernel sums for itself
             auto scalars = [&](const uint4& e, int k) {
                 if (!want_sums) return;
                 const unsigned p = (e.w >> 16) * (unsigned)prm.W + (e.w & 0xffffu);
@@ -391,6 +393,11 @@ expand_kernel(const GatherParams prm)
 // only by the frame-to-frame displacement, so a source line is fetched from HBM once per batch
 // and the other frames hit it in L2 (one frame's features alone, 204 MB, exceed the 126 MB L2).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void fma4(float4& a, const float4& v, float w)
+{
+    a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
+}
+
 struct RowCtx {
     const char* G;        // group plane 0
     const float* S;       // scalar plane 0
@@ -401,13 +408,13 @@ struct RowCtx {
     float eps;
     bool in_top, in_bot;
     bool raw;             // flagged tile: write un-normalised sums, heavy_finish_kernel divides
-    bool count_nz;        // count the non-zero outputs of the lane's two pixels (GatherParams::nnz)
 };
 
 // K  = compile-time number of register-resident slots (the warp's list length rounded up);
-// GI = channel groups per iteration: K * GI <= 12 independent LDG.128 are issued before the
-//      first FMA that consumes them (a warp pays one full memory latency per iteration).
-template <int NT, int K, int GI>
+// GI = groups of 8 channels per iteration.  Per batch at most 6 independent 256-bit loads (6 KB per warp) are
+//      issued before the first FMA that consumes them (a warp pays one full memory latency per batch).
+// NZ = count the non-zero outputs (GatherParams::nnz).
+template <int NT, int K, int GI, bool NZ>
 __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk)[kRegSlots],
                                             const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
                                             float (&sum_t)[NT + 1], float (&sum_b)[NT + 1], int (&nz)[2])
@@ -445,38 +452,31 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
     const float inv_b = c.raw ? 1.0f : 1.0f / fmaxf(sum_b[NT], c.eps);
 
     const char* Gg = c.G;
-    const size_t gstride = (size_t)(c.P + 1) * 16;
+    const size_t gstride = (size_t)(c.P + 1) * kGroupBytes;
     const size_t ostride = (size_t)c.P;
     float* o = c.out_top;
-    for (int g = 0; g < c.groups; g += GI, Gg += GI * gstride, o += 4 * GI * ostride) {
-        constexpr int B = K <= 12 ? K : K / 2;       // the deepest bucket loads in two halves
-        float4 at[GI], ab[GI];
+    for (int g = 0; g < c.groups; g += GI, Gg += GI * gstride, o += kGroupChannels * GI * ostride) {
+        constexpr int B = K * GI <= 6 ? K : (K <= 6 ? K : (K == 8 || K == 16 ? 4 : 6));     // loads per batch and group
+        float8 at[GI], ab[GI];
         #pragma unroll
-        for (int gi = 0; gi < GI; ++gi) at[gi] = ab[gi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int gi = 0; gi < GI; ++gi) {
+            at[gi].lo = at[gi].hi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            ab[gi] = at[gi];
+        }
         #pragma unroll
         for (int kb = 0; kb < K; kb += B) {
-            float4 v[GI][B];
+            float8 v[GI][B];
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
-                for (int k = 0; k < B; ++k) v[gi][k] = __ldg(px16(Gg + gi * gstride, pk[kb + k]));
+                for (int k = 0; k < B; ++k) v[gi][k] = ldg256(px32(Gg + gi * gstride, pk[kb + k]));
             }
             #pragma unroll
             for (int gi = 0; gi < GI; ++gi) {
                 #pragma unroll
                 for (int k = 0; k < B; ++k) {
-                    if (slot_role(kb + k) != kBottomOnly) {
-                        at[gi].x = fmaf(v[gi][k].x, wt[kb + k], at[gi].x);
-                        at[gi].y = fmaf(v[gi][k].y, wt[kb + k], at[gi].y);
-                        at[gi].z = fmaf(v[gi][k].z, wt[kb + k], at[gi].z);
-                        at[gi].w = fmaf(v[gi][k].w, wt[kb + k], at[gi].w);
-                    }
-                    if (slot_role(kb + k) != kTopOnly) {
-                        ab[gi].x = fmaf(v[gi][k].x, wb[kb + k], ab[gi].x);
-                        ab[gi].y = fmaf(v[gi][k].y, wb[kb + k], ab[gi].y);
-                        ab[gi].z = fmaf(v[gi][k].z, wb[kb + k], ab[gi].z);
-                        ab[gi].w = fmaf(v[gi][k].w, wb[kb + k], ab[gi].w);
-                    }
+                    if (slot_role(kb + k) != kBottomOnly) { fma4(at[gi].lo, v[gi][k].lo, wt[kb + k]); fma4(at[gi].hi, v[gi][k].hi, wt[kb + k]); }
+                    if (slot_role(kb + k) != kTopOnly) { fma4(ab[gi].lo, v[gi][k].lo, wb[kb + k]); fma4(ab[gi].hi, v[gi][k].hi, wb[kb + k]); }
                 }
             }
         }
@@ -485,37 +485,37 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
             if (K == kRegSlots) {
                 for (int k = kRegSlots; k < c.kmax; ++k) {
                     const uint4 e = __ldcg(c.list + k * 32);
-                    const float4 t = __ldg(px16(Gg + gi * gstride, e.x & kPixelMask));
+                    const float8 t = ldg256(px32(Gg + gi * gstride, e.x & kPixelMask));
                     const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
-                    at[gi].x = fmaf(t.x, w0, at[gi].x); at[gi].y = fmaf(t.y, w0, at[gi].y);
-                    at[gi].z = fmaf(t.z, w0, at[gi].z); at[gi].w = fmaf(t.w, w0, at[gi].w);
-                    ab[gi].x = fmaf(t.x, w1, ab[gi].x); ab[gi].y = fmaf(t.y, w1, ab[gi].y);
-                    ab[gi].z = fmaf(t.z, w1, ab[gi].z); ab[gi].w = fmaf(t.w, w1, ab[gi].w);
+                    fma4(at[gi].lo, t.lo, w0); fma4(at[gi].hi, t.hi, w0);
+                    fma4(ab[gi].lo, t.lo, w1); fma4(ab[gi].hi, t.hi, w1);
                 }
             }
-            float* og = o + 4 * gi * ostride;
-            const float rt[4] = {at[gi].x * inv_t, at[gi].y * inv_t, at[gi].z * inv_t, at[gi].w * inv_t};
-            const float rb[4] = {ab[gi].x * inv_b, ab[gi].y * inv_b, ab[gi].z * inv_b, ab[gi].w * inv_b};
+            float* og = o + kGroupChannels * gi * ostride;
+            const float rt[8] = {at[gi].lo.x * inv_t, at[gi].lo.y * inv_t, at[gi].lo.z * inv_t, at[gi].lo.w * inv_t,
+                                 at[gi].hi.x * inv_t, at[gi].hi.y * inv_t, at[gi].hi.z * inv_t, at[gi].hi.w * inv_t};
+            const float rb[8] = {ab[gi].lo.x * inv_b, ab[gi].lo.y * inv_b, ab[gi].lo.z * inv_b, ab[gi].lo.w * inv_b,
+                                 ab[gi].hi.x * inv_b, ab[gi].hi.y * inv_b, ab[gi].hi.z * inv_b, ab[gi].hi.w * inv_b};
             #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (4 * (g + gi) + j < c.C) {
+            for (int j = 0; j < 8; ++j) {
+                if (kGroupChannels * (g + gi) + j < c.C) {
                     if (c.in_top) __stcs(og + j * ostride, rt[j]);
                     if (c.in_bot) __stcs(og + j * ostride + c.W, rb[j]);
-                    if (c.count_nz) { nz[0] += rt[j] != 0.0f; nz[1] += rb[j] != 0.0f; }
+                    if (NZ) { nz[0] += rt[j] != 0.0f; nz[1] += rb[j] != 0.0f; }
                 }
             }
         }
     }
 }
 
-template <int NT, int K>
+template <int NT, int K, bool NZ>
 __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsigned (&pk)[kRegSlots],
                                                      const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
                                                      float (&sum_t)[NT + 1], float (&sum_b)[NT + 1], int (&nz)[2])
 {
-    constexpr int GI = K <= 2 ? 4 : K <= 6 ? 2 : 1;
-    if (c.groups % GI == 0) gather_rows<NT, K, GI>(c, pk, wt, wb, sum_t, sum_b, nz);
-    else gather_rows<NT, K, 1>(c, pk, wt, wb, sum_t, sum_b, nz);
+    constexpr int GI = K <= 2 ? 2 : 1;
+    if (c.groups % GI == 0) gather_rows<NT, K, GI, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else gather_rows<NT, K, 1, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
 }
 
 
@@ -523,7 +523,7 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
 // the SAME tile in consecutive frames read source regions that differ only by one frame's
 // displacement, so with F > 1 they share most of their lines in this SM's L1 as well (the
 // frame-fastest CTA order already shares them in L2).  R < 4 splits a tile's row pairs over CTAs.
-template <int NT, int F, int R>
+template <int NT, int F, int R, bool NZ>
 __global__ void __launch_bounds__(32 * F * R, (SLR_GATHER_MINBLOCKS * kCols) / (32 * F * R))
 rowgather_kernel(const GatherParams prm)
 {
@@ -566,14 +566,13 @@ rowgather_kernel(const GatherParams prm)
     }
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
     int nz[2] = {0, 0};
-    c.count_nz = prm.nnz != nullptr && !c.raw;
     // the list length is warp-uniform: pick the unroll that fits
-    if (kmax <= 2) gather_rows_dispatch<NT, 2>(c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 4) gather_rows_dispatch<NT, 4>(c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 6) gather_rows_dispatch<NT, 6>(c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 8) gather_rows_dispatch<NT, 8>(c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 12) gather_rows_dispatch<NT, 12>(c, pk, wt, wb, sum_t, sum_b, nz);
-    else gather_rows_dispatch<NT, 16>(c, pk, wt, wb, sum_t, sum_b, nz);
+    if (kmax <= 2) gather_rows_dispatch<NT, 2, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 4) gather_rows_dispatch<NT, 4, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 6) gather_rows_dispatch<NT, 6, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 8) gather_rows_dispatch<NT, 8, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 12) gather_rows_dispatch<NT, 12, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else gather_rows_dispatch<NT, 16, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
 
     #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -592,7 +591,7 @@ rowgather_kernel(const GatherParams prm)
             for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = sum[j];
         }
         if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
-        if (prm.nnz) prm.nnz[(int64_t)f * P + px] = (float)nz[r];
+        if (NZ) prm.nnz[(int64_t)f * P + px] = (float)nz[r];
     }
 }
 
@@ -657,11 +656,6 @@ __device__ __forceinline__ void stage_issue(const StageCtx& c, int q)
         }
     }
     __syncwarp();
-}
-
-__device__ __forceinline__ void fma4(float4& a, const float4& v, float w)
-{
-    a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
 }
 
 // normalise and store 4 channels of the lane's two pixels
@@ -918,9 +912,8 @@ heavy_scatter_kernel(const GatherParams prm)
     const int tid = threadIdx.x;
     const int64_t P = prm.P;
     const int64_t sstride = P + 1;
-    const size_t gstride = (size_t)(P + 1) * 16;
     // chunk 0 = the scalar planes (tail..., e^Z); chunk c > 0 = channel groups [(c-1)*kHeavyGroups, ...)
-    const unsigned n_chunks = 1u + (unsigned)((prm.groups + kHeavyGroups - 1) / kHeavyGroups);
+    const unsigned n_chunks = 1u + (unsigned)((2 * prm.groups + kHeavyGroups - 1) / kHeavyGroups);
     const unsigned n_work = *prm.flag_count * n_chunks;
     for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         const unsigned item = prm.flag_list[wi / n_chunks];
@@ -935,8 +928,8 @@ heavy_scatter_kernel(const GatherParams prm)
         const bool self_static = t.inframe && __ldg(prm.motion + t.pix) == 0.0f && __ldg(prm.motion + P + t.pix) == 0.0f;
         float* out = prm.out + (int64_t)t.f * prm.C * P;
         float* sums = prm.heavy_sums + (int64_t)t.f * 3 * P;
-        const int g_lo = (chunk - 1) * kHeavyGroups, g_hi = min(prm.groups, g_lo + kHeavyGroups);
-        const char* Gg = prm.G + (size_t)max(g_lo, 0) * gstride;
+        const int groups4 = 2 * prm.groups;           // groups of four channels
+        const int g_lo = (chunk - 1) * kHeavyGroups, g_hi = min(groups4, g_lo + kHeavyGroups);
 
         // one (destination pixel, source pixel, weight) pair
         auto add_pair = [&](int64_t dpix, unsigned p, float w) {
@@ -948,7 +941,7 @@ heavy_scatter_kernel(const GatherParams prm)
                 float4 v[kHeavyGroups];
                 #pragma unroll
                 for (int gi = 0; gi < kHeavyGroups; ++gi)
-                    v[gi] = g_lo + gi < g_hi ? __ldg(px16(Gg + gi * gstride, p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[gi] = g_lo + gi < g_hi ? ldg_group4(prm.G, P, g_lo + gi, p) : make_float4(0.f, 0.f, 0.f, 0.f);
                 #pragma unroll
                 for (int gi = 0; gi < kHeavyGroups; ++gi) {
                     const float r[4] = {v[gi].x * w, v[gi].y * w, v[gi].z * w, v[gi].w * w};
@@ -987,7 +980,6 @@ heavy_excess_kernel(const GatherParams prm)
 {
     const int64_t P = prm.P;
     const int64_t sstride = P + 1;
-    const size_t gstride = (size_t)(P + 1) * 16;
     const unsigned n = min(*prm.excess_count, prm.excess_cap);
     for (unsigned i = blockIdx.x * TILE + threadIdx.x; i < n; i += gridDim.x * TILE) {
         const uint4 e = __ldcg(prm.excess + i);
@@ -1000,12 +992,11 @@ heavy_excess_kernel(const GatherParams prm)
         #pragma unroll
         for (int j = 0; j <= NT; ++j) red_add(sums + (int64_t)j * P, __ldg(prm.S + (int64_t)j * sstride + e.y) * w);
         float* out = prm.out + (int64_t)f * prm.C * P + dpix;
-        const char* Gg = prm.G;
-        for (int g0 = 0; g0 < prm.groups; g0 += 4, Gg += 4 * gstride) {     // four loads in flight per thread
+        for (int g0 = 0; g0 < 2 * prm.groups; g0 += 4) {     // groups of four channels, four loads in flight per thread
             float4 v[4];
             #pragma unroll
             for (int gi = 0; gi < 4; ++gi)
-                v[gi] = g0 + gi < prm.groups ? __ldg(px16(Gg + gi * gstride, e.y)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[gi] = g0 + gi < 2 * prm.groups ? ldg_group4(prm.G, P, g0 + gi, e.y) : make_float4(0.f, 0.f, 0.f, 0.f);
             #pragma unroll
             for (int gi = 0; gi < 4; ++gi) {
                 const float r[4] = {v[gi].x * w, v[gi].y * w, v[gi].z * w, v[gi].w * w};
@@ -1090,9 +1081,9 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
     const Workspace ws = carve(const_cast<void*>(workspace), H, W, n_frames);
     SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "workspace too small (see slr_clip_workspace_bytes)");
-    const int groups = (int)((C + 3) / 4);
+    const int groups = (int)scene_groups8(C);
     prm.G = (const char*)scene;
-    prm.S = (const float*)scene + (int64_t)groups * 4 * (P + 1);
+    prm.S = (const float*)scene + (int64_t)groups * kGroupChannels * (P + 1);
     prm.Q = (const char*)((const float*)scene + scene_quilt_offset_floats(C, n_tail, P));
     prm.fallback = ws.fallback;
     prm.only_fallback = 0;
@@ -1142,13 +1133,20 @@ void launch_stagegather(const GatherParams& prm, unsigned grid, cudaStream_t s)
     stagegather_kernel<NT><<<grid, kStageThreads, kStageBytes, s>>>(prm);
 }
 
+template <int F, int R, bool NZ>
+void launch_rowgather_nz(const GatherParams& prm, int n_tail, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)(kPairsPerTile / R) * (unsigned)((prm.n_frames + F - 1) / F);
+    if (n_tail == 0) rowgather_kernel<0, F, R, NZ><<<grid, 32 * F * R, 0, s>>>(prm);
+    else if (n_tail == 1) rowgather_kernel<1, F, R, NZ><<<grid, 32 * F * R, 0, s>>>(prm);
+    else rowgather_kernel<2, F, R, NZ><<<grid, 32 * F * R, 0, s>>>(prm);
+}
+
 template <int F, int R>
 void launch_rowgather(const GatherParams& prm, int n_tail, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)prm.n_tiles * (unsigned)(kPairsPerTile / R) * (unsigned)((prm.n_frames + F - 1) / F);
-    if (n_tail == 0) rowgather_kernel<0, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
-    else if (n_tail == 1) rowgather_kernel<1, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
-    else rowgather_kernel<2, F, R><<<grid, 32 * F * R, 0, s>>>(prm);
+    if (prm.nnz) launch_rowgather_nz<F, R, true>(prm, n_tail, s);
+    else launch_rowgather_nz<F, R, false>(prm, n_tail, s);
 }
 
 }  // namespace
@@ -1163,7 +1161,8 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
     if (rc) return rc;
     const int per_cta = prm.staged ? kStageFrames : 1;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + per_cta - 1) / per_cta);
-    expand_kernel<<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    if (prm.staged) expand_kernel<true><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
+    else expand_kernel<false><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
     return SLR_LAUNCH_STATUS();
 }
 

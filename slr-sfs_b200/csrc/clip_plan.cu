@@ -1,7 +1,7 @@
 // Clip pipeline, part 1: everything that depends on the scene or on the motion only.
 //
-//   scene_prep      once per scene: G4[g][p] = feat[4g..4g+3][p] * e^(Z[p]-zsub) as float4
-//                   (one 16-byte load later fetches 4 channels of a source pixel),
+//   scene_prep      once per scene: G8[g][p] = feat[8g..8g+7][p] * e^(Z[p]-zsub), 32 bytes
+//                   (one 256-bit load later fetches 8 channels of a source pixel),
 //                   S[j][p] = scalar planes (2-layer tail channels, e^Z).
 //   euler_table     once per batch of frames: both Euler chains in registers, landing
 //                   coordinates of every (frame, direction, pixel), and per-(frame,
@@ -23,32 +23,35 @@ namespace slr {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, const float* __restrict__ zsub,
-                  const float* __restrict__ tail, int n_tail, float4* __restrict__ G4, float* __restrict__ S,
+                  const float* __restrict__ tail, int n_tail, float8* __restrict__ G8, float* __restrict__ S,
                   int C, int64_t P)
 {
     // planes have stride P + 1: pixel P is the all-zero pixel unused gather slots read
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p > P) return;
+    const int groups = (int)scene_groups8(C);
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (p == P) {
-        const int groups = (C + 3) >> 2;
         if (blockIdx.y == 0) {
-            for (int g = 0; g < groups; ++g) G4[(int64_t)g * (P + 1) + P] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int g = 0; g < groups; ++g) { float8 v; v.lo = zero4; v.hi = zero4; G8[(int64_t)g * (P + 1) + P] = v; }
             for (int j = 0; j <= n_tail; ++j) S[(int64_t)j * (P + 1) + P] = 0.0f;
         }
         return;
     }
     const float ez = expf(z[p] - (zsub ? *zsub : 0.0f));
-    const int groups = (C + 3) >> 2;
     const int g0 = blockIdx.y * ((groups + gridDim.y - 1) / gridDim.y);
     const int g1 = min(groups, g0 + (groups + (int)gridDim.y - 1) / (int)gridDim.y);
     for (int g = g0; g < g1; ++g) {
-        float v[4];
+        float v[8];
         #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = 4 * g + j;
+        for (int j = 0; j < 8; ++j) {
+            const int c = 8 * g + j;
             v[j] = c < C ? feat[(int64_t)c * P + p] * ez : 0.0f;
         }
-        G4[(int64_t)g * (P + 1) + p] = make_float4(v[0], v[1], v[2], v[3]);
+        float8 o;
+        o.lo = make_float4(v[0], v[1], v[2], v[3]);
+        o.hi = make_float4(v[4], v[5], v[6], v[7]);
+        G8[(int64_t)g * (P + 1) + p] = o;
     }
     if (blockIdx.y == 0) {
         for (int j = 0; j < n_tail; ++j) S[(int64_t)j * (P + 1) + p] = tail[(int64_t)j * P + p];
@@ -63,7 +66,7 @@ scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, c
 // only those) can derive Q locally.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-scene_quilt_kernel(const float4* __restrict__ G4, float4* __restrict__ Q, int groups, int H, int W, int64_t P)
+scene_quilt_kernel(const char* __restrict__ G, float4* __restrict__ Q, int groups4, int H, int W, int64_t P)
 {
     // one thread per (pixel column slot of a block row, chunk): x runs over 2 * Wb columns (the last may be padding)
     const int Wb = (int)quilt_row_blocks(W);
@@ -83,7 +86,7 @@ scene_quilt_kernel(const float4* __restrict__ G4, float4* __restrict__ Q, int gr
     #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int g = 4 * q + u;
-        block[slot ^ (unsigned)u] = g < groups ? __ldg(G4 + (int64_t)g * (P + 1) + p) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        block[slot ^ (unsigned)u] = g < groups4 ? ldg_group4(G, P, g, (unsigned)p) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -293,13 +296,13 @@ extern "C" size_t slr_scene_bytes(int64_t C, int n_tail, int64_t H, int64_t W)
 extern "C" int slr_scene_quilt(void* scene, int64_t C, int n_tail, int64_t H, int64_t W, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) && n_tail >= 0 && n_tail <= 2 &&
-                   ((uintptr_t)scene & 15) == 0, "slr_scene_quilt: bad arguments");
+                   ((uintptr_t)scene & 31) == 0, "slr_scene_quilt: bad arguments");
     const int64_t P = H * W;
-    const int groups = (int)((C + 3) / 4);
+    const int groups = (int)(scene_groups8(C) * 2);          // groups of four channels held by the G8 region
     float4* Q = (float4*)((float*)scene + scene_quilt_offset_floats(C, n_tail, P));
     const int64_t n = H * quilt_row_blocks(W) * 2 + 8;
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)scene_chunks(C), 1);
-    scene_quilt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float4*)scene, Q, groups, (int)H, (int)W, P);
+    scene_quilt_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const char*)scene, Q, groups, (int)H, (int)W, P);
     return SLR_LAUNCH_STATUS();
 }
 
@@ -308,14 +311,14 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
                               int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
 {
     SLR_CHECK_ARGS(feat && z && scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
-                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 15) == 0,
+                   n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 31) == 0,
                    "slr_scene_prep: bad arguments");
     const int64_t P = H * W;
-    const int groups = (int)((C + 3) / 4);
-    float4* G4 = (float4*)scene;
-    float* S = (float*)scene + (int64_t)groups * 4 * (P + 1);
+    const int groups = (int)scene_groups8(C);
+    float8* G8 = (float8*)scene;
+    float* S = (float*)scene + (int64_t)groups * kGroupChannels * (P + 1);
     dim3 grid((unsigned)((P + 1 + 255) / 256), (unsigned)std::min(groups, 4), 1);
-    scene_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(feat, z, zsub, tail, n_tail, G4, S, (int)C, P);
+    scene_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(feat, z, zsub, tail, n_tail, G8, S, (int)C, P);
     const int rc = SLR_LAUNCH_STATUS();
     if (rc) return rc;
     return slr_scene_quilt(scene, C, n_tail, H, W, stream_);
