@@ -114,7 +114,7 @@ def current_stream(device):
 KERNELS_PER_CALL = {
     "slr_softsplat_sum_fwd": 1, "slr_softsplat_grad_input": 1, "slr_softsplat_grad_flow": 1,
     "slr_maxsplat_fwd": 2, "slr_maxwarpnorm": 3, "slr_euler": 1, "slr_euler_grad_motion": 1, "slr_reduce_max": 2,
-    "slr_joint_scatter": 1, "slr_joint_scatter_weights": 1, "slr_normalize": 1, "slr_scene_prep": 2, "slr_scene_quilt": 1, "slr_clip_frames": 9,
+    "slr_joint_scatter": 1, "slr_joint_scatter_weights": 1, "slr_normalize": 1, "slr_scene_prep": 1, "slr_scene_quilt": 1, "slr_clip_frames": 9,
     "slr_clip_plan": 3, "slr_clip_table": 2, "slr_clip_bin": 1, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 4, "slr_frame_sink_u8": 1,
 }
 _launches = 0

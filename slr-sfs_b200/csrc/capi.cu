@@ -1,4 +1,5 @@
 // Library-wide pieces of the C ABI: version, error text, device properties.
+#include <stdlib.h>
 #include <string.h>
 
 #include "slr_host.h"
@@ -27,6 +28,12 @@ int sm_count()
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+bool gather_staged()
+{
+    const char* e = getenv("SLR_GATHER_MODE");
+    return e && strcmp(e, "staged") == 0;
 }
 
 }  // namespace slr_host

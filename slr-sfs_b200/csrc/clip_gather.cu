@@ -398,6 +398,19 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float w)
     a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
 }
 
+#ifndef SLR_GATHER_LOADS
+#define SLR_GATHER_LOADS 6             // 256-bit loads a warp has in flight per batch (6 KB); measured: profiles/r02
+#endif
+constexpr int kGatherLoads = SLR_GATHER_LOADS;
+// largest divisor B of K with B * GI <= kGatherLoads
+__host__ __device__ constexpr int batch_slots(int K, int GI)
+{
+    int best = 1;
+    for (int b = 1; b <= K; ++b)
+        if (K % b == 0 && b * GI <= kGatherLoads) best = b;
+    return best;
+}
+
 struct RowCtx {
     const char* G;        // group plane 0
     const float* S;       // scalar plane 0
@@ -456,7 +469,7 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
     const size_t ostride = (size_t)c.P;
     float* o = c.out_top;
     for (int g = 0; g < c.groups; g += GI, Gg += GI * gstride, o += kGroupChannels * GI * ostride) {
-        constexpr int B = K * GI <= 6 ? K : (K <= 6 ? K : (K == 8 || K == 16 ? 4 : 6));     // loads per batch and group
+        constexpr int B = batch_slots(K, GI);        // slots per batch: B * GI loads in flight
         float8 at[GI], ab[GI];
         #pragma unroll
         for (int gi = 0; gi < GI; ++gi) {
@@ -513,7 +526,7 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
                                                      const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
                                                      float (&sum_t)[NT + 1], float (&sum_b)[NT + 1], int (&nz)[2])
 {
-    constexpr int GI = K <= 2 ? 2 : 1;
+    constexpr int GI = K * 2 <= kGatherLoads ? 2 : 1;
     if (c.groups % GI == 0) gather_rows<NT, K, GI, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
     else gather_rows<NT, K, 1, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
 }
@@ -1058,16 +1071,6 @@ using slr_host::Workspace;
 
 namespace {
 
-// Which gather runs: "ldg" (default) = rowgather_kernel for every tile; "staged" = stagegather_kernel (sources staged in
-// shared memory by the TMA unit) with rowgather_kernel for the tiles that do not fit.  Measured on B200 at
-// 768x1024x64, motion A (profiles/r02): the staged gather's main loop is ~30 % faster, but the staging plan (in
-// expand_kernel), the copy issue and the per-chunk synchronisation cost more than that saves; see DESIGN.md 4.2.
-bool gather_staged()
-{
-    const char* e = getenv("SLR_GATHER_MODE");
-    return e && strcmp(e, "staged") == 0;
-}
-
 // Fills the kernel parameters shared by slr_clip_expand and slr_clip_gather.
 int make_params(GatherParams& prm, const void* scene, const float* motion, int64_t C, int n_tail,
                 int64_t H, int64_t W, int start, int end, int t0, int n_frames, float alpha_lo, float alpha_hi,
@@ -1090,7 +1093,7 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     prm.records = ws.records;
     prm.n_tail = n_tail;
     // the plan packs a source row into 14 bits and a column into 16 (plan_key)
-    prm.staged = gather_staged() && H <= 16384 && W <= 65535 ? 1 : 0;
+    prm.staged = slr_host::gather_staged() && H <= 16384 && W <= 65535 ? 1 : 0;
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;

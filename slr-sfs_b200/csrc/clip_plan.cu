@@ -320,7 +320,7 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
     dim3 grid((unsigned)((P + 1 + 255) / 256), (unsigned)std::min(groups, 4), 1);
     scene_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(feat, z, zsub, tail, n_tail, G8, S, (int)C, P);
     const int rc = SLR_LAUNCH_STATUS();
-    if (rc) return rc;
+    if (rc || !slr_host::gather_staged()) return rc;      // only the staged gather reads the quilted copy
     return slr_scene_quilt(scene, C, n_tail, H, W, stream_);
 }
 

@@ -10,6 +10,12 @@ namespace slr_host {
 int fail(int code, const char* msg);
 // SM count of the current device (cached per device).
 int sm_count();
+// Which gather runs (environment variable SLR_GATHER_MODE, read at every call): "ldg" (default) = rowgather_kernel
+// for every tile; "staged" = stagegather_kernel (sources staged in shared memory by the TMA unit) with
+// rowgather_kernel for the tiles that do not fit.  Measured on B200 at 768x1024x64, motion A (profiles/r02): the
+// staged gather's main loop is ~30 % faster, but the staging plan (in expand_kernel), the copy issue and the
+// per-chunk synchronisation cost more than that saves; see DESIGN.md 4.2.
+bool gather_staged();
 }  // namespace slr_host
 
 #define SLR_CHECK_ARGS(cond, msg) \

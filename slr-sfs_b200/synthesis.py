@@ -246,7 +246,8 @@ class JointSplat:
                     self._wait_inputs(cur)
                     _BufferPool.take_over(self._scene_entry, cur)
                     if self.feat is None:       # a received scene core (from_scene_buffer(core_only=True))
-                        _lib.call("slr_scene_quilt", _lib.ptr(self._scene), self.C, self.n_tail, self.H, self.W, s)
+                        if os.environ.get("SLR_GATHER_MODE") == "staged":      # only the staged gather reads the quilted copy
+                            _lib.call("slr_scene_quilt", _lib.ptr(self._scene), self.C, self.n_tail, self.H, self.W, s)
                     else:
                         _lib.call("slr_scene_prep", _lib.ptr(self.feat), _lib.ptr(self.Z), _lib.ptr(self._zsub),
                                   _lib.ptr(self.tail), self.n_tail, _lib.ptr(self._scene), self.C, self.H, self.W, s)
