@@ -3,7 +3,7 @@ B="--no-cpu-baseline --no-e2e --steps 30"
 for i in 1 2; do
   timeout 90 python bench.py $B > gpurun_out/tune_base_$i.json 2>> gpurun_out/tune.err
   SLR_GATHER_SHAPE=1x4 timeout 90 python bench.py $B > gpurun_out/tune_shape1x4_$i.json 2>> gpurun_out/tune.err
-  for v in loads4 loads8 mb3l8 mb3l12; do
+  for v in loads10 loads12 loads16; do
     SLR_LIB=gpurun_variants/libslr_splat_$v.so timeout 90 python profiles/bench_with_lib.py $B > gpurun_out/tune_${v}_$i.json 2>> gpurun_out/tune.err
   done
 done

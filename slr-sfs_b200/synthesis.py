@@ -57,7 +57,11 @@ class _BufferPool:
     device-wide synchronisation -- in the middle of the pipeline (measured: occasional bench runs
     35 % slower).  An entry remembers, per stream, the last event after which its contents are no
     longer needed; whoever takes it over makes its writing stream wait for those on the device."""
-    KEEP = 4          # free entries kept per kind; more are handed back to the allocator
+    # Free entries kept per kind.  Two is what the pipeline needs (the scene being gathered and the next one whose
+    # table / scene buffer the side stream builds): the pool then reaches its steady state within two scenes.  With
+    # more, a host that runs ahead of the GPU keeps GROWING the pool (every entry still busy -> a fresh 0.4-0.8 GB
+    # cudaMalloc, a device-wide synchronisation) well into a run: measured as one bench run in five 25 % slow.
+    KEEP = 2
 
     def __init__(self, device):
         self.device = device
