@@ -267,9 +267,6 @@ expand_kernel(const GatherParams prm)
         const int64_t pair0 = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile;
         uint4* lists_tile = prm.lists + pair0 * (kListDepth * 32);
 
-        // this thread's first bin entry flies while the table is cleared
-        float4 first = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (beg + tid < end) first = __ldcs(ent + beg + tid);
         __syncthreads();            // the table is free: phase B, or the previous frame's write-out, is over
         for (int i = tid; i < kCanon * kCols; i += TILE) tab[i] = make_uint4(kEmpty, 0u, 0u, 0u);
         if (tid < kCols) { occ[tid] = 0u; ovf[tid] = 0u; }
@@ -312,7 +309,7 @@ expand_kernel(const GatherParams prm)
         // (its forward and backward splat both land exactly on it); it was not binned
         if (still) insert(lane, warp, source_field((unsigned)kSetSelf, (unsigned)pix, pack_xy(X, Y)), (unsigned)pix, a_f + a_b, 0u, 0, 0, pack_xy(X, Y));
         for (unsigned e = beg + tid; e < end; e += TILE) {
-            const float4 en = e == beg + tid ? first : __ldcs(ent + e);
+            const float4 en = __ldcs(ent + e);
             const unsigned pd = __float_as_uint(en.x), xy = __float_as_uint(en.w);
             const Footprint fp = footprint_at(en.y, en.z, prm.H, prm.W);
             const unsigned dir = pd >> 31;

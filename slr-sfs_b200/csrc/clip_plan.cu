@@ -238,47 +238,28 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
     unsigned* cur = cursors + (int64_t)f * n_tiles;
     float4* e = ent + (int64_t)f * cap;
     const unsigned xy = pack_xy((int)(p % W), (int)(p / W));      // the source's own coordinates, for the staging plan
-    // Both directions' landing coordinates first (four independent loads), then ALL slot reservations of the
-    // warp (up to eight warp-aggregated atomics whose round trips to L2 overlap), then the entries: the kernel
-    // is bound by those latencies, not by bandwidth.
-    float ox[2], oy[2];
-    ox[0] = __ldcs(land + ((int64_t)(f * 2 + 0) * 2) * P + p);
-    // static pixels carry the marker in every frame and direction: a warp of them (about half of the
-    // warps of a scene with a still background) has nothing to bin
-    if (__all_sync(0xffffffffu, !active || ox[0] == kStaticLand)) return;
-    oy[0] = __ldcs(land + ((int64_t)(f * 2 + 0) * 2 + 1) * P + p);
-    ox[1] = __ldcs(land + ((int64_t)(f * 2 + 1) * 2) * P + p);
-    oy[1] = __ldcs(land + ((int64_t)(f * 2 + 1) * 2 + 1) * P + p);
-    const unsigned lane = threadIdx.x & 31u;
-    int tiles[2][4];
-    unsigned base[2][4], peers[2][4];
     #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
+        const float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
+        const float ox = __ldcs(l);
+        // static pixels carry the marker in every frame and direction: a warp of them (about half of the
+        // warps of a scene with a still background) has nothing to bin
+        if (__all_sync(0xffffffffu, !active || ox == kStaticLand)) break;
+        const float oy = __ldcs(l + P);
+        int tiles[4];
         if (active) {
-            const Footprint fp = footprint_at(ox[dir], oy[dir], H, W);
-            touched_tiles(fp, ox[dir], oy[dir], H, W, tiles_x, tiles[dir]);
+            const Footprint fp = footprint_at(ox, oy, H, W);
+            touched_tiles(fp, ox, oy, H, W, tiles_x, tiles);
         } else {
-            tiles[dir][0] = tiles[dir][1] = tiles[dir][2] = tiles[dir][3] = -1;
+            tiles[0] = tiles[1] = tiles[2] = tiles[3] = -1;
         }
         #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            peers[dir][k] = 0u;
-            base[dir][k] = 0u;
-            if (!__any_sync(0xffffffffu, tiles[dir][k] >= 0)) continue;      // warp-uniform
-            peers[dir][k] = __match_any_sync(0xffffffffu, tiles[dir][k]);
-            if (tiles[dir][k] >= 0 && (int)lane == __ffs(peers[dir][k]) - 1)
-                base[dir][k] = atomicAdd(cur + tiles[dir][k], (unsigned)__popc(peers[dir][k]));
-        }
-    }
-    #pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-        #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (peers[dir][k] == 0u) continue;                                 // warp-uniform (set for all lanes or for none)
-            const unsigned b0 = __shfl_sync(0xffffffffu, base[dir][k], __ffs(peers[dir][k]) - 1);
-            if (tiles[dir][k] >= 0) {
-                const int64_t at = (int64_t)off[tiles[dir][k]] + b0 + (unsigned)__popc(peers[dir][k] & ((1u << lane) - 1u));
-                e[at] = make_float4(__uint_as_float((unsigned)p | (dir ? kDirBit : 0u)), ox[dir], oy[dir], __uint_as_float(xy));
+            if (!__any_sync(0xffffffffu, tiles[k] >= 0)) continue;
+            const unsigned slot = warp_reserve(cur, tiles[k]);
+            if (tiles[k] >= 0) {
+                const int64_t at = (int64_t)off[tiles[k]] + slot;
+                e[at] = make_float4(__uint_as_float((unsigned)p | (dir ? kDirBit : 0u)), ox, oy, __uint_as_float(xy));
             }
         }
     }
