@@ -515,12 +515,24 @@ def main():
         step_resident(1, exchange_on=False)
         ms_nobc = timed(lambda: step_resident(k, exchange_on=False)) / k
         ms_bc = timed(lambda: step_resident(k)) / k
-        multi = {"broadcast": "core of the prepared scene (%.1f MB) + motion per scene from its owner, NCCL, one scene ahead on a "
+        # the other legal partition: whole scenes per rank -- no exchange, full batches, one
+        # Euler chain per clip: the throughput-optimal assignment when there are at least as many scenes as GPUs
+        whole = ClipRunner(C, H, W, dev, group=min(N, 4 * batch))
+
+        def scene_major(steps):
+            for _ in range(steps):
+                whole.run(pkg.JointSplat(*own_dev, inputs_event=False), 0, N - 1, 0, N)
+        scene_major(1)
+        ms_sm = timed(lambda: scene_major(k)) / k
+        multi = {"scene_major": {"value": world * N / (ms_sm / 1000.0), "unit": UNIT, "ms_per_step": ms_sm,
+                                 "what": "every rank synthesises all %d frames of its own scene: no exchange" % N},
+                 "broadcast": "core of the prepared scene (%.1f MB) + motion per scene from its owner, NCCL, one scene ahead on a "
                               "communication stream, inside the timed region" % (pkg.JointSplat.scene_core_numel(C, 0, H, W) * 4 / 1e6),
                  "ms_per_step_with_broadcast": ms_bc, "ms_per_step_without_broadcast": ms_nobc,
                  "exposed_broadcast_us_per_scene": 1000.0 * (ms_bc - ms_nobc) / world,
                  "frames_per_rank_per_step": N,
                  "frame_blocks": "contiguous, rotated by the scene index (every rank: %d frames per %d scenes)" % (N, world)}
+        del whole
 
     # ---------------- --check: every frame of every scene against a single-rank recomputation -----------------
     check = None
