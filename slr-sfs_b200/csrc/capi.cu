@@ -36,6 +36,12 @@ bool gather_staged()
     return e && strcmp(e, "staged") == 0;
 }
 
+bool index_direct()
+{
+    const char* e = getenv("SLR_GATHER_MODE");
+    return !(e && (strcmp(e, "staged") == 0 || strcmp(e, "bins") == 0));
+}
+
 }  // namespace slr_host
 
 extern "C" int slr_version(void) { return 100; }  // 0.1.0

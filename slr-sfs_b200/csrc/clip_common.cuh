@@ -184,6 +184,8 @@ struct Workspace {
     unsigned* excess_count; // [1]
     unsigned excess_cap;
     float* heavy_sums;    // [n][3][P]           (tail..., norm) sums of flagged tiles
+    uint2* occ;           // [n][n_tiles * 4][32] direct index: per lane (canonical slots in use, overflow slots claimed)
+    const float** land_ref;   // [1]              direct index: where the landing coordinates of the batch's first frame are
     size_t bytes;
 };
 
@@ -219,7 +221,8 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     using namespace slr;
     const int64_t P = H * W;
     const int64_t tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
-    const int64_t cap = 8 * P;      // every (pixel, direction) touches at most 4 tiles
+    const bool direct = index_direct();      // no bins, no staging plans
+    const int64_t cap = direct ? 0 : 8 * P;  // every (pixel, direction) touches at most 4 tiles
     char* p = (char*)base;
     size_t o = 0;
     Workspace w;
@@ -231,13 +234,15 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * kPairsPerTile * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.fallback = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
-    w.records = (slr::StageRecord*)(p + o); o += align_up(sizeof(slr::StageRecord) * tiles * ((n + kStageFrames - 1) / kStageFrames));
+    w.records = (slr::StageRecord*)(p + o); o += direct ? 0 : align_up(sizeof(slr::StageRecord) * tiles * ((n + kStageFrames - 1) / kStageFrames));
     w.flag_list = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.flag_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.excess_cap = (unsigned)std::min<int64_t>(2 * P * n, 1ll << 30);
     w.excess = (uint4*)(p + o);      o += align_up(sizeof(uint4) * (size_t)w.excess_cap);
     w.excess_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.heavy_sums = (float*)(p + o);  o += align_up(sizeof(float) * 3 * P * n);
+    w.occ = (uint2*)(p + o);         o += direct ? align_up(sizeof(uint2) * 32 * (size_t)(tiles * kPairsPerTile) * n) : 0;
+    w.land_ref = (const float**)(p + o); o += align_up(sizeof(float*));
     w.bytes = o;
     return w;
 }

@@ -82,6 +82,9 @@ struct GatherParams {
     int n_tail;                // scalar planes of S besides the normaliser
     int staged;                // expand_kernel: plan the staging (stagegather_kernel follows) or not (rowgather_kernel for all)
     StageRecord* records;      // [frame pairs][n_tiles] staging plans
+    uint2* occ;                // direct index: [frames][n_tiles * 4][32] per lane (bit k: canonical slot k in use, overflow slots claimed)
+    const float* const* land_ref;   // direct index: -> landing coordinates [frames][2 dirs][2][P] of the batch (in the clip table)
+    int direct;                // lists built by insert_kernel (no bins, no row_k: the gather reads `occ`)
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -385,6 +388,146 @@ expand_kernel(const GatherParams prm)
 }
 
 // ---------------------------------------------------------------------------
+// insert_kernel: the DIRECT index (default).  No bins, no per-tile pass: one thread per (source pixel, frame)
+// turns the pixel's two landing positions into list cells and writes them where the gather reads them.
+//
+// A source with north-west cell (x0, y0) feeds, per column cx = x0 + dx, the pixels (cx, y0) and (cx, y0 + 1).
+// y0 even: both belong to the lane cx of ONE row pair -> one cell (source, w_north, w_south) in the canonical
+// slot (direction, dx, "both").  y0 odd: the bottom pixel of one row pair and the top pixel of the next -> two
+// cells with one weight each (slots "bottom only" / "top only").  So a thread always writes WHOLE cells, and a
+// slot is claimed with one atomicOr on the lane's slot word: nobody ever reads a cell another thread is still
+// writing.  A second source that maps to the same canonical slot (the flow compresses there) takes the lane's
+// next overflow slot (atomicAdd); beyond kListDepth its pairs go to the excess list and the tile is flagged,
+// exactly like expand_kernel does it.  Cells of the 32 consecutive sources a warp holds are consecutive
+// 16-byte entries of one slot row in regular flow: 512-byte stores, one atomic request per 128-byte line.
+// ---------------------------------------------------------------------------
+constexpr int kCellsPerSource = 8;      // 2 directions x 2 columns x (north-or-both cell, south cell)
+
+// The list cells one source pixel writes in one frame.  Cell i is unused when slot[i] < 0.
+struct SourceCells {
+    int slot[kCellsPerSource];          // canonical slot
+    unsigned at[kCellsPerSource];       // destination lane: (row pair within the batch) * 32 + lane   (< 2^32: n * P / 2)
+    float wt[kCellsPerSource];          // weight for the lane's top pixel
+    float wb[kCellsPerSource];          // ... bottom pixel
+};
+
+__device__ __forceinline__ unsigned lane_index(const GatherParams& prm, int f, int cx, int ytop)
+{
+    const int tile = (ytop / TH) * prm.tiles_x + cx / TW;
+    return (unsigned)((((int64_t)f * prm.n_tiles + tile) * kPairsPerTile + (ytop % TH) / 2) * 32 + cx % TW);
+}
+
+// top pixel (x, y) of a destination lane
+__device__ __forceinline__ void lane_pixel(const GatherParams& prm, unsigned at, int& cx, int& ytop)
+{
+    const unsigned pair = (at >> 5) % (unsigned)(prm.n_tiles * kPairsPerTile);
+    const int tile = (int)(pair / kPairsPerTile);
+    cx = (tile % prm.tiles_x) * TW + (int)(at & 31u);
+    ytop = (tile / prm.tiles_x) * TH + 2 * (int)(pair % kPairsPerTile);
+}
+
+// `land` = the frame's landing coordinates [2 dirs][2][P] at pixel p = (x, y).  All four coordinates are loaded
+// before anything depends on them (one memory latency per thread).
+__device__ __forceinline__ void source_cells(const GatherParams& prm, const float* land, int f, int x, int y, SourceCells& c)
+{
+    const int64_t P = prm.P;
+    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
+    const float o[4] = {__ldcs(land), __ldcs(land + P), __ldcs(land + 2 * P), __ldcs(land + 3 * P)};
+    #pragma unroll
+    for (int i = 0; i < kCellsPerSource; ++i) { c.slot[i] = -1; c.at[i] = 0u; c.wt[i] = c.wb[i] = 0.0f; }
+    if (o[0] == kStaticLand) {
+        // a pixel with exactly zero motion (the marker is in every frame and direction) receives itself with
+        // weight a + (1 - a): its forward and backward splat both land exactly on it
+        const float w = a_f + a_b;
+        c.slot[0] = y & 1;
+        c.at[0] = lane_index(prm, f, x, y & ~1);
+        c.wt[0] = (y & 1) ? 0.0f : w;
+        c.wb[0] = (y & 1) ? w : 0.0f;
+        return;
+    }
+    #pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const Footprint fp = footprint_at(o[2 * dir], o[2 * dir + 1], prm.H, prm.W);
+        const float a = dir ? a_b : a_f;
+        const bool even = (fp.y0 & 1) == 0;
+        #pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int i = (dir * 2 + dx) * 2;
+            const int cx = fp.x0 + dx;
+            const float wn = (fp.ok >> dx & 1u) ? fp.w[dx] * a : 0.0f;               // north corner (cx, y0)
+            const float ws = (fp.ok >> (2 + dx) & 1u) ? fp.w[2 + dx] * a : 0.0f;     // south corner (cx, y0 + 1)
+            if (even) {          // both corners belong to one lane: one cell
+                if (wn != 0.0f || ws != 0.0f) {
+                    c.slot[i] = canon_slot((unsigned)dir, 0, dx);
+                    c.at[i] = lane_index(prm, f, cx, fp.y0);
+                    c.wt[i] = wn; c.wb[i] = ws;
+                }
+            } else {             // bottom pixel of one row pair, top pixel of the next
+                if (wn != 0.0f) {
+                    c.slot[i] = canon_slot((unsigned)dir, 1, dx);
+                    c.at[i] = lane_index(prm, f, cx, fp.y0 - 1);
+                    c.wb[i] = wn;
+                }
+                if (ws != 0.0f) {
+                    c.slot[i + 1] = canon_slot((unsigned)dir, -1, dx);
+                    c.at[i + 1] = lane_index(prm, f, cx, fp.y0 + 1);
+                    c.wt[i + 1] = ws;
+                }
+            }
+        }
+    }
+}
+
+// A cell whose canonical slot was taken (or: the lane's overflow slots): the next overflow slot of the lane, or,
+// beyond the list depth (a convergence point), the excess list: those pairs are added by fp32 reductions at L2
+// after the gather (heavy_excess_kernel), which leaves the flagged tile un-normalised for them.
+__device__ __forceinline__ void spill_cell(const GatherParams& prm, int f, unsigned at, unsigned src, float wt, float wb, unsigned xy)
+{
+    const int so = kCanon + (int)atomicAdd(&prm.occ[at].y, 1u);
+    if (so < kListDepth) {
+        __stcg(prm.lists + ((int64_t)(at >> 5) * kListDepth + so) * 32 + (at & 31u),
+               make_uint4(src, __float_as_uint(wt), __float_as_uint(wb), xy));
+        return;
+    }
+    int cx, ytop;
+    lane_pixel(prm, at, cx, ytop);
+    const int tile = (ytop / TH) * prm.tiles_x + cx / TW;
+    if (atomicExch(prm.tile_flag + (int64_t)f * prm.n_tiles + tile, 1u) == 0u)
+        prm.flag_list[atomicAdd(prm.flag_count, 1u)] = (unsigned)(tile * prm.n_frames + f);
+    const unsigned n = (wt != 0.0f ? 1u : 0u) + (wb != 0.0f ? 1u : 0u);
+    unsigned i = atomicAdd(prm.excess_count, n);       // a count beyond excess_cap = "overflowed": see overflow_*_kernel
+    const unsigned dpix = (unsigned)(ytop * prm.W + cx);
+    if (wt != 0.0f) { if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix, src, __float_as_uint(wt), (unsigned)f)); ++i; }
+    if (wb != 0.0f) { if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix + (unsigned)prm.W, src, __float_as_uint(wb), (unsigned)f)); }
+}
+
+__global__ void __launch_bounds__(256)
+insert_kernel(const GatherParams prm)
+{
+    const int f = blockIdx.y;
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= prm.P) return;
+    const int y = (int)(p / prm.W), x = (int)(p - (int64_t)y * prm.W);
+    SourceCells c;
+    source_cells(prm, *prm.land_ref + (int64_t)f * 4 * prm.P + p, f, x, y, c);
+    // all claims are issued before the first answer is looked at: one atomic round trip per thread, not one per cell
+    unsigned old[kCellsPerSource];
+    #pragma unroll
+    for (int i = 0; i < kCellsPerSource; ++i) {
+        old[i] = 0u;
+        if (c.slot[i] >= 0) old[i] = atomicOr(&prm.occ[c.at[i]].x, 1u << c.slot[i]);
+    }
+    const unsigned xy = pack_xy(x, y);
+    #pragma unroll
+    for (int i = 0; i < kCellsPerSource; ++i) {
+        if (c.slot[i] < 0) continue;
+        if (old[i] >> c.slot[i] & 1u) spill_cell(prm, f, c.at[i], (unsigned)p, c.wt[i], c.wb[i], xy);
+        else __stcg(prm.lists + ((int64_t)(c.at[i] >> 5) * kListDepth + c.slot[i]) * 32 + (c.at[i] & 31u),
+                    make_uint4((unsigned)p, __float_as_uint(c.wt[i]), __float_as_uint(c.wb[i]), xy));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // rowgather_kernel
 // One warp per row pair; a CTA is F frames x R row pairs of one destination tile (template
 // parameters, default 2 x 2: vertically shared sources and the sources of the same rows in the
@@ -417,11 +560,19 @@ struct RowCtx {
     const uint4* list;    // this lane's column of the row-pair list (slot stride 32)
     float* out_top;       // this lane's top pixel in plane 0 of the frame (bottom = + W)
     int64_t P;
-    int W, groups, C, kmax;
+    int W, groups, C;
+    int my_hi;            // slots [0, my_hi) of THIS lane's column hold entries (direct index: the rest was never
+                          // written); the warp's list length is the maximum over its lanes
     float eps;
     bool in_top, in_bot;
     bool raw;             // flagged tile: write un-normalised sums, heavy_finish_kernel divides
 };
+
+// entry k >= kRegSlots of the lane's column, or the all-zero pixel with zero weights
+__device__ __forceinline__ uint4 deep_entry(const RowCtx& c, int k)
+{
+    return k < c.my_hi ? __ldcg(c.list + k * 32) : make_uint4((unsigned)c.P, 0u, 0u, 0u);
+}
 
 // K  = compile-time number of register-resident slots (the warp's list length rounded up);
 // GI = groups of 8 channels per iteration.  Per batch at most 6 independent 256-bit loads (6 KB per warp) are
@@ -450,9 +601,10 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
             }
         }
     }
+    const int kmax = K == kRegSlots ? __reduce_max_sync(0xffffffffu, c.my_hi) : K;
     if (K == kRegSlots) {
-        for (int k = kRegSlots; k < c.kmax; ++k) {          // rare: lists deeper than the registers hold
-            const uint4 e = __ldcg(c.list + k * 32);
+        for (int k = kRegSlots; k < kmax; ++k) {          // rare: lists deeper than the registers hold
+            const uint4 e = deep_entry(c, k);
             #pragma unroll
             for (int t = 0; t <= NT; ++t) {
                 const float s = __ldg(c.S + (int64_t)t * sstride + (e.x & kPixelMask));
@@ -496,8 +648,8 @@ __device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk
         #pragma unroll
         for (int gi = 0; gi < GI; ++gi) {
             if (K == kRegSlots) {
-                for (int k = kRegSlots; k < c.kmax; ++k) {
-                    const uint4 e = __ldcg(c.list + k * 32);
+                for (int k = kRegSlots; k < kmax; ++k) {
+                    const uint4 e = deep_entry(c, k);
                     const float8 t = ldg256(px32(Gg + gi * gstride, e.x & kPixelMask));
                     const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
                     fma4(at[gi].lo, t.lo, w0); fma4(at[gi].hi, t.hi, w0);
@@ -536,7 +688,9 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
 // the SAME tile in consecutive frames read source regions that differ only by one frame's
 // displacement, so with F > 1 they share most of their lines in this SM's L1 as well (the
 // frame-fastest CTA order already shares them in L2).  R < 4 splits a tile's row pairs over CTAs.
-template <int NT, int F, int R, bool NZ>
+// DIRECT: the lists were written by insert_kernel: which slots of a lane hold an entry is in its slot word
+// (GatherParams::occ), the others were never written and read as the all-zero pixel.
+template <int NT, int F, int R, bool NZ, bool DIRECT>
 __global__ void __launch_bounds__(32 * F * R, (SLR_GATHER_MINBLOCKS * kCols) / (32 * F * R))
 rowgather_kernel(const GatherParams prm)
 {
@@ -556,7 +710,17 @@ rowgather_kernel(const GatherParams prm)
     const int64_t P = prm.P;
     const int64_t pix = (int64_t)Y * prm.W + X;
     const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + pr;
-    const int kmax = (int)__ldg(prm.row_k + pair);
+    int kmax, my_hi;
+    unsigned used = 0xffffffffu;          // register-resident slots of this lane that hold an entry
+    if (DIRECT) {
+        const uint2 oc = __ldcg(prm.occ + pair * 32 + (tid & 31));
+        const int n_ovf = (int)min(oc.y, (unsigned)(kListDepth - kCanon));      // the rest is in the excess list
+        my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz((int)oc.x);
+        kmax = __reduce_max_sync(0xffffffffu, my_hi);
+        used = oc.x | ((1u << min(n_ovf, kRegSlots - kCanon)) - 1u) << kCanon;
+    } else {
+        kmax = my_hi = (int)__ldg(prm.row_k + pair);
+    }
 
     RowCtx c;
     c.G = prm.G; c.S = prm.S; c.P = P; c.W = prm.W; c.groups = prm.groups; c.C = prm.C; c.eps = prm.eps;
@@ -564,7 +728,7 @@ rowgather_kernel(const GatherParams prm)
     c.out_top = prm.out + (int64_t)f * prm.C * P + pix;
     c.in_top = X < prm.W && Y < prm.H;
     c.in_bot = X < prm.W && Y + 1 < prm.H;
-    c.kmax = kmax;
+    c.my_hi = my_hi;
     c.raw = flag == 1u;
 
     unsigned pk[kRegSlots];
@@ -572,7 +736,7 @@ rowgather_kernel(const GatherParams prm)
     #pragma unroll
     for (int k = 0; k < kRegSlots; ++k) {
         uint4 e = make_uint4((unsigned)P, 0u, 0u, 0u);
-        if (k < kmax) e = __ldcg(c.list + k * 32);
+        if (DIRECT ? (used >> k & 1u) != 0u : k < kmax) e = __ldcg(c.list + k * 32);
         pk[k] = e.x & kPixelMask;
         wt[k] = __uint_as_float(e.y);
         wb[k] = __uint_as_float(e.z);
@@ -985,14 +1149,39 @@ heavy_scatter_kernel(const GatherParams prm)
     }
 }
 
+// One (destination pixel, source pixel, weight) pair of frame f by fp32 reductions at L2: onto the un-normalised
+// sums in `out` / `heavy_sums`.
+template <int NT>
+__device__ __forceinline__ void red_pair(const GatherParams& prm, int f, int64_t dpix, unsigned src, float w)
+{
+    const int64_t P = prm.P;
+    const int64_t sstride = P + 1;
+    float* sums = prm.heavy_sums + (int64_t)f * 3 * P + dpix;
+    #pragma unroll
+    for (int j = 0; j <= NT; ++j) red_add(sums + (int64_t)j * P, __ldg(prm.S + (int64_t)j * sstride + src) * w);
+    float* out = prm.out + (int64_t)f * prm.C * P + dpix;
+    for (int g0 = 0; g0 < 2 * prm.groups; g0 += 4) {     // groups of four channels, four loads in flight per thread
+        float4 v[4];
+        #pragma unroll
+        for (int gi = 0; gi < 4; ++gi)
+            v[gi] = g0 + gi < 2 * prm.groups ? ldg_group4(prm.G, P, g0 + gi, src) : make_float4(0.f, 0.f, 0.f, 0.f);
+        #pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+            const float r[4] = {v[gi].x * w, v[gi].y * w, v[gi].z * w, v[gi].w * w};
+            #pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * (g0 + gi) + j < prm.C) red_add(out + (int64_t)(4 * (g0 + gi) + j) * P, r[j]);
+        }
+    }
+}
+
 // The pairs that did not fit the lists of flag-1 tiles: one thread per pair, fp32 reductions at
 // L2 onto the un-normalised sums the gather left in `out` / `heavy_sums`.
 template <int NT>
 __global__ void __launch_bounds__(TILE)
 heavy_excess_kernel(const GatherParams prm)
 {
-    const int64_t P = prm.P;
-    const int64_t sstride = P + 1;
+    if (prm.direct && *prm.excess_count > prm.excess_cap) return;      // the batch is redone by overflow_*_kernel
     const unsigned n = min(*prm.excess_count, prm.excess_cap);
     for (unsigned i = blockIdx.x * TILE + threadIdx.x; i < n; i += gridDim.x * TILE) {
         const uint4 e = __ldcg(prm.excess + i);
@@ -1000,64 +1189,105 @@ heavy_excess_kernel(const GatherParams prm)
         const int64_t dpix = e.x;
         const int tile = (int)(dpix / prm.W) / TH * prm.tiles_x + (int)(dpix % prm.W) / TW;
         if (prm.tile_flag[(int64_t)f * prm.n_tiles + tile] != 1u) continue;     // flag 2: done from the bin
-        const float w = __uint_as_float(e.z);
-        float* sums = prm.heavy_sums + (int64_t)f * 3 * P + dpix;
+        red_pair<NT>(prm, f, dpix, e.y, __uint_as_float(e.z));
+    }
+}
+
+// Divides the un-normalised sums of one pixel by its norm (and writes the optional planes).
+template <int NT>
+__device__ __forceinline__ void finish_pixel(const GatherParams& prm, int f, int64_t pix)
+{
+    const int64_t P = prm.P;
+    const float* sums = prm.heavy_sums + (int64_t)f * 3 * P + pix;
+    const float nrm = __ldcg(sums + (int64_t)NT * P);
+    const float inv = 1.0f / fmaxf(nrm, prm.eps);
+    float* out = prm.out + (int64_t)f * prm.C * P + pix;
+    int nz = 0;
+    // eight independent loads in flight per thread (one load -> store chain per channel is a
+    // full memory latency each: 64 of them made this kernel 33 us whatever the tile count)
+    for (int c0 = 0; c0 < prm.C; c0 += 8) {
+        float v[8];
         #pragma unroll
-        for (int j = 0; j <= NT; ++j) red_add(sums + (int64_t)j * P, __ldg(prm.S + (int64_t)j * sstride + e.y) * w);
-        float* out = prm.out + (int64_t)f * prm.C * P + dpix;
-        for (int g0 = 0; g0 < 2 * prm.groups; g0 += 4) {     // groups of four channels, four loads in flight per thread
-            float4 v[4];
-            #pragma unroll
-            for (int gi = 0; gi < 4; ++gi)
-                v[gi] = g0 + gi < 2 * prm.groups ? ldg_group4(prm.G, P, g0 + gi, e.y) : make_float4(0.f, 0.f, 0.f, 0.f);
-            #pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
-                const float r[4] = {v[gi].x * w, v[gi].y * w, v[gi].z * w, v[gi].w * w};
-                #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (4 * (g0 + gi) + j < prm.C) red_add(out + (int64_t)(4 * (g0 + gi) + j) * P, r[j]);
+        for (int j = 0; j < 8; ++j) v[j] = c0 + j < prm.C ? __ldcg(out + (int64_t)(c0 + j) * P) : 0.0f;
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (c0 + j < prm.C) {
+                const float r = v[j] * inv;
+                out[(int64_t)(c0 + j) * P] = r;
+                nz += r != 0.0f;
             }
         }
     }
+    if (prm.nnz) prm.nnz[(int64_t)f * P + pix] = (float)nz;
+    if (prm.aux) {
+        float* a = prm.aux + (int64_t)f * (NT + 1) * P + pix;
+        #pragma unroll
+        for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = __ldcg(sums + (int64_t)j * P);
+    }
+    if (prm.mask) prm.mask[(int64_t)f * P + pix] = nrm > prm.eps ? 1.0f : 0.0f;
 }
 
 template <int NT>
 __global__ void __launch_bounds__(TILE)
 heavy_finish_kernel(const GatherParams prm)
 {
+    if (prm.direct && *prm.excess_count > prm.excess_cap) return;      // the batch is redone by overflow_*_kernel
     const unsigned n = *prm.flag_count;
     for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
         const HeavyTile t = heavy_tile(prm, prm.flag_list[i], threadIdx.x);
-        if (!t.inframe) continue;
-        const int64_t P = prm.P;
-        const float* sums = prm.heavy_sums + (int64_t)t.f * 3 * P + t.pix;
-        const float nrm = __ldcg(sums + (int64_t)NT * P);
-        const float inv = 1.0f / fmaxf(nrm, prm.eps);
-        float* out = prm.out + (int64_t)t.f * prm.C * P + t.pix;
-        int nz = 0;
-        // eight independent loads in flight per thread (one load -> store chain per channel is a
-        // full memory latency each: 64 of them made this kernel 33 us whatever the tile count)
-        for (int c0 = 0; c0 < prm.C; c0 += 8) {
-            float v[8];
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = c0 + j < prm.C ? __ldcg(out + (int64_t)(c0 + j) * P) : 0.0f;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (c0 + j < prm.C) {
-                    const float r = v[j] * inv;
-                    out[(int64_t)(c0 + j) * P] = r;
-                    nz += r != 0.0f;
-                }
-            }
-        }
-        if (prm.nnz) prm.nnz[(int64_t)t.f * P + t.pix] = (float)nz;
-        if (prm.aux) {
-            float* a = prm.aux + (int64_t)t.f * (NT + 1) * P + t.pix;
-            #pragma unroll
-            for (int j = 0; j <= NT; ++j) a[(int64_t)j * P] = __ldcg(sums + (int64_t)j * P);
-        }
-        if (prm.mask) prm.mask[(int64_t)t.f * P + t.pix] = nrm > prm.eps ? 1.0f : 0.0f;
+        if (t.inframe) finish_pixel<NT>(prm, t.f, t.pix);
     }
+}
+
+// ---------------------------------------------------------------------------
+// Direct index, excess list full (a flow that piles more than excess_cap pairs beyond the list depth onto
+// single lanes -- adversarial input; never seen on a motion field of the benchmark): pairs were dropped, so the
+// whole batch is redone the way the reference does every frame: scatter with fp32 reductions, then divide.
+// Always launched, each kernel leaves at once unless the counter says "overflowed": correctness for any
+// input at the price of three empty launches per batch.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+overflow_zero_kernel(const GatherParams prm)
+{
+    if (*prm.excess_count <= prm.excess_cap) return;
+    const int64_t n_out = (int64_t)prm.n_frames * prm.C * prm.P, n_sum = (int64_t)prm.n_frames * 3 * prm.P;
+    const int64_t step = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_out; i += step) prm.out[i] = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_sum; i += step) prm.heavy_sums[i] = 0.0f;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256)
+overflow_scatter_kernel(const GatherParams prm)
+{
+    if (*prm.excess_count <= prm.excess_cap) return;
+    const int64_t total = prm.P * prm.n_frames;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += (int64_t)gridDim.x * 256) {
+        const int f = (int)(i0 / prm.P);
+        const int64_t p = i0 - (int64_t)f * prm.P;
+        const int y = (int)(p / prm.W), x = (int)(p - (int64_t)y * prm.W);
+        SourceCells c;
+        source_cells(prm, *prm.land_ref + (int64_t)f * 4 * prm.P + p, f, x, y, c);
+        #pragma unroll 1
+        for (int j = 0; j < 2 * kCellsPerSource; ++j) {       // (cell, row): not unrolled -- this path is never hot
+            const int i = j >> 1;
+            const float w = (j & 1) ? c.wb[i] : c.wt[i];
+            if (c.slot[i] < 0 || w == 0.0f) continue;
+            int cx, ytop;
+            lane_pixel(prm, c.at[i], cx, ytop);
+            red_pair<NT>(prm, f, (int64_t)(ytop + (j & 1)) * prm.W + cx, (unsigned)p, w);
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256)
+overflow_finish_kernel(const GatherParams prm)
+{
+    if (*prm.excess_count <= prm.excess_cap) return;
+    const int64_t total = prm.P * prm.n_frames;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256)
+        finish_pixel<NT>(prm, (int)(i / prm.P), i % prm.P);
 }
 
 }  // namespace slr
@@ -1094,6 +1324,8 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     prm.n_tail = n_tail;
     // the plan packs a source row into 14 bits and a column into 16 (plan_key)
     prm.staged = slr_host::gather_staged() && H <= 16384 && W <= 65535 ? 1 : 0;
+    prm.direct = slr_host::index_direct() ? 1 : 0;
+    prm.occ = ws.occ; prm.land_ref = ws.land_ref;
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;
@@ -1101,7 +1333,7 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     prm.out = out; prm.aux = aux; prm.mask = mask; prm.nnz = nnz;
     prm.C = (int)C; prm.groups = groups; prm.H = (int)H; prm.W = (int)W;
     prm.tiles_x = tiles_x; prm.n_tiles = tiles_x * tiles_y; prm.n_frames = n_frames;
-    prm.P = P; prm.cap = 8 * P; prm.eps = 1e-8f;
+    prm.P = P; prm.cap = prm.direct ? 0 : 8 * P; prm.eps = 1e-8f;
     for (int f = 0; f < n_frames; ++f) {
         // alpha = 1 - (t - start) / (end - start + 1) in fp32 (animating_softmax_splating.py:860),
         // optionally clamped (2layers...py:952)
@@ -1136,20 +1368,42 @@ void launch_stagegather(const GatherParams& prm, unsigned grid, cudaStream_t s)
     stagegather_kernel<NT><<<grid, kStageThreads, kStageBytes, s>>>(prm);
 }
 
-template <int F, int R, bool NZ>
+template <int NT>
+void launch_heavy(const GatherParams& prm, unsigned heavy_grid, cudaStream_t s)
+{
+    if (!prm.direct) {           // whole-tile heavy tiles (flag 2) exist with bins only
+        heavy_prepare_kernel<<<heavy_grid, TILE, 0, s>>>(prm, NT + 1);
+        heavy_scatter_kernel<NT><<<heavy_grid, TILE, 0, s>>>(prm);
+    }
+    heavy_excess_kernel<NT><<<heavy_grid, TILE, 0, s>>>(prm);
+    heavy_finish_kernel<NT><<<heavy_grid, TILE, 0, s>>>(prm);
+    if (prm.direct) {
+        // fixed small grids (grid-stride loops): an empty launch costs its CTAs
+        overflow_zero_kernel<<<heavy_grid, 256, 0, s>>>(prm);
+        overflow_scatter_kernel<NT><<<heavy_grid, 256, 0, s>>>(prm);
+        overflow_finish_kernel<NT><<<heavy_grid, 256, 0, s>>>(prm);
+    }
+}
+
+template <int F, int R, bool NZ, bool DIRECT>
 void launch_rowgather_nz(const GatherParams& prm, int n_tail, cudaStream_t s)
 {
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)(kPairsPerTile / R) * (unsigned)((prm.n_frames + F - 1) / F);
-    if (n_tail == 0) rowgather_kernel<0, F, R, NZ><<<grid, 32 * F * R, 0, s>>>(prm);
-    else if (n_tail == 1) rowgather_kernel<1, F, R, NZ><<<grid, 32 * F * R, 0, s>>>(prm);
-    else rowgather_kernel<2, F, R, NZ><<<grid, 32 * F * R, 0, s>>>(prm);
+    if (n_tail == 0) rowgather_kernel<0, F, R, NZ, DIRECT><<<grid, 32 * F * R, 0, s>>>(prm);
+    else if (n_tail == 1) rowgather_kernel<1, F, R, NZ, DIRECT><<<grid, 32 * F * R, 0, s>>>(prm);
+    else rowgather_kernel<2, F, R, NZ, DIRECT><<<grid, 32 * F * R, 0, s>>>(prm);
 }
 
 template <int F, int R>
 void launch_rowgather(const GatherParams& prm, int n_tail, cudaStream_t s)
 {
-    if (prm.nnz) launch_rowgather_nz<F, R, true>(prm, n_tail, s);
-    else launch_rowgather_nz<F, R, false>(prm, n_tail, s);
+    if (prm.direct) {
+        if (prm.nnz) launch_rowgather_nz<F, R, true, true>(prm, n_tail, s);
+        else launch_rowgather_nz<F, R, false, true>(prm, n_tail, s);
+    } else {
+        if (prm.nnz) launch_rowgather_nz<F, R, true, false>(prm, n_tail, s);
+        else launch_rowgather_nz<F, R, false, false>(prm, n_tail, s);
+    }
 }
 
 }  // namespace
@@ -1162,6 +1416,10 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
     const int rc = make_params(prm, scene, motion, C, n_tail, H, W, start, end, t0, n_frames, alpha_lo, alpha_hi,
                                nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
+    if (prm.direct) {
+        insert_kernel<<<dim3((unsigned)((prm.P + 255) / 256), (unsigned)n_frames), 256, 0, (cudaStream_t)stream_>>>(prm);
+        return SLR_LAUNCH_STATUS();
+    }
     const int per_cta = prm.staged ? kStageFrames : 1;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)((n_frames + per_cta - 1) / per_cta);
     if (prm.staged) expand_kernel<true><<<grid, TILE, 0, (cudaStream_t)stream_>>>(prm);
@@ -1209,20 +1467,9 @@ extern "C" int slr_clip_heavy(const void* scene, const float* motion, int64_t C,
     cudaStream_t s = (cudaStream_t)stream_;
     const unsigned grid = (unsigned)prm.n_tiles * (unsigned)n_frames;
     const unsigned heavy_grid = std::min<unsigned>(grid, 8u * (unsigned)slr_host::sm_count());
-    heavy_prepare_kernel<<<heavy_grid, TILE, 0, s>>>(prm, n_tail + 1);
-    if (n_tail == 0) {
-        heavy_scatter_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
-        heavy_excess_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
-        heavy_finish_kernel<0><<<heavy_grid, TILE, 0, s>>>(prm);
-    } else if (n_tail == 1) {
-        heavy_scatter_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
-        heavy_excess_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
-        heavy_finish_kernel<1><<<heavy_grid, TILE, 0, s>>>(prm);
-    } else {
-        heavy_scatter_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
-        heavy_excess_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
-        heavy_finish_kernel<2><<<heavy_grid, TILE, 0, s>>>(prm);
-    }
+    if (n_tail == 0) launch_heavy<0>(prm, heavy_grid, s);
+    else if (n_tail == 1) launch_heavy<1>(prm, heavy_grid, s);
+    else launch_heavy<2>(prm, heavy_grid, s);
     return SLR_LAUNCH_STATUS();
 }
 

@@ -113,6 +113,9 @@ __device__ __forceinline__ void euler_step(EulerState& s, const float* __restric
     if (s.invalid) { s.dx = cx; s.dy = cy; }
 }
 
+// COUNT: also count the entries of every (frame, destination tile) bin (the bin pipeline); the direct
+// index (insert_kernel) has no bins.
+template <bool COUNT>
 __global__ void __launch_bounds__(256)
 euler_table_kernel(const float* __restrict__ motion, int H, int W, int steps_f0, int steps_b0, int n,
                    float* __restrict__ land, unsigned* __restrict__ counts, int tiles_x, int n_tiles)
@@ -141,20 +144,22 @@ euler_table_kernel(const float* __restrict__ motion, int H, int W, int steps_f0,
         const float ddy = s.invalid ? sentinel : __fsub_rn(s.dy, cy);
         const float ox = is_static ? kStaticLand : __fadd_rn(cx, ddx);
         const float oy = is_static ? kStaticLand : __fadd_rn(cy, ddy);
-        int tiles[4];
+        int tiles[4] = {-1, -1, -1, -1};
         if (active) {
             float* l = land + ((int64_t)(f * 2 + dir) * 2) * P + p;
             l[0] = ox;
             l[P] = oy;
-            const Footprint fp = footprint_at(ox, oy, H, W);
-            touched_tiles(fp, ox, oy, H, W, tiles_x, tiles);
-        } else {
-            tiles[0] = tiles[1] = tiles[2] = tiles[3] = -1;
+            if (COUNT) {
+                const Footprint fp = footprint_at(ox, oy, H, W);
+                touched_tiles(fp, ox, oy, H, W, tiles_x, tiles);
+            }
         }
-        unsigned* cnt = counts + (int64_t)f * n_tiles;
-        #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (__any_sync(0xffffffffu, tiles[k] >= 0)) warp_reserve(cnt, tiles[k]);
+        if (COUNT) {
+            unsigned* cnt = counts + (int64_t)f * n_tiles;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (__any_sync(0xffffffffu, tiles[k] >= 0)) warp_reserve(cnt, tiles[k]);
+        }
     };
 
     // forward chain
@@ -333,11 +338,33 @@ int build_table(const float* motion, int64_t H, int64_t W, int start, int end, i
     const int64_t P = H * W;
     const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
     const int n_tiles = tiles_x * tiles_y;
-    SLR_CUDA(cudaMemsetAsync(tab.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
     const unsigned pblocks = (unsigned)((P + 255) / 256);
-    euler_table_kernel<<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
-                                               tab.land, tab.counts, tiles_x, n_tiles);
+    if (slr_host::index_direct()) {        // landing coordinates only: insert_kernel needs no bins
+        euler_table_kernel<false><<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
+                                                          tab.land, tab.counts, tiles_x, n_tiles);
+        return SLR_LAUNCH_STATUS();
+    }
+    SLR_CUDA(cudaMemsetAsync(tab.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
+    euler_table_kernel<true><<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
+                                                     tab.land, tab.counts, tiles_x, n_tiles);
     bin_scan_kernel<<<n_frames, 1024, 0, s>>>(tab.counts, tab.offsets, n_tiles);
+    return SLR_LAUNCH_STATUS();
+}
+
+// Direct index: a batch only REFERS to its landing coordinates (insert_kernel reads them where they are: in the
+// clip table, which must stay valid until the batch's slr_clip_heavy has run); its per-lane slot words, tile
+// flags and counters start at zero.
+__global__ void bind_batch_kernel(const float** land_ref, const float* land, unsigned* flag_count, unsigned* excess_count)
+{
+    if (threadIdx.x == 0) { *land_ref = land; *flag_count = 0u; *excess_count = 0u; }
+}
+
+int bind_batch(const float* land, int64_t H, int64_t W, int n_frames, const Workspace& ws, cudaStream_t s)
+{
+    const int n_tiles = (int)(((W + TW - 1) / TW) * ((H + TH - 1) / TH));
+    SLR_CUDA(cudaMemsetAsync(ws.occ, 0, sizeof(uint2) * 32 * (size_t)n_tiles * kPairsPerTile * n_frames, s));
+    SLR_CUDA(cudaMemsetAsync(ws.tile_flag, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
+    bind_batch_kernel<<<1, 32, 0, s>>>(ws.land_ref, land, ws.flag_count, ws.excess_count);
     return SLR_LAUNCH_STATUS();
 }
 
@@ -390,6 +417,7 @@ extern "C" int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, in
     const Workspace ws = carve(workspace, H, W, n_frames);
     SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_bin: workspace too small (see slr_clip_workspace_bytes)");
     cudaStream_t s = (cudaStream_t)stream_;
+    if (slr_host::index_direct()) return bind_batch(tab.land + (size_t)f0 * 4 * P, H, W, n_frames, ws, s);
     // the batch's own copy of its bin offsets (expand / gather / heavy read them from the workspace);
     // the fill cursors start at zero
     SLR_CUDA(cudaMemcpyAsync(ws.offsets, tab.offsets + (size_t)f0 * (n_tiles + 1),
@@ -413,5 +441,6 @@ extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int star
     tab.land = ws.land; tab.counts = ws.counts; tab.offsets = ws.offsets; tab.bytes = 0;
     const int rc = build_table(motion, H, W, start, end, t0, n_frames, tab, s);
     if (rc) return rc;
+    if (slr_host::index_direct()) return bind_batch(ws.land, H, W, n_frames, ws, s);
     return fill_bins(ws.land, H, W, n_frames, ws, s);       // bin_scan left the counts at zero: they are the cursors
 }

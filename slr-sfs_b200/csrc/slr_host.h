@@ -16,6 +16,11 @@ int sm_count();
 // staged gather's main loop is ~30 % faster, but the staging plan (in expand_kernel), the copy issue and the
 // per-chunk synchronisation cost more than that saves; see DESIGN.md 4.2.
 bool gather_staged();
+// How the per-lane source lists of a batch are built (same variable): by default ("ldg") every moving source
+// pixel writes its pairs straight into the lists of the destination lanes (insert_kernel, csrc/clip_gather.cu);
+// "bins" and "staged" sort the sources into per-tile bins first and expand them tile by tile (bin_fill_kernel +
+// expand_kernel: the round-1 pipeline, which the staging plan of "staged" is built on).
+bool index_direct();
 }  // namespace slr_host
 
 #define SLR_CHECK_ARGS(cond, msg) \

@@ -116,6 +116,7 @@ def clip_table_bin_stats(be, H=40, W=72, C=6, start=1, end=12, t0=2, n_table=9, 
 
     # a one-step sink: the tile that receives everything is flagged, its pairs beyond the list
     # depth are counted, and with one frame in the batch the excess list (2 * P entries) overflows
+    # (bin pipeline: whole-tile reductions; direct index: the batch is redone by scatter + divide)
     ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
     sink = np.stack([(W / 2 + 0.3) - xs, (H / 3 + 0.6) - ys])[None].astype(np.float32)
     d_sink = be.dev(sink)
@@ -126,6 +127,9 @@ def clip_table_bin_stats(be, H=40, W=72, C=6, start=1, end=12, t0=2, n_table=9, 
             be.ptr(out), None, None, None, be.ptr(ws), ws_bytes, s)
     stats = (ctypes.c_uint32 * 6)()
     be.call("slr_clip_stats_host", be.ptr(ws), ws_bytes, H, W, 1, stats, s)
-    assert stats[0] >= 1 and stats[1] >= 1 and stats[2] > stats[3] == 2 * H * W and stats[5] == 5 * 3
+    assert stats[0] >= 1 and stats[2] > stats[3] == 2 * H * W and stats[5] == 5 * 3
+    # whole-tile heavy tiles exist with the bin pipeline only (the direct index redoes the batch by scatter + divide)
+    import os
+    assert (stats[1] >= 1) == (os.environ.get("SLR_GATHER_MODE") in ("bins", "staged"))
     want = oracle.joint_splat_baseline(feat, Z, sink, (0, 1, 2))
     assert rel_err(be.host(out), want) <= TOL

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: run in a process started with LD_PRELOAD=libasan (tests/test_emu_asan.py).
 Drives the AddressSanitizer build of the emulated library over the whole clip pipeline -- ragged
-shapes, both rowgather CTA shapes, the heavy paths -- and the operator-level
+shapes, both index modes, both rowgather CTA shapes, the heavy paths -- and the operator-level
 entry points, with every buffer (inputs, outputs, scene, table, workspace) allocated at exactly
 the size the C ABI asks for, so that an out-of-bounds access of any kernel aborts the process."""
 import ctypes
@@ -29,11 +29,15 @@ for (H, W, C, kind, n) in [(17, 37, 5, "A", 3), (24, 40, 4, "B", 2), (9, 33, 3, 
     if kind == "sink":
         ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
         m = np.stack([(W / 2 + 0.3) - xs, (H / 3 + 0.6) - ys])[None].astype(np.float32)
-    for shape in ("1x4", "2x2"):
+    # index modes: the direct index (insert_kernel, default) and the bin pipeline (bin_fill + expand_kernel)
+    for (mode, shape) in (("ldg", "1x4"), ("ldg", "2x2"), ("bins", "1x4"), ("bins", "2x2")):
+        os.environ["SLR_GATHER_MODE"] = mode
         os.environ["SLR_GATHER_SHAPE"] = shape
         sc = emu.Scene(feat, Z, m)
         sc.frames(0, 7, 1, n, want_mask=True)
         sc.frames(0, 7, 1, n, table=sc.table(0, 7, 0, 8))
+        if kind == "sink":
+            print("sink", mode, sc.stats, flush=True)
     rng = np.random.default_rng(0)
     inp = rng.standard_normal((2, 3, H, W)).astype(np.float32)
     flow = rng.uniform(-6, 6, (2, 2, H, W)).astype(np.float32)

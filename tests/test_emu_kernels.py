@@ -218,18 +218,53 @@ def test_emu_convergent_flows_take_the_heavy_paths():
     assert seen_flagged > 0
 
 
-def test_emu_excess_list_overflow_falls_back_to_whole_tile_reductions():
+@pytest.mark.parametrize("mode", ["ldg", "bins"])
+def test_emu_excess_list_overflow_falls_back_to_reductions(mode, monkeypatch):
     """A one-step sink puts 4*P pairs onto four pixels; with a single frame in the batch the excess
-    list (2*P*n entries) overflows and the tile goes the flag-2 way: zeroed, every pair of its
-    bin added by reductions, divided at the end."""
+    list (2*P*n entries) overflows.  Bin pipeline: the tile goes the flag-2 way (zeroed, every pair of its
+    bin added by reductions, divided at the end).  Direct index: pairs were dropped, so the whole batch is
+    redone by scatter + divide (overflow_*_kernel); also with the optional planes and a 2-layer tail."""
+    monkeypatch.setenv("SLR_GATHER_MODE", mode)
     H, W, C, N = 40, 72, 6, 3
     feat, Z, sink, _ = _sink_scene(H, W, C, 9)
     sc = emu.Scene(feat, Z, sink)
-    got = sc.frames(0, N - 1, 1, 1)
-    assert sc.stats["full"] > 0 and sc.stats["excess"] > sc.stats["excess_cap"]
+    got, aux, mask, nnz = sc.frames(0, N - 1, 1, 1, want_aux=True, want_mask=True, want_nnz=True)
+    assert sc.stats["excess"] > sc.stats["excess_cap"]
+    assert (sc.stats["full"] > 0) == (mode == "bins")
     want = oracle.joint_splat_baseline(feat, Z, sink, (0, 1, N - 1))
     assert rel_err(got, want) <= TOL
     assert np.all(got[want == 0.0] == 0.0)
+    assert np.array_equal(nnz[0, 0], (got[0] != 0).sum(0).astype(np.float32))
+    assert np.array_equal(mask[0, 0] != 0, aux[0, -1] > 1e-8)
+
+
+@pytest.mark.parametrize("kind", ["A", "B", "sink", "squeeze"])
+def test_emu_direct_index_equals_bin_pipeline(kind, monkeypatch):
+    """insert_kernel (every source writes its cells straight into the destination lanes' lists) against
+    bin_fill + expand_kernel: the same (source, weight) pairs in the same canonical slots -- only which of two
+    competing sources gets the canonical slot and which the overflow slot may differ, i.e. the summation order."""
+    from slr_sfs_b200 import workloads
+    H, W, C, N = 40, 72, 6, 7
+    feat, Z, motion = _scene(H, W, C, "A" if kind in ("sink", "squeeze") else kind, 31)
+    if kind in ("sink", "squeeze"):
+        _, _, sink, squeeze = _sink_scene(H, W, C, 31)
+        motion = sink if kind == "sink" else squeeze
+    tail = np.abs(feat[:, :2]) + 0.5
+    res = {}
+    for mode in ("ldg", "bins"):
+        monkeypatch.setenv("SLR_GATHER_MODE", mode)
+        sc = emu.Scene(feat, Z, motion, tail=tail)
+        res[mode] = sc.frames(0, N - 1, 1, 5, want_aux=True, want_mask=True, want_nnz=True)
+        res[mode + "_stats"] = sc.stats
+    for a, b in zip(res["ldg"], res["bins"]):
+        assert rel_err(a, b) <= 1e-5
+    # an overflow cell of the direct index carries both rows' weights of its source (expand_kernel spills one entry
+    # per pair): its lists are never deeper
+    assert res["ldg_stats"]["flagged"] <= res["bins_stats"]["flagged"]
+    for i in (0, 4):
+        want = oracle.joint_splat_baseline(feat, Z, motion, (0, 1 + i, N - 1))
+        assert rel_err(res["ldg"][0][i:i + 1], want) <= TOL
+        assert np.all(res["ldg"][0][i:i + 1][want == 0.0] == 0.0)
 
 
 def test_emu_static_pixels_and_negative_zero():
@@ -270,10 +305,11 @@ def test_emu_euler_grad_motion_vs_oracle(sign):
 
 
 # ---------------------------------------------------------------------------
-# stagegather_kernel (sources staged in shared memory by bulk copies) vs rowgather_kernel (through L1)
+# stagegather_kernel (sources staged in shared memory by bulk copies) vs rowgather_kernel (through L1), both on the
+# lists expand_kernel builds from the bins (SLR_GATHER_MODE=bins: the direct index fills the same slots in another order)
 # ---------------------------------------------------------------------------
 def _both_modes(monkeypatch, make):
-    monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+    monkeypatch.setenv("SLR_GATHER_MODE", "bins")
     sc = make()
     ldg = sc.frames(0, sc.N - 1, 0, sc.N, want_aux=True, want_mask=True)
     assert sc.stats["fallback"] == 0
@@ -329,7 +365,7 @@ def test_emu_staged_gather_incoherent_flow_falls_back(monkeypatch):
         sc = emu.Scene(feat, Z, motion)
         sc.N = N
         return sc
-    monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+    monkeypatch.setenv("SLR_GATHER_MODE", "bins")
     sc = make()
     ldg = sc.frames(0, N - 1, 5, 4)
     monkeypatch.setenv("SLR_GATHER_MODE", "staged")
@@ -345,7 +381,7 @@ def test_emu_staged_gather_deep_lists_and_heavy_tiles(monkeypatch):
     H, W, C, N = 40, 72, 6, 3
     feat, Z, sink, squeeze = _sink_scene(H, W, C, 9)
     for m in (sink, squeeze):
-        monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+        monkeypatch.setenv("SLR_GATHER_MODE", "bins")
         ldg = emu.Scene(feat, Z, m).frames(0, N - 1, 1, 2)
         monkeypatch.setenv("SLR_GATHER_MODE", "staged")
         sc = emu.Scene(feat, Z, m)
@@ -362,7 +398,7 @@ def test_emu_staged_gather_single_stage_and_capacity_fallback(monkeypatch):
     chunk wait for the gather of the current one) and tiles that do not fit (L1 fallback)."""
     H, W, C, N = 40, 100, 37, 6
     feat, Z, motion = _scene(H, W, C, "A", 23)
-    monkeypatch.setenv("SLR_GATHER_MODE", "ldg")
+    monkeypatch.setenv("SLR_GATHER_MODE", "bins")
     ldg = emu.Scene(feat, Z, motion).frames(0, N - 1, 0, N)
     monkeypatch.setenv("SLR_GATHER_MODE", "staged")
     seen = []
