@@ -48,6 +48,9 @@ struct StageRecord {
 // forward and the backward sources of a tile lie a whole displacement apart):
 constexpr int kSetShift = 28;                       // H * W < 2^27: the bits above are free
 constexpr unsigned kPixelMask = (1u << kSetShift) - 1u;
+// Direct index: the slot word of a lane (Workspace::occ) -- bits 0 .. kCanon-1: canonical slot in use; bits 30 / 31:
+// the lane's top / bottom pixel has zero motion and receives itself (slot 0 / 1 is then reserved, holds no entry)
+constexpr unsigned kSelfTop = 1u << 30, kSelfBottom = 1u << 31;
 enum SourceSet { kSetForward = 0, kSetBackward = 1, kSetSelf = 2, kSets = 3 };   // self: static pixels receive themselves
 
 __host__ __device__ __forceinline__ unsigned pack_xy(int x, int y) { return (unsigned)y << 16 | (unsigned)x; }
@@ -185,6 +188,7 @@ struct Workspace {
     unsigned excess_cap;
     float* heavy_sums;    // [n][3][P]           (tail..., norm) sums of flagged tiles
     uint2* occ;           // [n][n_tiles * 4][32] direct index: per lane (canonical slots in use, overflow slots claimed)
+    uint2* occ0;          // [n_tiles * 4][32]   direct index, slr_clip_plan only: the initial slot words (else in the clip table)
     const float** land_ref;   // [1]              direct index: where the landing coordinates of the batch's first frame are
     size_t bytes;
 };
@@ -198,6 +202,7 @@ struct ClipTable {
     float* land;          // [n][2 dirs][2][P]   landing coordinates
     unsigned* counts;     // [n][n_tiles]        entries per destination tile (zero again after the scan)
     unsigned* offsets;    // [n][n_tiles + 1]    bin offsets
+    uint2* occ0;          // [n_tiles * 4][32]   direct index: the lanes' slot words before any source is inserted
     size_t bytes;
 };
 
@@ -212,6 +217,7 @@ inline ClipTable carve_table(void* base, int64_t H, int64_t W, int n)
     t.land = (float*)(p + o);        o += align_up(sizeof(float) * 4 * P * n);
     t.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
     t.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
+    t.occ0 = (uint2*)(p + o);        o += align_up(sizeof(uint2) * 32 * (size_t)(tiles * kPairsPerTile));
     t.bytes = o;
     return t;
 }
@@ -242,6 +248,7 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.excess_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.heavy_sums = (float*)(p + o);  o += align_up(sizeof(float) * 3 * P * n);
     w.occ = (uint2*)(p + o);         o += direct ? align_up(sizeof(uint2) * 32 * (size_t)(tiles * kPairsPerTile) * n) : 0;
+    w.occ0 = (uint2*)(p + o);        o += direct ? align_up(sizeof(uint2) * 32 * (size_t)(tiles * kPairsPerTile)) : 0;
     w.land_ref = (const float**)(p + o); o += align_up(sizeof(float*));
     w.bytes = o;
     return w;

@@ -401,9 +401,9 @@ expand_kernel(const GatherParams prm)
 // exactly like expand_kernel does it.  Cells of the 32 consecutive sources a warp holds are consecutive
 // 16-byte entries of one slot row in regular flow: 512-byte stores, one atomic request per 128-byte line.
 // ---------------------------------------------------------------------------
-constexpr int kCellsPerSource = 8;      // 2 directions x 2 columns x (north-or-both cell, south cell)
+constexpr int kCellsPerSource = 4;      // per direction: 2 columns x (north-or-both cell, south cell)
 
-// The list cells one source pixel writes in one frame.  Cell i is unused when slot[i] < 0.
+// The list cells one source pixel writes for one direction of one frame.  Cell i is unused when slot[i] < 0.
 struct SourceCells {
     int slot[kCellsPerSource];          // canonical slot
     unsigned at[kCellsPerSource];       // destination lane: (row pair within the batch) * 32 + lane   (< 2^32: n * P / 2)
@@ -426,61 +426,46 @@ __device__ __forceinline__ void lane_pixel(const GatherParams& prm, unsigned at,
     ytop = (tile / prm.tiles_x) * TH + 2 * (int)(pair % kPairsPerTile);
 }
 
-// `land` = the frame's landing coordinates [2 dirs][2][P] at pixel p = (x, y).  All four coordinates are loaded
-// before anything depends on them (one memory latency per thread).
-__device__ __forceinline__ void source_cells(const GatherParams& prm, const float* land, int f, int x, int y, SourceCells& c)
+// Cells of a source that lands on (ox, oy) in direction `dir` of frame f.
+__device__ __forceinline__ void source_cells(const GatherParams& prm, float ox, float oy, int f, int dir, SourceCells& c)
 {
-    const int64_t P = prm.P;
-    const float a_f = prm.alphas.a[f], a_b = 1.0f - a_f;
-    const float o[4] = {__ldcs(land), __ldcs(land + P), __ldcs(land + 2 * P), __ldcs(land + 3 * P)};
+    const float a_f = prm.alphas.a[f];
+    const float a = dir ? 1.0f - a_f : a_f;
+    const Footprint fp = footprint_at(ox, oy, prm.H, prm.W);
+    const bool even = (fp.y0 & 1) == 0;
     #pragma unroll
-    for (int i = 0; i < kCellsPerSource; ++i) { c.slot[i] = -1; c.at[i] = 0u; c.wt[i] = c.wb[i] = 0.0f; }
-    if (o[0] == kStaticLand) {
-        // a pixel with exactly zero motion (the marker is in every frame and direction) receives itself with
-        // weight a + (1 - a): its forward and backward splat both land exactly on it
-        const float w = a_f + a_b;
-        c.slot[0] = y & 1;
-        c.at[0] = lane_index(prm, f, x, y & ~1);
-        c.wt[0] = (y & 1) ? 0.0f : w;
-        c.wb[0] = (y & 1) ? w : 0.0f;
-        return;
-    }
-    #pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-        const Footprint fp = footprint_at(o[2 * dir], o[2 * dir + 1], prm.H, prm.W);
-        const float a = dir ? a_b : a_f;
-        const bool even = (fp.y0 & 1) == 0;
-        #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-            const int i = (dir * 2 + dx) * 2;
-            const int cx = fp.x0 + dx;
-            const float wn = (fp.ok >> dx & 1u) ? fp.w[dx] * a : 0.0f;               // north corner (cx, y0)
-            const float ws = (fp.ok >> (2 + dx) & 1u) ? fp.w[2 + dx] * a : 0.0f;     // south corner (cx, y0 + 1)
-            if (even) {          // both corners belong to one lane: one cell
-                if (wn != 0.0f || ws != 0.0f) {
-                    c.slot[i] = canon_slot((unsigned)dir, 0, dx);
-                    c.at[i] = lane_index(prm, f, cx, fp.y0);
-                    c.wt[i] = wn; c.wb[i] = ws;
-                }
-            } else {             // bottom pixel of one row pair, top pixel of the next
-                if (wn != 0.0f) {
-                    c.slot[i] = canon_slot((unsigned)dir, 1, dx);
-                    c.at[i] = lane_index(prm, f, cx, fp.y0 - 1);
-                    c.wb[i] = wn;
-                }
-                if (ws != 0.0f) {
-                    c.slot[i + 1] = canon_slot((unsigned)dir, -1, dx);
-                    c.at[i + 1] = lane_index(prm, f, cx, fp.y0 + 1);
-                    c.wt[i + 1] = ws;
-                }
+    for (int dx = 0; dx < 2; ++dx) {
+        const int i = dx * 2;
+        const int cx = fp.x0 + dx;
+        const float wn = (fp.ok >> dx & 1u) ? fp.w[dx] * a : 0.0f;               // north corner (cx, y0)
+        const float ws = (fp.ok >> (2 + dx) & 1u) ? fp.w[2 + dx] * a : 0.0f;     // south corner (cx, y0 + 1)
+        c.slot[i] = c.slot[i + 1] = -1;
+        c.at[i] = c.at[i + 1] = 0u;
+        c.wt[i] = c.wb[i] = c.wt[i + 1] = c.wb[i + 1] = 0.0f;
+        if (even) {          // both corners belong to one lane: one cell
+            if (wn != 0.0f || ws != 0.0f) {
+                c.slot[i] = canon_slot((unsigned)dir, 0, dx);
+                c.at[i] = lane_index(prm, f, cx, fp.y0);
+                c.wt[i] = wn; c.wb[i] = ws;
+            }
+        } else {             // bottom pixel of one row pair, top pixel of the next
+            if (wn != 0.0f) {
+                c.slot[i] = canon_slot((unsigned)dir, 1, dx);
+                c.at[i] = lane_index(prm, f, cx, fp.y0 - 1);
+                c.wb[i] = wn;
+            }
+            if (ws != 0.0f) {
+                c.slot[i + 1] = canon_slot((unsigned)dir, -1, dx);
+                c.at[i + 1] = lane_index(prm, f, cx, fp.y0 + 1);
+                c.wt[i + 1] = ws;
             }
         }
     }
 }
 
-// A cell whose canonical slot was taken (or: the lane's overflow slots): the next overflow slot of the lane, or,
-// beyond the list depth (a convergence point), the excess list: those pairs are added by fp32 reductions at L2
-// after the gather (heavy_excess_kernel), which leaves the flagged tile un-normalised for them.
+// A cell whose canonical slot was taken: the next overflow slot of the lane, or, beyond the list depth (a
+// convergence point), the excess list: those pairs are added by fp32 reductions at L2 after the gather
+// (heavy_excess_kernel), which leaves the flagged tile un-normalised for them.
 __device__ __forceinline__ void spill_cell(const GatherParams& prm, int f, unsigned at, unsigned src, float wt, float wb, unsigned xy)
 {
     const int so = kCanon + (int)atomicAdd(&prm.occ[at].y, 1u);
@@ -501,15 +486,21 @@ __device__ __forceinline__ void spill_cell(const GatherParams& prm, int f, unsig
     if (wb != 0.0f) { if (i < prm.excess_cap) __stcg(prm.excess + i, make_uint4(dpix + (unsigned)prm.W, src, __float_as_uint(wb), (unsigned)f)); }
 }
 
+// grid: (ceil(P / 256), 2 * frames): blockIdx.y = frame * 2 + direction.  Pixels with exactly zero motion carry
+// the marker in every frame and direction and leave after one load: what they receive from themselves is not a
+// list entry at all (rowgather_kernel makes it up from the lane's slot word, see static_lanes_kernel).
 __global__ void __launch_bounds__(256)
 insert_kernel(const GatherParams prm)
 {
-    const int f = blockIdx.y;
+    const int f = (int)(blockIdx.y >> 1), dir = (int)(blockIdx.y & 1u);
     const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= prm.P) return;
-    const int y = (int)(p / prm.W), x = (int)(p - (int64_t)y * prm.W);
+    const float* land = *prm.land_ref + ((int64_t)f * 4 + 2 * dir) * prm.P + p;
+    const float ox = __ldcs(land);
+    if (ox == kStaticLand) return;
+    const float oy = __ldcs(land + prm.P);
     SourceCells c;
-    source_cells(prm, *prm.land_ref + (int64_t)f * 4 * prm.P + p, f, x, y, c);
+    source_cells(prm, ox, oy, f, dir, c);
     // all claims are issued before the first answer is looked at: one atomic round trip per thread, not one per cell
     unsigned old[kCellsPerSource];
     #pragma unroll
@@ -517,6 +508,7 @@ insert_kernel(const GatherParams prm)
         old[i] = 0u;
         if (c.slot[i] >= 0) old[i] = atomicOr(&prm.occ[c.at[i]].x, 1u << c.slot[i]);
     }
+    const int y = (int)(p / prm.W), x = (int)(p - (int64_t)y * prm.W);
     const unsigned xy = pack_xy(x, y);
     #pragma unroll
     for (int i = 0; i < kCellsPerSource; ++i) {
@@ -712,12 +704,17 @@ rowgather_kernel(const GatherParams prm)
     const int64_t pair = (int64_t)f * prm.n_tiles * kPairsPerTile + (int64_t)tile * kPairsPerTile + pr;
     int kmax, my_hi;
     unsigned used = 0xffffffffu;          // register-resident slots of this lane that hold an entry
+    unsigned self = 0u;                   // direct index: the lane's top / bottom pixel receives itself (static_lanes_kernel)
     if (DIRECT) {
         const uint2 oc = __ldcg(prm.occ + pair * 32 + (tid & 31));
         const int n_ovf = (int)min(oc.y, (unsigned)(kListDepth - kCanon));      // the rest is in the excess list
-        my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz((int)oc.x);
+        const unsigned canon = oc.x & ((1u << kCanon) - 1u);
+        my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz((int)canon);
         kmax = __reduce_max_sync(0xffffffffu, my_hi);
-        used = oc.x | ((1u << min(n_ovf, kRegSlots - kCanon)) - 1u) << kCanon;
+        used = canon | ((1u << min(n_ovf, kRegSlots - kCanon)) - 1u) << kCanon;
+        self = oc.x & (kSelfTop | kSelfBottom);
+        if (self & kSelfTop) used &= ~1u;          // slots 0 / 1 of a static pixel hold no entry: made up below
+        if (self & kSelfBottom) used &= ~2u;
     } else {
         kmax = my_hi = (int)__ldg(prm.row_k + pair);
     }
@@ -740,6 +737,14 @@ rowgather_kernel(const GatherParams prm)
         pk[k] = e.x & kPixelMask;
         wt[k] = __uint_as_float(e.y);
         wb[k] = __uint_as_float(e.z);
+    }
+    if (DIRECT) {
+        // a pixel with exactly zero motion receives itself with weight a + (1 - a): its forward and backward splat
+        // both land exactly on it (slot 0: the top pixel, slot 1: the bottom pixel; never inserted, see insert_kernel)
+        const float a_f = prm.alphas.a[f];
+        const float w_self = a_f + (1.0f - a_f);
+        if (self & kSelfTop) { pk[0] = (unsigned)pix; wt[0] = w_self; wb[0] = 0.0f; }
+        if (self & kSelfBottom) { pk[1] = (unsigned)pix + (unsigned)prm.W; wb[1] = w_self; }
     }
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
     int nz[2] = {0, 0};
@@ -1265,17 +1270,25 @@ overflow_scatter_kernel(const GatherParams prm)
     for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += (int64_t)gridDim.x * 256) {
         const int f = (int)(i0 / prm.P);
         const int64_t p = i0 - (int64_t)f * prm.P;
-        const int y = (int)(p / prm.W), x = (int)(p - (int64_t)y * prm.W);
-        SourceCells c;
-        source_cells(prm, *prm.land_ref + (int64_t)f * 4 * prm.P + p, f, x, y, c);
+        const float* land = *prm.land_ref + (int64_t)f * 4 * prm.P + p;
+        if (__ldcs(land) == kStaticLand) {        // a pixel with zero motion receives itself with weight a + (1 - a)
+            const float a_f = prm.alphas.a[f];
+            red_pair<NT>(prm, f, p, (unsigned)p, a_f + (1.0f - a_f));
+            continue;
+        }
         #pragma unroll 1
-        for (int j = 0; j < 2 * kCellsPerSource; ++j) {       // (cell, row): not unrolled -- this path is never hot
-            const int i = j >> 1;
-            const float w = (j & 1) ? c.wb[i] : c.wt[i];
-            if (c.slot[i] < 0 || w == 0.0f) continue;
-            int cx, ytop;
-            lane_pixel(prm, c.at[i], cx, ytop);
-            red_pair<NT>(prm, f, (int64_t)(ytop + (j & 1)) * prm.W + cx, (unsigned)p, w);
+        for (int dir = 0; dir < 2; ++dir) {
+            SourceCells c;
+            source_cells(prm, __ldcs(land + 2 * dir * prm.P), __ldcs(land + (2 * dir + 1) * prm.P), f, dir, c);
+            #pragma unroll 1
+            for (int j = 0; j < 2 * kCellsPerSource; ++j) {       // (cell, row): not unrolled -- this path is never hot
+                const int i = j >> 1;
+                const float w = (j & 1) ? c.wb[i] : c.wt[i];
+                if (c.slot[i] < 0 || w == 0.0f) continue;
+                int cx, ytop;
+                lane_pixel(prm, c.at[i], cx, ytop);
+                red_pair<NT>(prm, f, (int64_t)(ytop + (j & 1)) * prm.W + cx, (unsigned)p, w);
+            }
         }
     }
 }
@@ -1417,7 +1430,7 @@ extern "C" int slr_clip_expand(const void* scene, const float* motion, int64_t C
                                nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes);
     if (rc) return rc;
     if (prm.direct) {
-        insert_kernel<<<dim3((unsigned)((prm.P + 255) / 256), (unsigned)n_frames), 256, 0, (cudaStream_t)stream_>>>(prm);
+        insert_kernel<<<dim3((unsigned)((prm.P + 255) / 256), 2u * (unsigned)n_frames), 256, 0, (cudaStream_t)stream_>>>(prm);
         return SLR_LAUNCH_STATUS();
     }
     const int per_cta = prm.staged ? kStageFrames : 1;

@@ -270,6 +270,37 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
     }
 }
 
+// Slot words of one frame's lanes before any source is inserted (a function of the motion field only: built once
+// per clip table, copied into every frame of a batch by occ_fill_kernel).  A lane whose top (bottom) pixel has
+// exactly zero motion receives that pixel itself with weight a + (1 - a) in canonical slot 0 (1): the slot is
+// marked taken (a moving source that maps to it goes to the overflow slots, as it always did) and flagged as a
+// self entry, which rowgather_kernel makes up instead of loading it.
+__global__ void __launch_bounds__(256)
+static_lanes_kernel(const float* __restrict__ motion, uint2* __restrict__ occ0, int H, int W, int tiles_x, int n_tiles)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;           // (row pair of the frame) * 32 + lane
+    if (i >= (int64_t)n_tiles * kPairsPerTile * 32) return;
+    const int64_t P = (int64_t)H * W;
+    const int pair = (int)(i >> 5), tile = pair / kPairsPerTile;
+    const int X = (tile % tiles_x) * TW + (int)(i & 31), Y = (tile / tiles_x) * TH + 2 * (pair % kPairsPerTile);
+    unsigned m = 0u;
+    if (X < W && Y < H) {
+        const int64_t px = (int64_t)Y * W + X;
+        if (__ldg(motion + px) == 0.0f && __ldg(motion + P + px) == 0.0f) m |= 1u | kSelfTop;
+        if (Y + 1 < H && __ldg(motion + px + W) == 0.0f && __ldg(motion + P + px + W) == 0.0f) m |= 2u | kSelfBottom;
+    }
+    occ0[i] = make_uint2(m, 0u);
+}
+
+__global__ void __launch_bounds__(256)
+occ_fill_kernel(const uint2* __restrict__ occ0, uint2* __restrict__ occ, int64_t per_frame, int n_frames)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= per_frame) return;
+    const uint2 v = __ldg(occ0 + i);
+    for (int f = 0; f < n_frames; ++f) __stcg(occ + (int64_t)f * per_frame + i, v);
+}
+
 }  // namespace slr
 
 // ===========================================================================
@@ -339,9 +370,11 @@ int build_table(const float* motion, int64_t H, int64_t W, int start, int end, i
     const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
     const int n_tiles = tiles_x * tiles_y;
     const unsigned pblocks = (unsigned)((P + 255) / 256);
-    if (slr_host::index_direct()) {        // landing coordinates only: insert_kernel needs no bins
+    if (slr_host::index_direct()) {        // landing coordinates and the lanes' initial slot words: insert_kernel needs no bins
         euler_table_kernel<false><<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
                                                           tab.land, tab.counts, tiles_x, n_tiles);
+        const int64_t lanes = (int64_t)n_tiles * kPairsPerTile * 32;
+        static_lanes_kernel<<<(unsigned)((lanes + 255) / 256), 256, 0, s>>>(motion, tab.occ0, (int)H, (int)W, tiles_x, n_tiles);
         return SLR_LAUNCH_STATUS();
     }
     SLR_CUDA(cudaMemsetAsync(tab.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
@@ -359,10 +392,11 @@ __global__ void bind_batch_kernel(const float** land_ref, const float* land, uns
     if (threadIdx.x == 0) { *land_ref = land; *flag_count = 0u; *excess_count = 0u; }
 }
 
-int bind_batch(const float* land, int64_t H, int64_t W, int n_frames, const Workspace& ws, cudaStream_t s)
+int bind_batch(const float* land, const uint2* occ0, int64_t H, int64_t W, int n_frames, const Workspace& ws, cudaStream_t s)
 {
     const int n_tiles = (int)(((W + TW - 1) / TW) * ((H + TH - 1) / TH));
-    SLR_CUDA(cudaMemsetAsync(ws.occ, 0, sizeof(uint2) * 32 * (size_t)n_tiles * kPairsPerTile * n_frames, s));
+    const int64_t lanes = (int64_t)n_tiles * kPairsPerTile * 32;
+    occ_fill_kernel<<<(unsigned)((lanes + 255) / 256), 256, 0, s>>>(occ0, ws.occ, lanes, n_frames);
     SLR_CUDA(cudaMemsetAsync(ws.tile_flag, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
     bind_batch_kernel<<<1, 32, 0, s>>>(ws.land_ref, land, ws.flag_count, ws.excess_count);
     return SLR_LAUNCH_STATUS();
@@ -417,7 +451,7 @@ extern "C" int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, in
     const Workspace ws = carve(workspace, H, W, n_frames);
     SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_bin: workspace too small (see slr_clip_workspace_bytes)");
     cudaStream_t s = (cudaStream_t)stream_;
-    if (slr_host::index_direct()) return bind_batch(tab.land + (size_t)f0 * 4 * P, H, W, n_frames, ws, s);
+    if (slr_host::index_direct()) return bind_batch(tab.land + (size_t)f0 * 4 * P, tab.occ0, H, W, n_frames, ws, s);
     // the batch's own copy of its bin offsets (expand / gather / heavy read them from the workspace);
     // the fill cursors start at zero
     SLR_CUDA(cudaMemcpyAsync(ws.offsets, tab.offsets + (size_t)f0 * (n_tiles + 1),
@@ -438,9 +472,9 @@ extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int star
     cudaStream_t s = (cudaStream_t)stream_;
     // the table of exactly this batch lives in the workspace itself
     slr_host::ClipTable tab;
-    tab.land = ws.land; tab.counts = ws.counts; tab.offsets = ws.offsets; tab.bytes = 0;
+    tab.land = ws.land; tab.counts = ws.counts; tab.offsets = ws.offsets; tab.occ0 = ws.occ0; tab.bytes = 0;
     const int rc = build_table(motion, H, W, start, end, t0, n_frames, tab, s);
     if (rc) return rc;
-    if (slr_host::index_direct()) return bind_batch(ws.land, H, W, n_frames, ws, s);
+    if (slr_host::index_direct()) return bind_batch(ws.land, ws.occ0, H, W, n_frames, ws, s);
     return fill_bins(ws.land, H, W, n_frames, ws, s);       // bin_scan left the counts at zero: they are the cursors
 }

@@ -310,7 +310,9 @@ class JointSplat:
         bin sizes) for frames t0 .. t0+n-1 of the clip [start, end], built once on `side` and cached:
         later calls for any sub-range of it only cut their batches from it (slr_clip_bin)."""
         tb = self._table
-        if tb is not None and tb["clip"] == (start, end) and tb["t0"] <= t0 and t0 + n <= tb["t0"] + tb["n"]:
+        mode = os.environ.get("SLR_GATHER_MODE", "ldg")      # what a table holds depends on how the lists are built
+        if tb is not None and tb["clip"] == (start, end) and tb["t0"] <= t0 and t0 + n <= tb["t0"] + tb["n"] \
+                and tb["mode"] == mode:
             return tb
         nbytes = _lib.load().slr_clip_table_bytes(self.H, self.W, n)
         if tb is not None:                      # the old table goes back to the pool right away
@@ -328,7 +330,7 @@ class JointSplat:
             ready.record(side)
         _BufferPool.used(entry, side, ready)
         tb = self._table = {"clip": (start, end), "t0": t0, "n": n, "buf": buf, "bytes": nbytes,
-                            "ready": ready, "entry": entry}
+                            "ready": ready, "entry": entry, "mode": mode}
         return tb
 
     def prepare_clip(self, start, end, t0=None, n=None):
