@@ -27,6 +27,12 @@ constexpr int kListDepth = SLR_LIST_DEPTH;   // slots per lane in the global lis
 
 struct FrameAlphas { float a[kMaxFrames]; };
 
+// Direct index: what a batch workspace refers to instead of copying it (both live in the clip table)
+struct BatchRefs {
+    const float* land;         // landing coordinates [frames][2 dirs][2][P] of the batch's first frame
+    const unsigned* moving;    // [0] = number of 256-pixel blocks in which something moves, [1 ...] = those blocks
+};
+
 // Staging plan of one (destination tile, frame pair), written by expand_kernel and executed by
 // stagegather_kernel: which rows of blocks of the Q region to copy where in shared memory.
 constexpr int kStageFrames = 2;                      // frames that share one staged source region
@@ -48,9 +54,12 @@ struct StageRecord {
 // forward and the backward sources of a tile lie a whole displacement apart):
 constexpr int kSetShift = 28;                       // H * W < 2^27: the bits above are free
 constexpr unsigned kPixelMask = (1u << kSetShift) - 1u;
-// Direct index: the slot word of a lane (Workspace::occ) -- bits 0 .. kCanon-1: canonical slot in use; bits 30 / 31:
-// the lane's top / bottom pixel has zero motion and receives itself (slot 0 / 1 is then reserved, holds no entry)
-constexpr unsigned kSelfTop = 1u << 30, kSelfBottom = 1u << 31;
+// Direct index: the slot mask of a lane (16 bits; two lanes share a 32-bit word of Workspace::slot_mask, so the
+// atomic claims of a warp touch 64 bytes: on B200 the claims are bound by the sectors the L2 atomic units see) --
+// bits 0 .. kCanon-1: canonical slot in use; bits 14 / 15: the lane's top / bottom pixel has zero motion and
+// receives itself (slot 0 / 1 is then reserved and holds no entry)
+constexpr unsigned kSelfTop = 1u << 14, kSelfBottom = 1u << 15;
+__host__ __device__ __forceinline__ unsigned lane_mask_shift(unsigned at) { return (at & 1u) << 4; }     // of lane `at` in word at >> 1
 enum SourceSet { kSetForward = 0, kSetBackward = 1, kSetSelf = 2, kSets = 3 };   // self: static pixels receive themselves
 
 __host__ __device__ __forceinline__ unsigned pack_xy(int x, int y) { return (unsigned)y << 16 | (unsigned)x; }
@@ -187,9 +196,11 @@ struct Workspace {
     unsigned* excess_count; // [1]
     unsigned excess_cap;
     float* heavy_sums;    // [n][3][P]           (tail..., norm) sums of flagged tiles
-    uint2* occ;           // [n][n_tiles * 4][32] direct index: per lane (canonical slots in use, overflow slots claimed)
-    uint2* occ0;          // [n_tiles * 4][32]   direct index, slr_clip_plan only: the initial slot words (else in the clip table)
-    const float** land_ref;   // [1]              direct index: where the landing coordinates of the batch's first frame are
+    unsigned* slot_mask;  // [n][n_tiles * 4][16] direct index: per lane 16 bits (canonical slots in use, self flags)
+    unsigned* slot_over;  // [n][n_tiles * 4][32] direct index: per lane, overflow slots claimed
+    unsigned* mask0;      // [n_tiles * 4][16]   direct index, slr_clip_plan only: the initial slot masks (else in the clip table)
+    unsigned* moving;     // [1 + ceil(P / 256)] direct index, slr_clip_plan only: the moving blocks (else in the clip table)
+    slr::BatchRefs* refs; // [1]                 direct index: where the batch's landing coordinates / moving blocks are
     size_t bytes;
 };
 
@@ -202,7 +213,8 @@ struct ClipTable {
     float* land;          // [n][2 dirs][2][P]   landing coordinates
     unsigned* counts;     // [n][n_tiles]        entries per destination tile (zero again after the scan)
     unsigned* offsets;    // [n][n_tiles + 1]    bin offsets
-    uint2* occ0;          // [n_tiles * 4][32]   direct index: the lanes' slot words before any source is inserted
+    unsigned* mask0;      // [n_tiles * 4][16]   direct index: the lanes' slot masks before any source is inserted
+    unsigned* moving;     // [1 + ceil(P / 256)] direct index: count, then the 256-pixel blocks in which something moves
     size_t bytes;
 };
 
@@ -217,7 +229,8 @@ inline ClipTable carve_table(void* base, int64_t H, int64_t W, int n)
     t.land = (float*)(p + o);        o += align_up(sizeof(float) * 4 * P * n);
     t.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
     t.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
-    t.occ0 = (uint2*)(p + o);        o += align_up(sizeof(uint2) * 32 * (size_t)(tiles * kPairsPerTile));
+    t.mask0 = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * 16 * (size_t)(tiles * kPairsPerTile));
+    t.moving = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * (size_t)(1 + (P + 255) / 256));
     t.bytes = o;
     return t;
 }
@@ -247,9 +260,11 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.excess = (uint4*)(p + o);      o += align_up(sizeof(uint4) * (size_t)w.excess_cap);
     w.excess_count = (unsigned*)(p + o); o += align_up(sizeof(unsigned));
     w.heavy_sums = (float*)(p + o);  o += align_up(sizeof(float) * 3 * P * n);
-    w.occ = (uint2*)(p + o);         o += direct ? align_up(sizeof(uint2) * 32 * (size_t)(tiles * kPairsPerTile) * n) : 0;
-    w.occ0 = (uint2*)(p + o);        o += direct ? align_up(sizeof(uint2) * 32 * (size_t)(tiles * kPairsPerTile)) : 0;
-    w.land_ref = (const float**)(p + o); o += align_up(sizeof(float*));
+    w.slot_mask = (unsigned*)(p + o); o += direct ? align_up(sizeof(unsigned) * 16 * (size_t)(tiles * kPairsPerTile) * n) : 0;
+    w.slot_over = (unsigned*)(p + o); o += direct ? align_up(sizeof(unsigned) * 32 * (size_t)(tiles * kPairsPerTile) * n) : 0;
+    w.mask0 = (unsigned*)(p + o);    o += direct ? align_up(sizeof(unsigned) * 16 * (size_t)(tiles * kPairsPerTile)) : 0;
+    w.moving = (unsigned*)(p + o);   o += direct ? align_up(sizeof(unsigned) * (size_t)(1 + (P + 255) / 256)) : 0;
+    w.refs = (slr::BatchRefs*)(p + o); o += align_up(sizeof(slr::BatchRefs));
     w.bytes = o;
     return w;
 }

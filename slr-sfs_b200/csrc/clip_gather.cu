@@ -82,9 +82,10 @@ struct GatherParams {
     int n_tail;                // scalar planes of S besides the normaliser
     int staged;                // expand_kernel: plan the staging (stagegather_kernel follows) or not (rowgather_kernel for all)
     StageRecord* records;      // [frame pairs][n_tiles] staging plans
-    uint2* occ;                // direct index: [frames][n_tiles * 4][32] per lane (bit k: canonical slot k in use, overflow slots claimed)
-    const float* const* land_ref;   // direct index: -> landing coordinates [frames][2 dirs][2][P] of the batch (in the clip table)
-    int direct;                // lists built by insert_kernel (no bins, no row_k: the gather reads `occ`)
+    unsigned* slot_mask;       // direct index: [frames][n_tiles * 4][16] per lane 16 bits (bit k: canonical slot k in use; self flags)
+    unsigned* slot_over;       // direct index: [frames][n_tiles * 4][32] per lane, overflow slots claimed
+    const BatchRefs* refs;     // direct index: where the batch's landing coordinates and moving-block list are (in the clip table)
+    int direct;                // lists built by insert_kernel (no bins, no row_k: the gather reads the slot masks)
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
     float* mask;               // [frames][P] norm > eps, or NULL
@@ -401,6 +402,9 @@ expand_kernel(const GatherParams prm)
 // exactly like expand_kernel does it.  Cells of the 32 consecutive sources a warp holds are consecutive
 // 16-byte entries of one slot row in regular flow: 512-byte stores, one atomic request per 128-byte line.
 // ---------------------------------------------------------------------------
+#ifndef SLR_INSERT_STORE
+#define SLR_INSERT_STORE __stcs        // measured against __stcg: profiles/r02 (direct4_*)
+#endif
 constexpr int kCellsPerSource = 4;      // per direction: 2 columns x (north-or-both cell, south cell)
 
 // The list cells one source pixel writes for one direction of one frame.  Cell i is unused when slot[i] < 0.
@@ -463,17 +467,10 @@ __device__ __forceinline__ void source_cells(const GatherParams& prm, float ox, 
     }
 }
 
-// A cell whose canonical slot was taken: the next overflow slot of the lane, or, beyond the list depth (a
-// convergence point), the excess list: those pairs are added by fp32 reductions at L2 after the gather
-// (heavy_excess_kernel), which leaves the flagged tile un-normalised for them.
-__device__ __forceinline__ void spill_cell(const GatherParams& prm, int f, unsigned at, unsigned src, float wt, float wb, unsigned xy)
+// A cell beyond the list depth (a convergence point): its pairs go to the excess list and are added by fp32
+// reductions at L2 after the gather (heavy_excess_kernel), which leaves the flagged tile un-normalised for them.
+__device__ __forceinline__ void excess_cell(const GatherParams& prm, int f, unsigned at, unsigned src, float wt, float wb)
 {
-    const int so = kCanon + (int)atomicAdd(&prm.occ[at].y, 1u);
-    if (so < kListDepth) {
-        __stcg(prm.lists + ((int64_t)(at >> 5) * kListDepth + so) * 32 + (at & 31u),
-               make_uint4(src, __float_as_uint(wt), __float_as_uint(wb), xy));
-        return;
-    }
     int cx, ytop;
     lane_pixel(prm, at, cx, ytop);
     const int tile = (ytop / TH) * prm.tiles_x + cx / TW;
@@ -492,30 +489,42 @@ __device__ __forceinline__ void spill_cell(const GatherParams& prm, int f, unsig
 __global__ void __launch_bounds__(256)
 insert_kernel(const GatherParams prm)
 {
+    // only the blocks of 256 pixels in which something moves (euler_table_kernel lists them): the others leave at once
+    const unsigned* moving = prm.refs->moving;
+    if (blockIdx.x >= moving[0]) return;
     const int f = (int)(blockIdx.y >> 1), dir = (int)(blockIdx.y & 1u);
-    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t p = (int64_t)moving[1 + blockIdx.x] * 256 + threadIdx.x;
     if (p >= prm.P) return;
-    const float* land = *prm.land_ref + ((int64_t)f * 4 + 2 * dir) * prm.P + p;
-    const float ox = __ldcs(land);
+    const float* land = prm.refs->land + ((int64_t)f * 4 + 2 * dir) * prm.P + p;
+    const float ox = __ldcs(land), oy = __ldcs(land + prm.P);     // both before the test: one memory latency, not two
     if (ox == kStaticLand) return;
-    const float oy = __ldcs(land + prm.P);
     SourceCells c;
     source_cells(prm, ox, oy, f, dir, c);
-    // all claims are issued before the first answer is looked at: one atomic round trip per thread, not one per cell
-    unsigned old[kCellsPerSource];
+    // Three rounds, each issued for all the thread's cells before the first answer is looked at (a warp pays one
+    // memory latency per round, not one per cell): claim the canonical slots; the cells that lost theirs (the flow
+    // compresses there: in the benchmark scene some lane of two warps in three) take an overflow slot; store.
+    unsigned old[kCellsPerSource], ovf[kCellsPerSource];
     #pragma unroll
     for (int i = 0; i < kCellsPerSource; ++i) {
         old[i] = 0u;
-        if (c.slot[i] >= 0) old[i] = atomicOr(&prm.occ[c.at[i]].x, 1u << c.slot[i]);
+        if (c.slot[i] >= 0) old[i] = atomicOr(&prm.slot_mask[c.at[i] >> 1], (1u << c.slot[i]) << lane_mask_shift(c.at[i]));
+    }
+    #pragma unroll
+    for (int i = 0; i < kCellsPerSource; ++i) {
+        ovf[i] = 0xffffffffu;          // "kept the canonical slot"
+        if (c.slot[i] >= 0 && (old[i] >> lane_mask_shift(c.at[i]) >> c.slot[i] & 1u)) ovf[i] = atomicAdd(&prm.slot_over[c.at[i]], 1u);
     }
     const int y = (int)(p / prm.W), x = (int)(p - (int64_t)y * prm.W);
     const unsigned xy = pack_xy(x, y);
     #pragma unroll
     for (int i = 0; i < kCellsPerSource; ++i) {
         if (c.slot[i] < 0) continue;
-        if (old[i] >> c.slot[i] & 1u) spill_cell(prm, f, c.at[i], (unsigned)p, c.wt[i], c.wb[i], xy);
-        else __stcg(prm.lists + ((int64_t)(c.at[i] >> 5) * kListDepth + c.slot[i]) * 32 + (c.at[i] & 31u),
-                    make_uint4((unsigned)p, __float_as_uint(c.wt[i]), __float_as_uint(c.wb[i]), xy));
+        const int so = ovf[i] == 0xffffffffu ? c.slot[i] : (int)min(ovf[i], (unsigned)kListDepth) + kCanon;
+        // streaming stores: the lists (40 MB per frame, next read by the gather) need not stay in L2
+        if (so < kListDepth)
+            SLR_INSERT_STORE(prm.lists + ((int64_t)(c.at[i] >> 5) * kListDepth + so) * 32 + (c.at[i] & 31u),
+                             make_uint4((unsigned)p, __float_as_uint(c.wt[i]), __float_as_uint(c.wb[i]), xy));
+        else excess_cell(prm, f, c.at[i], (unsigned)p, c.wt[i], c.wb[i]);
     }
 }
 
@@ -681,7 +690,7 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
 // displacement, so with F > 1 they share most of their lines in this SM's L1 as well (the
 // frame-fastest CTA order already shares them in L2).  R < 4 splits a tile's row pairs over CTAs.
 // DIRECT: the lists were written by insert_kernel: which slots of a lane hold an entry is in its slot word
-// (GatherParams::occ), the others were never written and read as the all-zero pixel.
+// (GatherParams::slot_mask), the others were never written and read as the all-zero pixel.
 template <int NT, int F, int R, bool NZ, bool DIRECT>
 __global__ void __launch_bounds__(32 * F * R, (SLR_GATHER_MINBLOCKS * kCols) / (32 * F * R))
 rowgather_kernel(const GatherParams prm)
@@ -706,13 +715,14 @@ rowgather_kernel(const GatherParams prm)
     unsigned used = 0xffffffffu;          // register-resident slots of this lane that hold an entry
     unsigned self = 0u;                   // direct index: the lane's top / bottom pixel receives itself (static_lanes_kernel)
     if (DIRECT) {
-        const uint2 oc = __ldcg(prm.occ + pair * 32 + (tid & 31));
-        const int n_ovf = (int)min(oc.y, (unsigned)(kListDepth - kCanon));      // the rest is in the excess list
-        const unsigned canon = oc.x & ((1u << kCanon) - 1u);
+        const unsigned at = (unsigned)(pair * 32 + (tid & 31));
+        const unsigned mask = __ldcg(prm.slot_mask + (at >> 1)) >> lane_mask_shift(at);
+        const int n_ovf = (int)min(__ldcg(prm.slot_over + at), (unsigned)(kListDepth - kCanon));      // the rest is in the excess list
+        const unsigned canon = mask & ((1u << kCanon) - 1u);
         my_hi = n_ovf > 0 ? kCanon + n_ovf : 32 - __clz((int)canon);
         kmax = __reduce_max_sync(0xffffffffu, my_hi);
         used = canon | ((1u << min(n_ovf, kRegSlots - kCanon)) - 1u) << kCanon;
-        self = oc.x & (kSelfTop | kSelfBottom);
+        self = mask & (kSelfTop | kSelfBottom);
         if (self & kSelfTop) used &= ~1u;          // slots 0 / 1 of a static pixel hold no entry: made up below
         if (self & kSelfBottom) used &= ~2u;
     } else {
@@ -1270,7 +1280,7 @@ overflow_scatter_kernel(const GatherParams prm)
     for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < total; i0 += (int64_t)gridDim.x * 256) {
         const int f = (int)(i0 / prm.P);
         const int64_t p = i0 - (int64_t)f * prm.P;
-        const float* land = *prm.land_ref + (int64_t)f * 4 * prm.P + p;
+        const float* land = prm.refs->land + (int64_t)f * 4 * prm.P + p;
         if (__ldcs(land) == kStaticLand) {        // a pixel with zero motion receives itself with weight a + (1 - a)
             const float a_f = prm.alphas.a[f];
             red_pair<NT>(prm, f, p, (unsigned)p, a_f + (1.0f - a_f));
@@ -1338,7 +1348,7 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     // the plan packs a source row into 14 bits and a column into 16 (plan_key)
     prm.staged = slr_host::gather_staged() && H <= 16384 && W <= 65535 ? 1 : 0;
     prm.direct = slr_host::index_direct() ? 1 : 0;
-    prm.occ = ws.occ; prm.land_ref = ws.land_ref;
+    prm.slot_mask = ws.slot_mask; prm.slot_over = ws.slot_over; prm.refs = ws.refs;
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;
     prm.flag_list = ws.flag_list; prm.flag_count = ws.flag_count; prm.heavy_sums = ws.heavy_sums;

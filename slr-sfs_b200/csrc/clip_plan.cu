@@ -118,7 +118,7 @@ __device__ __forceinline__ void euler_step(EulerState& s, const float* __restric
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
 euler_table_kernel(const float* __restrict__ motion, int H, int W, int steps_f0, int steps_b0, int n,
-                   float* __restrict__ land, unsigned* __restrict__ counts, int tiles_x, int n_tiles)
+                   float* __restrict__ land, unsigned* __restrict__ counts, int tiles_x, int n_tiles, unsigned* __restrict__ moving)
 {
     const int64_t P = (int64_t)H * W;
     const int64_t p_raw = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -133,6 +133,10 @@ euler_table_kernel(const float* __restrict__ motion, int H, int W, int steps_f0,
     // not binned at all: the gather adds their self-contribution implicitly.  Their landing
     // entry is a far-away marker, which the count and fill passes skip like any off-frame pixel.
     const bool is_static = __ldg(motion + p) == 0.0f && __ldg(motion + P + p) == 0.0f;
+    if (!COUNT) {        // direct index: insert_kernel only visits the blocks in which something moves
+        const int any = __syncthreads_or(active && !is_static);
+        if (any && threadIdx.x == 0) moving[1u + atomicAdd(moving, 1u)] = blockIdx.x;
+    }
     if (__all_sync(0xffffffffu, is_static || !active)) {
         if (active)
             for (int i = 0; i < 4 * n; ++i) land[(int64_t)i * P + p] = kStaticLand;
@@ -270,35 +274,46 @@ bin_fill_kernel(const float* __restrict__ land, const unsigned* __restrict__ off
     }
 }
 
-// Slot words of one frame's lanes before any source is inserted (a function of the motion field only: built once
-// per clip table, copied into every frame of a batch by occ_fill_kernel).  A lane whose top (bottom) pixel has
+// Slot masks of one frame's lanes before any source is inserted (a function of the motion field only: built once
+// per clip table, copied into every frame of a batch by slot_fill_kernel).  A lane whose top (bottom) pixel has
 // exactly zero motion receives that pixel itself with weight a + (1 - a) in canonical slot 0 (1): the slot is
 // marked taken (a moving source that maps to it goes to the overflow slots, as it always did) and flagged as a
-// self entry, which rowgather_kernel makes up instead of loading it.
+// self entry, which rowgather_kernel makes up instead of loading it.  One thread per PAIR of lanes (one word).
 __global__ void __launch_bounds__(256)
-static_lanes_kernel(const float* __restrict__ motion, uint2* __restrict__ occ0, int H, int W, int tiles_x, int n_tiles)
+static_lanes_kernel(const float* __restrict__ motion, unsigned* __restrict__ mask0, int H, int W, int tiles_x, int n_tiles)
 {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;           // (row pair of the frame) * 32 + lane
-    if (i >= (int64_t)n_tiles * kPairsPerTile * 32) return;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;           // (row pair of the frame) * 16 + lane / 2
+    if (i >= (int64_t)n_tiles * kPairsPerTile * 16) return;
     const int64_t P = (int64_t)H * W;
-    const int pair = (int)(i >> 5), tile = pair / kPairsPerTile;
-    const int X = (tile % tiles_x) * TW + (int)(i & 31), Y = (tile / tiles_x) * TH + 2 * (pair % kPairsPerTile);
-    unsigned m = 0u;
-    if (X < W && Y < H) {
-        const int64_t px = (int64_t)Y * W + X;
-        if (__ldg(motion + px) == 0.0f && __ldg(motion + P + px) == 0.0f) m |= 1u | kSelfTop;
-        if (Y + 1 < H && __ldg(motion + px + W) == 0.0f && __ldg(motion + P + px + W) == 0.0f) m |= 2u | kSelfBottom;
+    const int pair = (int)(i >> 4), tile = pair / kPairsPerTile;
+    const int Y = (tile / tiles_x) * TH + 2 * (pair % kPairsPerTile);
+    unsigned word = 0u;
+    #pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int X = (tile % tiles_x) * TW + 2 * (int)(i & 15) + h;
+        unsigned m = 0u;
+        if (X < W && Y < H) {
+            const int64_t px = (int64_t)Y * W + X;
+            if (__ldg(motion + px) == 0.0f && __ldg(motion + P + px) == 0.0f) m |= 1u | kSelfTop;
+            if (Y + 1 < H && __ldg(motion + px + W) == 0.0f && __ldg(motion + P + px + W) == 0.0f) m |= 2u | kSelfBottom;
+        }
+        word |= m << (16 * h);
     }
-    occ0[i] = make_uint2(m, 0u);
+    mask0[i] = word;
 }
 
+// masks <- the initial masks, overflow counts <- 0, for every frame of the batch
 __global__ void __launch_bounds__(256)
-occ_fill_kernel(const uint2* __restrict__ occ0, uint2* __restrict__ occ, int64_t per_frame, int n_frames)
+slot_fill_kernel(const unsigned* __restrict__ mask0, unsigned* __restrict__ slot_mask, unsigned* __restrict__ slot_over,
+                 int64_t words_per_frame, int n_frames)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= per_frame) return;
-    const uint2 v = __ldg(occ0 + i);
-    for (int f = 0; f < n_frames; ++f) __stcg(occ + (int64_t)f * per_frame + i, v);
+    if (i >= words_per_frame) return;
+    const unsigned v = __ldg(mask0 + i);
+    for (int f = 0; f < n_frames; ++f) {
+        __stcg(slot_mask + (int64_t)f * words_per_frame + i, v);
+        __stcg(reinterpret_cast<uint2*>(slot_over) + (int64_t)f * words_per_frame + i, make_uint2(0u, 0u));
+    }
 }
 
 }  // namespace slr
@@ -371,15 +386,16 @@ int build_table(const float* motion, int64_t H, int64_t W, int start, int end, i
     const int n_tiles = tiles_x * tiles_y;
     const unsigned pblocks = (unsigned)((P + 255) / 256);
     if (slr_host::index_direct()) {        // landing coordinates and the lanes' initial slot words: insert_kernel needs no bins
+        SLR_CUDA(cudaMemsetAsync(tab.moving, 0, sizeof(unsigned), s));
         euler_table_kernel<false><<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
-                                                          tab.land, tab.counts, tiles_x, n_tiles);
-        const int64_t lanes = (int64_t)n_tiles * kPairsPerTile * 32;
-        static_lanes_kernel<<<(unsigned)((lanes + 255) / 256), 256, 0, s>>>(motion, tab.occ0, (int)H, (int)W, tiles_x, n_tiles);
+                                                          tab.land, tab.counts, tiles_x, n_tiles, tab.moving);
+        const int64_t words = (int64_t)n_tiles * kPairsPerTile * 16;
+        static_lanes_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(motion, tab.mask0, (int)H, (int)W, tiles_x, n_tiles);
         return SLR_LAUNCH_STATUS();
     }
     SLR_CUDA(cudaMemsetAsync(tab.counts, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
     euler_table_kernel<true><<<pblocks, 256, 0, s>>>(motion, (int)H, (int)W, t0 - start, end - t0 + 1, n_frames,
-                                                     tab.land, tab.counts, tiles_x, n_tiles);
+                                                     tab.land, tab.counts, tiles_x, n_tiles, nullptr);
     bin_scan_kernel<<<n_frames, 1024, 0, s>>>(tab.counts, tab.offsets, n_tiles);
     return SLR_LAUNCH_STATUS();
 }
@@ -387,18 +403,18 @@ int build_table(const float* motion, int64_t H, int64_t W, int start, int end, i
 // Direct index: a batch only REFERS to its landing coordinates (insert_kernel reads them where they are: in the
 // clip table, which must stay valid until the batch's slr_clip_heavy has run); its per-lane slot words, tile
 // flags and counters start at zero.
-__global__ void bind_batch_kernel(const float** land_ref, const float* land, unsigned* flag_count, unsigned* excess_count)
+__global__ void bind_batch_kernel(BatchRefs* refs, const float* land, const unsigned* moving, unsigned* flag_count, unsigned* excess_count)
 {
-    if (threadIdx.x == 0) { *land_ref = land; *flag_count = 0u; *excess_count = 0u; }
+    if (threadIdx.x == 0) { refs->land = land; refs->moving = moving; *flag_count = 0u; *excess_count = 0u; }
 }
 
-int bind_batch(const float* land, const uint2* occ0, int64_t H, int64_t W, int n_frames, const Workspace& ws, cudaStream_t s)
+int bind_batch(const float* land, const unsigned* mask0, const unsigned* moving, int64_t H, int64_t W, int n_frames, const Workspace& ws, cudaStream_t s)
 {
     const int n_tiles = (int)(((W + TW - 1) / TW) * ((H + TH - 1) / TH));
-    const int64_t lanes = (int64_t)n_tiles * kPairsPerTile * 32;
-    occ_fill_kernel<<<(unsigned)((lanes + 255) / 256), 256, 0, s>>>(occ0, ws.occ, lanes, n_frames);
+    const int64_t words = (int64_t)n_tiles * kPairsPerTile * 16;
+    slot_fill_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(mask0, ws.slot_mask, ws.slot_over, words, n_frames);
     SLR_CUDA(cudaMemsetAsync(ws.tile_flag, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
-    bind_batch_kernel<<<1, 32, 0, s>>>(ws.land_ref, land, ws.flag_count, ws.excess_count);
+    bind_batch_kernel<<<1, 32, 0, s>>>(ws.refs, land, moving, ws.flag_count, ws.excess_count);
     return SLR_LAUNCH_STATUS();
 }
 
@@ -451,7 +467,7 @@ extern "C" int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, in
     const Workspace ws = carve(workspace, H, W, n_frames);
     SLR_CHECK_ARGS(ws.bytes <= workspace_bytes, "slr_clip_bin: workspace too small (see slr_clip_workspace_bytes)");
     cudaStream_t s = (cudaStream_t)stream_;
-    if (slr_host::index_direct()) return bind_batch(tab.land + (size_t)f0 * 4 * P, tab.occ0, H, W, n_frames, ws, s);
+    if (slr_host::index_direct()) return bind_batch(tab.land + (size_t)f0 * 4 * P, tab.mask0, tab.moving, H, W, n_frames, ws, s);
     // the batch's own copy of its bin offsets (expand / gather / heavy read them from the workspace);
     // the fill cursors start at zero
     SLR_CUDA(cudaMemcpyAsync(ws.offsets, tab.offsets + (size_t)f0 * (n_tiles + 1),
@@ -472,9 +488,9 @@ extern "C" int slr_clip_plan(const float* motion, int64_t H, int64_t W, int star
     cudaStream_t s = (cudaStream_t)stream_;
     // the table of exactly this batch lives in the workspace itself
     slr_host::ClipTable tab;
-    tab.land = ws.land; tab.counts = ws.counts; tab.offsets = ws.offsets; tab.occ0 = ws.occ0; tab.bytes = 0;
+    tab.land = ws.land; tab.counts = ws.counts; tab.offsets = ws.offsets; tab.mask0 = ws.mask0; tab.moving = ws.moving; tab.bytes = 0;
     const int rc = build_table(motion, H, W, start, end, t0, n_frames, tab, s);
     if (rc) return rc;
-    if (slr_host::index_direct()) return bind_batch(ws.land, ws.occ0, H, W, n_frames, ws, s);
+    if (slr_host::index_direct()) return bind_batch(ws.land, ws.mask0, ws.moving, H, W, n_frames, ws, s);
     return fill_bins(ws.land, H, W, n_frames, ws, s);       // bin_scan left the counts at zero: they are the cursors
 }
