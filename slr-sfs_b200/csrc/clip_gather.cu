@@ -692,15 +692,14 @@ __device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsi
 // DIRECT: the lists were written by insert_kernel: which slots of a lane hold an entry is in its slot word
 // (GatherParams::slot_mask), the others were never written and read as the all-zero pixel.
 template <int NT, int F, int R, bool NZ, bool DIRECT>
-__global__ void __launch_bounds__(32 * F * R, (SLR_GATHER_MINBLOCKS * kCols) / (32 * F * R))
-rowgather_kernel(const GatherParams prm)
+__device__ __forceinline__ void rowgather_item(const GatherParams& prm, unsigned item)
 {
     constexpr int kParts = kPairsPerTile / R;           // CTAs per (tile, frame group)
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int n_fg = (prm.n_frames + F - 1) / F;
-    const int f = (int)(blockIdx.x % (unsigned)n_fg) * F + warp / R;
-    const int part = (int)(blockIdx.x / (unsigned)n_fg);
+    const int f = (int)(item % (unsigned)n_fg) * F + warp / R;
+    const int part = (int)(item / (unsigned)n_fg);
     const int tile = part / kParts, pr = (part % kParts) * R + warp % R;      // row pair within the tile
     if (f >= prm.n_frames) return;
     const unsigned flag = __ldg(prm.tile_flag + (int64_t)f * prm.n_tiles + tile);
@@ -785,6 +784,13 @@ rowgather_kernel(const GatherParams prm)
         if (prm.mask) prm.mask[(int64_t)f * P + px] = sum[NT] > prm.eps ? 1.0f : 0.0f;
         if (NZ) prm.nnz[(int64_t)f * P + px] = (float)nz[r];
     }
+}
+
+template <int NT, int F, int R, bool NZ, bool DIRECT>
+__global__ void __launch_bounds__(32 * F * R, (SLR_GATHER_MINBLOCKS * kCols) / (32 * F * R))
+rowgather_kernel(const GatherParams prm)
+{
+    rowgather_item<NT, F, R, NZ, DIRECT>(prm, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------
