@@ -178,9 +178,11 @@ size_t slr_clip_workspace_bytes(int64_t H, int64_t W, int n_frames);
  *        (layers/partialconv2d.py:61-66): nnz is exactly the per-pixel channel sum, so neither the
  *        per-element mask nor the all-ones mask convolution over C channels has to be materialised
  * workspace: slr_clip_workspace_bytes(H, W, n_frames) bytes, 16-byte aligned.
- * slr_clip_frames = slr_clip_plan (Euler chains, landing table, destination-tile
- * bins; depends on the motion only), slr_clip_expand (per-lane source lists of every
- * destination row pair; depends on the motion and the blend weights),
+ * slr_clip_frames = slr_clip_plan (Euler chains, landing table; with the bin pipeline also the
+ * destination-tile bins; depends on the motion only), slr_clip_expand (per-lane source lists of every
+ * destination row pair; depends on the motion and the blend weights.  Default: every moving source
+ * pixel writes its list cells straight into the lists of the destination lanes -- the "direct index";
+ * environment variable SLR_GATHER_MODE=bins|staged: from per-tile bins, tile by tile),
  * slr_clip_gather (the gather itself: every tile whose lists fit) and slr_clip_heavy
  * (the few tiles in convergence zones of the flow whose lists do not fit, by fp32
  * reductions at L2; touches only those tiles) on the same workspace and the same motion
@@ -216,7 +218,11 @@ int slr_clip_frames(const void* scene, const float* motion, int64_t C, int n_tai
  *   slr_clip_bin(table, ..., table_frames, f0, n, workspace)      bins of frames f0 .. f0+n-1 of the
  *                                                                 table (n <= 64) into a batch workspace
  * after which slr_clip_expand / slr_clip_gather / slr_clip_heavy run on that workspace with
- * t0 = (the table's t0) + f0 exactly as after slr_clip_plan. */
+ * t0 = (the table's t0) + f0 exactly as after slr_clip_plan.  With the direct index (default)
+ * slr_clip_bin does not copy anything out of the table: the workspace REFERS to the table's landing
+ * coordinates, so the table must stay valid and unchanged until the batch's slr_clip_heavy has run
+ * (the bin pipeline only needs it until slr_clip_bin has run).  A table and the workspaces cut from
+ * it must be used under the same SLR_GATHER_MODE they were built under. */
 size_t slr_clip_table_bytes(int64_t H, int64_t W, int n_frames);
 int slr_clip_table(const float* motion, int64_t H, int64_t W, int start, int end, int t0,
                    int n_frames, void* table, size_t table_bytes, slr_stream_t stream);
@@ -226,8 +232,9 @@ int slr_clip_bin(const void* table, size_t table_bytes, int64_t H, int64_t W, in
 /* Diagnostics (a `_host` call: copies counters and the tile flags to the host and synchronises
  * `stream`).  After slr_clip_expand on `workspace`: stats[0] = flagged destination tiles of the batch
  * (some lane's source list was cut at the list depth), stats[1] = of those, tiles done entirely by
- * per-pair reductions from their bins, stats[2] = (destination, source) pairs beyond the list
- * depth, stats[3] = capacity of that excess list, stats[4] (valid after slr_clip_gather) = tiles whose
+ * per-pair reductions from their bins (bin pipeline only), stats[2] = (destination, source) pairs beyond
+ * the list depth, stats[3] = capacity of that excess list (direct index: stats[2] > stats[3] means the
+ * whole batch was redone by scatter + divide inside slr_clip_heavy), stats[4] (valid after slr_clip_gather) = tiles whose
  * sources did not fit the shared-memory staging area and were gathered through L1 instead,
  * stats[5] = tiles x frames of the batch. */
 int slr_clip_stats_host(const void* workspace, size_t workspace_bytes, int64_t H, int64_t W, int n_frames,

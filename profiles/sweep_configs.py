@@ -52,15 +52,18 @@ def run(H, W, C=64, N=60, two_layer=False, batch=12, reps=3):
     ms_frame = e0.elapsed_time(e1) / (reps * N)
     P = H * W
     n_a, n_w, n_extra = (2, 3, 1) if two_layer else (0, 1, 0)
-    whole = 4.0 * P * (4 * C + 3 + n_a + 2 * n_w + n_extra)          # SURVEY 8d whole-path bytes per frame
+    whole = 4.0 * P * (4 * C + 3 + n_a + 2 * n_w + n_extra)          # SURVEY 8d whole-path bytes per frame (two passes)
+    floor = 4.0 * P * (2 * C + 3 + n_a + n_extra)                    # one pass: inputs once + outputs once
     return {"H": H, "W": W, "C": C, "two_layer": two_layer, "batch": batch, "frames_per_s": 1000.0 / ms_frame,
-            "us_per_frame": 1000.0 * ms_frame, "whole_path_MB_per_frame": whole / 1e6,
-            "whole_path_GBs": whole / ms_frame / 1e6, "whole_path_roofline_frac": whole / ms_frame / 1e6 / PEAK}
+            "us_per_frame": 1000.0 * ms_frame, "one_pass_floor_MB_per_frame": floor / 1e6,
+            "frac_one_pass_floor": floor / ms_frame / 1e6 / PEAK,
+            "two_pass_MB_per_frame": whole / 1e6, "frac_two_pass": whole / ms_frame / 1e6 / PEAK,
+            "workspace_MB_per_frame_of_batch": pkg._lib.load().slr_clip_workspace_bytes(H, W, 1) / 1e6}
 
 
 if __name__ == "__main__":
     rows = [run(768, 1024), run(768, 1024, two_layer=True)]
-    for (H, W, b) in [(256, 256, 12), (512, 512, 12), (1024, 1024, 8), (1536, 2048, 3)]:
+    for (H, W, b) in [(256, 256, 12), (512, 512, 12), (1024, 1024, 12), (1536, 2048, 12), (1536, 2048, 3)]:
         rows.append(run(H, W, batch=b))
     if "--batches" in sys.argv:      # small frames are launch-bound: fewer, larger batches (kMaxFrames = 64)
         for (H, W) in [(256, 256), (512, 512)]:
