@@ -24,14 +24,6 @@ constexpr int kCanon = 12;             // canonical slots (direction x source-ro
 #define SLR_LIST_DEPTH 96
 #endif
 constexpr int kListDepth = SLR_LIST_DEPTH;   // slots per lane in the global lists; deeper = heavy tile
-// Direct index: the first kShallowSlots slots of every lane have a fixed place ([row pair][slot][lane]: 8 KB per row
-// pair); the deeper ones (convergence zones only) live in blocks of kDeepSlots slots x 32 lanes that insert_kernel
-// takes from a pool when a row pair first needs them (Workspace::deep_tab: block per (row pair, 8 slots)).
-constexpr int kShallowSlots = 16;
-constexpr int kDeepSlots = 8;
-constexpr int kDeepBlocks = (kListDepth - kShallowSlots + kDeepSlots - 1) / kDeepSlots;    // per row pair
-static_assert(kListDepth >= kShallowSlots, "the list depth includes the shallow slots");
-constexpr unsigned kDeepLocked = 0xffffffffu, kDeepFull = 0xfffffffeu;      // deep_tab: being allocated / pool exhausted
 
 struct FrameAlphas { float a[kMaxFrames]; };
 
@@ -39,7 +31,6 @@ struct FrameAlphas { float a[kMaxFrames]; };
 struct BatchRefs {
     const float* land;         // landing coordinates [frames][2 dirs][2][P] of the batch's first frame
     const unsigned* moving;    // [0] = number of 256-pixel blocks in which something moves, [1 ...] = those blocks
-    unsigned deep_next;        // blocks of the deep-slot pool handed out so far
 };
 
 // Staging plan of one (destination tile, frame pair), written by expand_kernel and executed by
@@ -194,11 +185,7 @@ struct Workspace {
     unsigned* counts;     // [n][n_tiles]        entries per destination tile (then fill cursors)
     unsigned* offsets;    // [n][n_tiles + 1]    bin offsets
     float4* ent;          // [n][cap]            bin entries (pixel | dir << 31, landing x, landing y, -)
-    uint4* lists;         // [n][n_tiles * 4][kListDepth][32]  row-pair lists (source, w_top, w_bottom, -); direct index:
-                          // [n][n_tiles * 4][kShallowSlots][32], the deeper slots in deep_pool
-    unsigned* deep_tab;   // [n][n_tiles * 4][kDeepBlocks]  direct index: pool block + 1 of a row pair's slots 16 + 8 b .. (0: none)
-    uint4* deep_pool;     // [deep_blocks][kDeepSlots][32]   direct index: the pool
-    unsigned deep_blocks;
+    uint4* lists;         // [n][n_tiles * 4][kListDepth][32]  row-pair lists (source, w_top, w_bottom, -)
     unsigned* row_k;      // [n][n_tiles * 4]    slots in use per row pair
     unsigned* tile_flag;  // [n][n_tiles]        1 = heavy tile
     unsigned* fallback;   // [n][n_tiles]        1 = the tile's sources do not fit the staging area: rowgather_kernel does it
@@ -262,10 +249,7 @@ inline Workspace carve(void* base, int64_t H, int64_t W, int n)
     w.counts = (unsigned*)(p + o);   o += align_up(sizeof(unsigned) * tiles * n);
     w.offsets = (unsigned*)(p + o);  o += align_up(sizeof(unsigned) * (tiles + 1) * n);
     w.ent = (float4*)(p + o);        o += align_up(sizeof(float4) * cap * n);
-    w.lists = (uint4*)(p + o);       o += align_up(sizeof(uint4) * 32 * (direct ? kShallowSlots : kListDepth) * (size_t)(tiles * kPairsPerTile) * n);
-    w.deep_tab = (unsigned*)(p + o); o += direct ? align_up(sizeof(unsigned) * kDeepBlocks * (size_t)(tiles * kPairsPerTile) * n) : 0;
-    w.deep_blocks = direct ? (unsigned)std::min<int64_t>(((P + 63) / 64) * n, 1ll << 24) : 0u;     // one block per row pair on average (64 bytes per pixel and frame)
-    w.deep_pool = (uint4*)(p + o);   o += align_up(sizeof(uint4) * 32 * kDeepSlots * (size_t)w.deep_blocks);
+    w.lists = (uint4*)(p + o);       o += align_up(sizeof(uint4) * 32 * kListDepth * (size_t)(tiles * kPairsPerTile) * n);
     w.row_k = (unsigned*)(p + o);    o += align_up(sizeof(unsigned) * tiles * kPairsPerTile * n);
     w.tile_flag = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);
     w.fallback = (unsigned*)(p + o); o += align_up(sizeof(unsigned) * tiles * n);

@@ -45,7 +45,6 @@ namespace slr {
 #endif
 constexpr int kRegSlots = 16;          // list slots a lane keeps in registers; deeper ones are re-read per group
 constexpr int kSmemSlots = 16;         // list slots expand_kernel stages in shared memory (>= kCanon)
-static_assert(kRegSlots == kShallowSlots, "the gather's register-resident slots are the ones with a fixed place");
 static_assert(kSmemSlots >= kCanon && kSmemSlots <= kRegSlots, "shared list table: kCanon <= slots <= kRegSlots");
 constexpr int kCols = TW * kPairsPerTile;   // 128 lanes (columns of row pairs) per tile
 #ifndef SLR_HEAVY_GROUPS
@@ -66,10 +65,7 @@ struct GatherParams {
     const float4* ent;         // [frames][cap] bin entries
     const float* motion;       // [2][P]: a destination pixel with zero motion contributes to itself
     const unsigned* offsets;   // [frames][n_tiles + 1]
-    uint4* lists;              // [frames][n_tiles * 4][kListDepth][32]; direct index: [frames][n_tiles * 4][kShallowSlots][32]
-    unsigned* deep_tab;        // direct index: [frames][n_tiles * 4][kDeepBlocks] pool block + 1 holding a row pair's deeper slots
-    uint4* deep_pool;          // direct index: [deep_blocks][kDeepSlots][32]
-    unsigned deep_blocks;
+    uint4* lists;              // [frames][n_tiles * 4][kListDepth][32]
     unsigned* row_k;           // [frames][n_tiles * 4]    slots in use per row pair
     unsigned* tile_flag;       // [frames][n_tiles]: 0 normal, 1 = some lane's list was cut at kListDepth (the
                                // rest is in `excess`), 2 = excess list full: the whole tile goes the heavy way
@@ -88,7 +84,7 @@ struct GatherParams {
     StageRecord* records;      // [frame pairs][n_tiles] staging plans
     unsigned* slot_mask;       // direct index: [frames][n_tiles * 4][16] per lane 16 bits (bit k: canonical slot k in use; self flags)
     unsigned* slot_over;       // direct index: [frames][n_tiles * 4][32] per lane, overflow slots claimed
-    BatchRefs* refs;           // direct index: where the batch's landing coordinates and moving-block list are (in the clip table)
+    const BatchRefs* refs;     // direct index: where the batch's landing coordinates and moving-block list are (in the clip table)
     int direct;                // lists built by insert_kernel (no bins, no row_k: the gather reads the slot masks)
     float* out;                // [frames][C][P]
     float* aux;                // [frames][n_tail + 1][P] raw sums (tail..., norm) or NULL
@@ -471,35 +467,6 @@ __device__ __forceinline__ void source_cells(const GatherParams& prm, float ox, 
     }
 }
 
-// The pool block that holds slots kShallowSlots + kDeepSlots * b .. of row pair `pair`; the first thread that needs
-// it takes it from the pool (the others wait for the number to appear).  kDeepFull: the pool is exhausted.
-__device__ __forceinline__ unsigned deep_block(const GatherParams& prm, unsigned pair, int b)
-{
-    unsigned* t = prm.deep_tab + (size_t)pair * kDeepBlocks + b;
-    unsigned id = *reinterpret_cast<volatile unsigned*>(t);
-    if (id == 0u) {
-        const unsigned prev = atomicCAS(t, 0u, kDeepLocked);
-        if (prev == 0u) {
-            const unsigned k = atomicAdd(&prm.refs->deep_next, 1u);
-            id = k < prm.deep_blocks ? k + 1u : kDeepFull;
-            atomicExch(t, id);
-        } else {
-            id = prev;
-        }
-    }
-    while (id == kDeepLocked) id = *reinterpret_cast<volatile unsigned*>(t);
-    return id;
-}
-
-// Where slot `so` (< kListDepth) of destination lane `at` lives; nullptr: nowhere (pool exhausted).
-__device__ __forceinline__ uint4* cell_address(const GatherParams& prm, unsigned at, int so)
-{
-    if (so < kShallowSlots) return prm.lists + ((int64_t)(at >> 5) * kShallowSlots + so) * 32 + (at & 31u);
-    const unsigned id = deep_block(prm, at >> 5, (so - kShallowSlots) / kDeepSlots);
-    if (id == kDeepFull) return nullptr;
-    return prm.deep_pool + ((int64_t)(id - 1u) * kDeepSlots + (so - kShallowSlots) % kDeepSlots) * 32 + (at & 31u);
-}
-
 // A cell beyond the list depth (a convergence point): its pairs go to the excess list and are added by fp32
 // reductions at L2 after the gather (heavy_excess_kernel), which leaves the flagged tile un-normalised for them.
 __device__ __forceinline__ void excess_cell(const GatherParams& prm, int f, unsigned at, unsigned src, float wt, float wb)
@@ -554,8 +521,9 @@ insert_kernel(const GatherParams prm)
         if (c.slot[i] < 0) continue;
         const int so = ovf[i] == 0xffffffffu ? c.slot[i] : (int)min(ovf[i], (unsigned)kListDepth) + kCanon;
         // streaming stores: the lists (40 MB per frame, next read by the gather) need not stay in L2
-        uint4* cell = so < kListDepth ? cell_address(prm, c.at[i], so) : nullptr;
-        if (cell) SLR_INSERT_STORE(cell, make_uint4((unsigned)p, __float_as_uint(c.wt[i]), __float_as_uint(c.wb[i]), xy));
+        if (so < kListDepth)
+            SLR_INSERT_STORE(prm.lists + ((int64_t)(c.at[i] >> 5) * kListDepth + so) * 32 + (c.at[i] & 31u),
+                             make_uint4((unsigned)p, __float_as_uint(c.wt[i]), __float_as_uint(c.wb[i]), xy));
         else excess_cell(prm, f, c.at[i], (unsigned)p, c.wt[i], c.wb[i]);
     }
 }
@@ -602,16 +570,9 @@ struct RowCtx {
 };
 
 // entry k >= kRegSlots of the lane's column, or the all-zero pixel with zero weights
-__device__ __forceinline__ uint4 deep_entry(const GatherParams& prm, const RowCtx& c, int k)
+__device__ __forceinline__ uint4 deep_entry(const RowCtx& c, int k)
 {
-    const uint4 none = make_uint4((unsigned)c.P, 0u, 0u, 0u);
-    if (k >= c.my_hi) return none;
-    if (!prm.direct) return __ldcg(c.list + k * 32);
-    // direct index: the deeper slots live in pool blocks (clip_common.cuh); c.list = lists + (pair * kShallowSlots) * 32 + lane
-    const size_t at = (size_t)(c.list - prm.lists);
-    const unsigned id = __ldcg(prm.deep_tab + (at / (kShallowSlots * 32)) * kDeepBlocks + (k - kShallowSlots) / kDeepSlots);
-    if (id == 0u || id == kDeepFull) return none;          // pool exhausted: the cell went to the excess list
-    return __ldcg(prm.deep_pool + ((int64_t)(id - 1u) * kDeepSlots + (k - kShallowSlots) % kDeepSlots) * 32 + (at & 31u));
+    return k < c.my_hi ? __ldcg(c.list + k * 32) : make_uint4((unsigned)c.P, 0u, 0u, 0u);
 }
 
 // K  = compile-time number of register-resident slots (the warp's list length rounded up);
@@ -619,7 +580,7 @@ __device__ __forceinline__ uint4 deep_entry(const GatherParams& prm, const RowCt
 //      issued before the first FMA that consumes them (a warp pays one full memory latency per batch).
 // NZ = count the non-zero outputs (GatherParams::nnz).
 template <int NT, int K, int GI, bool NZ>
-__device__ __forceinline__ void gather_rows(const GatherParams& prm, const RowCtx& c, const unsigned (&pk)[kRegSlots],
+__device__ __forceinline__ void gather_rows(const RowCtx& c, const unsigned (&pk)[kRegSlots],
                                             const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
                                             float (&sum_t)[NT + 1], float (&sum_b)[NT + 1], int (&nz)[2])
 {
@@ -644,7 +605,7 @@ __device__ __forceinline__ void gather_rows(const GatherParams& prm, const RowCt
     const int kmax = K == kRegSlots ? __reduce_max_sync(0xffffffffu, c.my_hi) : K;
     if (K == kRegSlots) {
         for (int k = kRegSlots; k < kmax; ++k) {          // rare: lists deeper than the registers hold
-            const uint4 e = deep_entry(prm, c, k);
+            const uint4 e = deep_entry(c, k);
             #pragma unroll
             for (int t = 0; t <= NT; ++t) {
                 const float s = __ldg(c.S + (int64_t)t * sstride + (e.x & kPixelMask));
@@ -689,7 +650,7 @@ __device__ __forceinline__ void gather_rows(const GatherParams& prm, const RowCt
         for (int gi = 0; gi < GI; ++gi) {
             if (K == kRegSlots) {
                 for (int k = kRegSlots; k < kmax; ++k) {
-                    const uint4 e = deep_entry(prm, c, k);
+                    const uint4 e = deep_entry(c, k);
                     const float8 t = ldg256(px32(Gg + gi * gstride, e.x & kPixelMask));
                     const float w0 = __uint_as_float(e.y), w1 = __uint_as_float(e.z);
                     fma4(at[gi].lo, t.lo, w0); fma4(at[gi].hi, t.hi, w0);
@@ -714,13 +675,13 @@ __device__ __forceinline__ void gather_rows(const GatherParams& prm, const RowCt
 }
 
 template <int NT, int K, bool NZ>
-__device__ __forceinline__ void gather_rows_dispatch(const GatherParams& prm, const RowCtx& c, const unsigned (&pk)[kRegSlots],
+__device__ __forceinline__ void gather_rows_dispatch(const RowCtx& c, const unsigned (&pk)[kRegSlots],
                                                      const float (&wt)[kRegSlots], const float (&wb)[kRegSlots],
                                                      float (&sum_t)[NT + 1], float (&sum_b)[NT + 1], int (&nz)[2])
 {
     constexpr int GI = K * 2 <= kGatherLoads ? 2 : 1;
-    if (c.groups % GI == 0) gather_rows<NT, K, GI, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
-    else gather_rows<NT, K, 1, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
+    if (c.groups % GI == 0) gather_rows<NT, K, GI, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else gather_rows<NT, K, 1, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
 }
 
 
@@ -769,7 +730,7 @@ __device__ __forceinline__ void rowgather_item(const GatherParams& prm, unsigned
 
     RowCtx c;
     c.G = prm.G; c.S = prm.S; c.P = P; c.W = prm.W; c.groups = prm.groups; c.C = prm.C; c.eps = prm.eps;
-    c.list = prm.lists + pair * ((DIRECT ? kShallowSlots : kListDepth) * 32) + (tid & 31);
+    c.list = prm.lists + pair * (kListDepth * 32) + (tid & 31);
     c.out_top = prm.out + (int64_t)f * prm.C * P + pix;
     c.in_top = X < prm.W && Y < prm.H;
     c.in_bot = X < prm.W && Y + 1 < prm.H;
@@ -797,12 +758,12 @@ __device__ __forceinline__ void rowgather_item(const GatherParams& prm, unsigned
     float sum_t[NT + 1] = {0.0f}, sum_b[NT + 1] = {0.0f};
     int nz[2] = {0, 0};
     // the list length is warp-uniform: pick the unroll that fits
-    if (kmax <= 2) gather_rows_dispatch<NT, 2, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 4) gather_rows_dispatch<NT, 4, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 6) gather_rows_dispatch<NT, 6, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 8) gather_rows_dispatch<NT, 8, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
-    else if (kmax <= 12) gather_rows_dispatch<NT, 12, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
-    else gather_rows_dispatch<NT, 16, NZ>(prm, c, pk, wt, wb, sum_t, sum_b, nz);
+    if (kmax <= 2) gather_rows_dispatch<NT, 2, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 4) gather_rows_dispatch<NT, 4, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 6) gather_rows_dispatch<NT, 6, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 8) gather_rows_dispatch<NT, 8, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else if (kmax <= 12) gather_rows_dispatch<NT, 12, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
+    else gather_rows_dispatch<NT, 16, NZ>(c, pk, wt, wb, sum_t, sum_b, nz);
 
     #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -1393,7 +1354,6 @@ int make_params(GatherParams& prm, const void* scene, const float* motion, int64
     // the plan packs a source row into 14 bits and a column into 16 (plan_key)
     prm.staged = slr_host::gather_staged() && H <= 16384 && W <= 65535 ? 1 : 0;
     prm.direct = slr_host::index_direct() ? 1 : 0;
-    prm.deep_tab = ws.deep_tab; prm.deep_pool = ws.deep_pool; prm.deep_blocks = ws.deep_blocks;
     prm.slot_mask = ws.slot_mask; prm.slot_over = ws.slot_over; prm.refs = ws.refs;
     prm.ent = ws.ent; prm.motion = motion; prm.offsets = ws.offsets;
     prm.lists = ws.lists; prm.row_k = ws.row_k; prm.tile_flag = ws.tile_flag;

@@ -405,7 +405,7 @@ int build_table(const float* motion, int64_t H, int64_t W, int start, int end, i
 // flags and counters start at zero.
 __global__ void bind_batch_kernel(BatchRefs* refs, const float* land, const unsigned* moving, unsigned* flag_count, unsigned* excess_count)
 {
-    if (threadIdx.x == 0) { refs->land = land; refs->moving = moving; refs->deep_next = 0u; *flag_count = 0u; *excess_count = 0u; }
+    if (threadIdx.x == 0) { refs->land = land; refs->moving = moving; *flag_count = 0u; *excess_count = 0u; }
 }
 
 int bind_batch(const float* land, const unsigned* mask0, const unsigned* moving, int64_t H, int64_t W, int n_frames, const Workspace& ws, cudaStream_t s)
@@ -414,7 +414,6 @@ int bind_batch(const float* land, const unsigned* mask0, const unsigned* moving,
     const int64_t words = (int64_t)n_tiles * kPairsPerTile * 16;
     slot_fill_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(mask0, ws.slot_mask, ws.slot_over, words, n_frames);
     SLR_CUDA(cudaMemsetAsync(ws.tile_flag, 0, sizeof(unsigned) * (size_t)n_tiles * n_frames, s));
-    SLR_CUDA(cudaMemsetAsync(ws.deep_tab, 0, sizeof(unsigned) * kDeepBlocks * (size_t)n_tiles * kPairsPerTile * n_frames, s));
     bind_batch_kernel<<<1, 32, 0, s>>>(ws.refs, land, moving, ws.flag_count, ws.excess_count);
     return SLR_LAUNCH_STATUS();
 }
