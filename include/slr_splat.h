@@ -88,6 +88,26 @@ int slr_euler_grad_motion(const float* motion, float sign, int T, const float* g
                           float* grad_motion, int64_t H, int64_t W, slr_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Training forward: the splat-input producer fused into the splat, and its backward.
+ * Replaces, per direction, models/animating_softmax_splating.py:606 (tenInput_f = cat([start_fs *
+ * Z_f_norm.exp() * alpha, Z_f_norm.exp() * alpha], 1); :651 for the backward direction with end_fs, Z_p and
+ * 1 - alpha), the ModuleSoftsplat('summation') call on it (:629-632 / :672-676 -> softsplat.py:157-202) and,
+ * in the backward pass, autograd through both (softsplat.py:204-326, :427-477 and the cat / exp / mul nodes).
+ *   fs [B,C,H,W], zn [B,1,H,W] (the normalised, clamped importance: :596-605), flow [B,2,H,W] (the
+ *   integrated displacement), alpha [B] on the device (:584-585).
+ * slr_producer_splat_fwd: acc [B,C+1,H,W] (+)= splat of (fs * e^zn * alpha, e^zn * alpha); accumulate != 0
+ *   adds into acc (the second direction: the reference adds the two splat outputs, :684-686), else acc is
+ *   overwritten.
+ * slr_producer_splat_bwd: from grad_acc [B,C+1,H,W] the gradients d_fs [B,C,H,W], d_zn [B,1,H,W], d_flow
+ *   [B,2,H,W]; any of the three may be NULL. */
+int slr_producer_splat_fwd(const float* fs, const float* zn, const float* flow, const float* alpha,
+                           float* acc, int64_t B, int64_t C, int64_t H, int64_t W, int accumulate,
+                           slr_stream_t stream);
+int slr_producer_splat_bwd(const float* fs, const float* zn, const float* flow, const float* alpha,
+                           const float* grad_acc, float* d_fs, float* d_zn, float* d_flow,
+                           int64_t B, int64_t C, int64_t H, int64_t W, slr_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Joint block level: what forward_flow() does between the encoder and the
  * decoder (models/animating_softmax_splating.py:847-924 and
  * models/animating_softmax_splating_2layers_alpha_seperate.py:921-1045).

@@ -321,3 +321,40 @@ def warp_flow_block(image, forward_flow, backward_flow, index, splat=softsplat_s
     gen = acc[:, :-1] + acc_p[:, :-1]                                                    # :1133
     norm = np.maximum(acc[:, -1:] + acc_p[:, -1:], np.float32(1e-8))                     # :1134-1137
     return gen / norm                                                                    # :1138
+
+
+def producer_splat(fs, zn, flow, alpha, splat=softsplat_sum):
+    """One direction of the TRAINING forward: tenInput = cat([fs * zn.exp() * alpha, zn.exp() * alpha], 1)
+    (animating_softmax_splating.py:606 / :651) through the summation splat (:629-632 / :672-676).
+    fs [B,C,H,W], zn [B,1,H,W] (already normalised and clamped), flow [B,2,H,W], alpha [B]."""
+    a = np.asarray(alpha, np.float32).reshape(-1, 1, 1, 1)
+    ez = np.exp(zn.astype(np.float32)).astype(np.float32)
+    ten = np.concatenate([(fs * ez) * a, ez * a], 1).astype(np.float32)
+    return splat(ten, flow), ten
+
+
+def producer_splat_grads(fs, zn, flow, alpha, grad_acc):
+    """(d_fs, d_zn, d_flow) of sum(producer_splat(...) * grad_acc): the chain rule autograd applies in the
+    reference -- the splat's two backward kernels (softsplat.py:204-326) on tenInput, then the cat / mul / exp
+    nodes -- written out in numpy on top of the pinned restatements of those kernels."""
+    a = np.asarray(alpha, np.float32).reshape(-1, 1, 1, 1)
+    _, ten = producer_splat(fs, zn, flow, alpha)
+    ez = np.exp(zn.astype(np.float32)).astype(np.float32)
+    g_ten = softsplat_grad_input(flow, grad_acc)                  # [B, C+1, H, W]
+    d_flow = softsplat_grad_flow(ten, flow, grad_acc)
+    C = fs.shape[1]
+    ga = g_ten * a
+    d_fs = (ga[:, :C] * ez).astype(np.float32)
+    d_ez = (ga[:, :C].astype(np.float64) * fs).sum(1, keepdims=True) + ga[:, C:]
+    d_zn = (d_ez * ez).astype(np.float32)
+    return d_fs, d_zn, d_flow
+
+
+def joint_block_training(start_fs, end_fs, Z_f, Z_p, flow_f, flow_p, alpha, splat=softsplat_sum):
+    """The softmax-splatter branch of AnimatingSoftmaxSplating.forward between the Euler integration and the
+    decoder (animating_softmax_splating.py:584-692), default options: Z - Z.max(), clamp to [-20, 20]."""
+    a = np.asarray(alpha, np.float32).reshape(-1)
+    zf = np.clip(Z_f - Z_f.max(), -20.0, 20.0).astype(np.float32)
+    zp = np.clip(Z_p - Z_p.max(), -20.0, 20.0).astype(np.float32)
+    acc = producer_splat(start_fs, zf, flow_f, a, splat)[0] + producer_splat(end_fs, zp, flow_p, np.float32(1.0) - a, splat)[0]
+    return acc[:, :-1] / np.maximum(acc[:, -1:], np.float32(1e-8))

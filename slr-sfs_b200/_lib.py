@@ -27,6 +27,8 @@ SIGNATURES = {
     "slr_maxwarpnorm": [_f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _strm],
     "slr_euler": [_f32p, _flt, _int, _f32p, _f32p, _i64, _i64, _strm],
     "slr_euler_grad_motion": [_f32p, _flt, _int, _f32p, _f32p, _i64, _i64, _strm],
+    "slr_producer_splat_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _int, _strm],
+    "slr_producer_splat_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _strm],
     "slr_reduce_max": [_f32p, _i64, _f32p, _strm],
     "slr_joint_scatter": [_f32p, _f32p, _f32p, _f32p, _int, _f32p, _f32p, _flt, _f32p, _i64, _i64, _i64, _strm],
     "slr_joint_scatter_weights": [_f32p, _f32p, _f32p, _f32p, _int, _f32p, _f32p, _flt, _flt, _f32p, _i64, _i64, _i64, _strm],
@@ -116,7 +118,20 @@ KERNELS_PER_CALL = {
     "slr_maxsplat_fwd": 2, "slr_maxwarpnorm": 3, "slr_euler": 1, "slr_euler_grad_motion": 1, "slr_reduce_max": 2,
     "slr_joint_scatter": 1, "slr_joint_scatter_weights": 1, "slr_normalize": 1, "slr_scene_prep": 1, "slr_scene_quilt": 1, "slr_clip_frames": 9,
     "slr_clip_plan": 3, "slr_clip_table": 2, "slr_clip_bin": 1, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 4, "slr_frame_sink_u8": 1,
+    "slr_producer_splat_fwd": 1, "slr_producer_splat_bwd": 1,
 }
+# the direct index (default SLR_GATHER_MODE): slr_clip_bin = slot_fill + bind_batch, slr_clip_heavy = excess + finish + the
+# three overflow kernels, slr_clip_plan = euler_table + static_lanes + slot_fill + bind_batch; staged: + stagegather
+_KERNELS_DIRECT = {"slr_clip_bin": 2, "slr_clip_heavy": 5, "slr_clip_plan": 4, "slr_clip_frames": 11}
+
+
+def _kernels_per_call(name):
+    mode = os.environ.get("SLR_GATHER_MODE", "ldg")
+    if mode not in ("bins", "staged") and name in _KERNELS_DIRECT:
+        return _KERNELS_DIRECT[name]
+    if mode == "staged" and name in ("slr_clip_gather", "slr_clip_frames"):
+        return KERNELS_PER_CALL[name] + 1
+    return KERNELS_PER_CALL.get(name, 0)
 _launches = 0
 _timing = None          # None, or list of (name, start_event, end_event)
 _timing_only = None     # None = every entry point, else the set of names to bracket
@@ -174,4 +189,4 @@ def call(name, *args):  # noqa: F811  (instrumented wrapper around the plain cal
         _timing.append((name, e0, e1))
     else:
         _plain_call(name, *args)
-    _launches += KERNELS_PER_CALL.get(name, 0)
+    _launches += _kernels_per_call(name)

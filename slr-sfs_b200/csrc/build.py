@@ -35,12 +35,25 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
+    # one process per GPU may arrive here at the same time (torchrun): the first one compiles, the others wait
+    # and find the library fresh
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not stale():
+            return LIB
+        return _compile(verbose)
+
+
+def _compile(verbose):
     # tuning knobs (see clip_gather.cu / clip_common.cuh); e.g. SLR_DEFINES="-DSLR_LIST_DEPTH=128"
     extra = os.environ.get("SLR_DEFINES", "").split()
-    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    tmp = LIB + ".tmp.%d" % os.getpid()          # never a half-written library at the final path
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout)
+    os.replace(tmp, LIB)
     if verbose:
         print(proc.stdout)
     return LIB
