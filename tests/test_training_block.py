@@ -94,6 +94,14 @@ def test_emu_producer_splat_gradients_are_the_derivative():
 
 
 # ---------------------------------------------------------------------------- GPU
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__
+    __graft_entry__.build()
+    import slr_sfs_b200
+    return slr_sfs_b200
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(2, 64, 256, 256), (1, 7, 45, 67)])
 def test_gpu_joint_block_training_forward_and_backward(pkg, shape):
