@@ -134,9 +134,11 @@ class JointSplat:
     positions C..C+n_tail-1 of the accumulator.
     """
 
-    #: frames per slr_clip_bin / expand / gather launch (the Euler chains are integrated once per run
-    #: of frames whatever the batch; 6-20 measured within 1 %, profiles/README.md)
-    batch = int(os.environ.get("SLR_BATCH", "12"))
+    #: frames per slr_clip_bin / expand / gather launch (the Euler chains are integrated once per run of frames
+    #: whatever the batch).  Measured with the direct index at 768x1024x64: 8 / 12 / 16 / 20 / 24 -> 7 569 / 7 765 /
+    #: 7 834 / 7 893 / 7 861 frames/s (profiles/r02/batch_sweep.jsonl).  Capped so that one batch workspace stays
+    #: below 15 % of the device memory (two exist: 1536x2048 then runs batches of 10).
+    batch = int(os.environ.get("SLR_BATCH", "20"))
     #: overlap plan + expand of the next batch with the gather of the current one (two streams)
     pipeline = True
 
@@ -294,6 +296,16 @@ class JointSplat:
                                                     "pool": _BufferPool(self.device)}
         return st
 
+    def _fitting_batch(self):
+        """``self.batch``, lowered where one batch workspace would exceed 15 % of the device memory."""
+        batch = max(1, int(self.batch))
+        try:
+            total = torch.cuda.get_device_properties(self.device).total_memory
+        except Exception:          # not a CUDA device (the emulated library in tests/)
+            return batch
+        per_frame = _lib.load().slr_clip_workspace_bytes(self.H, self.W, 1)
+        return max(1, min(batch, int(0.15 * total // max(per_frame, 1))))
+
     def _scratch(self, st, n, slot, side):
         need = _lib.load().slr_clip_workspace_bytes(self.H, self.W, n)
         ws = st["ws"].get(slot)
@@ -365,7 +377,8 @@ class JointSplat:
         aux = torch.empty(n, self.n_tail + 1, H, W, dtype=torch.float32, device=self.device) if want_aux else None
         mask = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_mask else None
         nnz = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_nnz else None
-        batches = [(b0, min(self.batch, n - b0)) for b0 in range(0, n, self.batch)]
+        batch = self._fitting_batch()
+        batches = [(b0, min(batch, n - b0)) for b0 in range(0, n, batch)]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             st = self._shared_state()
@@ -377,7 +390,7 @@ class JointSplat:
             for (b0, nb) in batches:
                 slot = st["turn"] = st["turn"] ^ 1
                 args = (C, self.n_tail, H, W, start, end, t0 + b0, nb, alpha_clamp[0], alpha_clamp[1])
-                ws, ws_bytes = self._scratch(st, self.batch, slot, side)
+                ws, ws_bytes = self._scratch(st, batch, slot, side)
                 with torch.cuda.stream(side):
                     for ev in st["free"].get(slot, ()):
                         side.wait_event(ev)

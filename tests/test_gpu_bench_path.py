@@ -1,7 +1,7 @@
 """GPU: parity of the code path bench.py measures, at the sizes BASELINE.json names.
 
 * configs[1]: the exact sequence of the bench (ClipRunner: prepare_clip for the frame block, groups of
-  48 frames in batches of 12, two-stream pipeline on, scene / table buffers recycled through the pool,
+  60 frames in batches of 20, two-stream pipeline on, scene / table buffers recycled through the pool,
   two scenes back to back) -- ALL 60 frames of the second scene against the reference's own CUDA
   kernel driven like forward_flow (oracle/refgpu.py), 768x1024x64.
 * configs[2]: the 2-layer block with 67 splatted channels at 768x1024 (gen_fs, alpha_fluid, mask).
@@ -64,8 +64,8 @@ def test_benched_sequence_all_60_frames_vs_reference_kernel(pkg, ref):
     dev = torch.device("cuda")
     assert (1, C + 1, H, W) in ref.baked_shapes()
     scenes = [tuple(t.to(dev) for t in workloads.scene(H, W, C, "A", seed=s)) for s in (0, 1)]
-    runner = ClipRunner(C, H, W, dev, group=48)           # bench.py: min(frames of the rank, 4 x batch)
-    assert pkg.JointSplat.batch == 12 and pkg.JointSplat.pipeline
+    assert pkg.JointSplat.batch == 20 and pkg.JointSplat.pipeline
+    runner = ClipRunner(C, H, W, dev, group=min(N, 4 * pkg.JointSplat.batch))      # bench.py: min(frames of the rank, 4 x batch)
     worst, holes = {}, {}
 
     def check(scene_id):
