@@ -87,6 +87,20 @@ int slr_euler(const float* motion, float sign, int T, float* disp, float* visibl
 int slr_euler_grad_motion(const float* motion, float sign, int T, const float* grad_disp,
                           float* grad_motion, int64_t H, int64_t W, slr_stream_t stream);
 
+/* The same summation splat (softsplat.py:157-202; _FunctionSoftsplat.forward, :407-416) through the GATHER
+ * pipeline of the joint block instead of fp32 atomics: per batch element the input is interleaved, the flow
+ * becomes a one-frame table, every source writes its list cells and every destination pixel pulls its
+ * contributions and writes the un-normalised sum once (output fully overwritten, exact zeros in holes).
+ * Same results up to fp32 summation order.  Pays off for large frames (1 x 65 x 768 x 1024 with a smooth flow:
+ * 0.29 ms against 0.40 ms, the reference's own kernel 0.41 ms on the same B200); the Python operator picks it
+ * above 2^25 elements per batch item.  scratch: slr_softsplat_gather_scratch_bytes(C, H, W) bytes,
+ * 256-byte aligned, reused for every batch element.  Needs the default SLR_GATHER_MODE (returns -1 / 0 bytes
+ * otherwise) and H * W < 2^27. */
+size_t slr_softsplat_gather_scratch_bytes(int64_t C, int64_t H, int64_t W);
+int slr_softsplat_sum_fwd_gather(const float* input, const float* flow, float* output,
+                                 int64_t B, int64_t C, int64_t H, int64_t W,
+                                 void* scratch, size_t scratch_bytes, slr_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Training forward: the splat-input producer fused into the splat, and its backward.
  * Replaces, per direction, models/animating_softmax_splating.py:606 (tenInput_f = cat([start_fs *

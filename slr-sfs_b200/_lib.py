@@ -27,6 +27,8 @@ SIGNATURES = {
     "slr_maxwarpnorm": [_f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _strm],
     "slr_euler": [_f32p, _flt, _int, _f32p, _f32p, _i64, _i64, _strm],
     "slr_euler_grad_motion": [_f32p, _flt, _int, _f32p, _f32p, _i64, _i64, _strm],
+    "slr_softsplat_gather_scratch_bytes": [_i64, _i64, _i64],
+    "slr_softsplat_sum_fwd_gather": [_f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _f32p, ctypes.c_size_t, _strm],
     "slr_producer_splat_fwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _int, _strm],
     "slr_producer_splat_bwd": [_f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64, _i64, _i64, _i64, _strm],
     "slr_reduce_max": [_f32p, _i64, _f32p, _strm],
@@ -54,7 +56,8 @@ SIGNATURES = {
     "slr_clip_stats_host": [_f32p, ctypes.c_size_t, _i64, _i64, _int, ctypes.POINTER(ctypes.c_uint32), _strm],
 }
 _OTHER_RESTYPE = {"slr_last_error_string": ctypes.c_char_p, "slr_scene_bytes": ctypes.c_size_t, "slr_scene_core_bytes": ctypes.c_size_t,
-                  "slr_clip_workspace_bytes": ctypes.c_size_t, "slr_clip_table_bytes": ctypes.c_size_t}
+                  "slr_clip_workspace_bytes": ctypes.c_size_t, "slr_clip_table_bytes": ctypes.c_size_t,
+                  "slr_softsplat_gather_scratch_bytes": ctypes.c_size_t}
 
 _lib = None
 _lock = threading.Lock()
@@ -119,6 +122,9 @@ KERNELS_PER_CALL = {
     "slr_joint_scatter": 1, "slr_joint_scatter_weights": 1, "slr_normalize": 1, "slr_scene_prep": 1, "slr_scene_quilt": 1, "slr_clip_frames": 9,
     "slr_clip_plan": 3, "slr_clip_table": 2, "slr_clip_bin": 1, "slr_clip_expand": 1, "slr_clip_gather": 1, "slr_clip_heavy": 4, "slr_frame_sink_u8": 1,
     "slr_producer_splat_fwd": 1, "slr_producer_splat_bwd": 1,
+    # per batch element: scene_prep, flow_table, static_lanes, slot_fill, bind_batch, insert, rowgather, heavy_excess,
+    # heavy_finish, overflow x 3 (counted for one element; bench.py's level0 leg uses B = 1)
+    "slr_softsplat_sum_fwd_gather": 12,
 }
 # the direct index (default SLR_GATHER_MODE): slr_clip_bin = slot_fill + bind_batch, slr_clip_heavy = excess + finish + the
 # three overflow kernels, slr_clip_plan = euler_table + static_lanes + slot_fill + bind_batch; staged: + stagegather

@@ -38,7 +38,7 @@ scene_prep_kernel(const float* __restrict__ feat, const float* __restrict__ z, c
         }
         return;
     }
-    const float ez = expf(z[p] - (zsub ? *zsub : 0.0f));
+    const float ez = z ? expf(z[p] - (zsub ? *zsub : 0.0f)) : 1.0f;      // no importance plane: plain features (weight 1)
     const int g0 = blockIdx.y * ((groups + gridDim.y - 1) / gridDim.y);
     const int g1 = min(groups, g0 + (groups + (int)gridDim.y - 1) / (int)gridDim.y);
     for (int g = g0; g < g1; ++g) {
@@ -316,6 +316,29 @@ slot_fill_kernel(const unsigned* __restrict__ mask0, unsigned* __restrict__ slot
     }
 }
 
+// A one-frame, one-direction "clip table" from a GIVEN flow (the operator-level summation splat through the
+// gather, slr_softsplat_sum_fwd_gather): landing = pixel + flow exactly as the reference scatter computes it
+// (softsplat.py:169-170); pixels with zero flow carry the static marker (they receive themselves through the
+// lanes' initial masks); the second direction does not exist (every pixel static: its threads leave at once).
+__global__ void __launch_bounds__(256)
+flow_table_kernel(const float* __restrict__ flow, int H, int W, float* __restrict__ land, unsigned* __restrict__ moving)
+{
+    const int64_t P = (int64_t)H * W;
+    const int64_t p_raw = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool active = p_raw < P;
+    const int64_t p = active ? p_raw : 0;
+    const float fx = __ldg(flow + p), fy = __ldg(flow + P + p);
+    const bool is_static = fx == 0.0f && fy == 0.0f;
+    const int any = __syncthreads_or(active && !is_static);
+    if (any && threadIdx.x == 0) moving[1u + atomicAdd(moving, 1u)] = blockIdx.x;
+    if (!active) return;
+    const int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    land[p] = is_static ? kStaticLand : __fadd_rn((float)x, fx);
+    land[P + p] = is_static ? kStaticLand : __fadd_rn((float)y, fy);
+    land[2 * P + p] = kStaticLand;
+    land[3 * P + p] = kStaticLand;
+}
+
 }  // namespace slr
 
 // ===========================================================================
@@ -361,7 +384,15 @@ extern "C" int slr_scene_prep(const float* feat, const float* z, const float* zs
                               const float* tail, int n_tail, void* scene,
                               int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
 {
-    SLR_CHECK_ARGS(feat && z && scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
+    SLR_CHECK_ARGS(z, "slr_scene_prep: bad arguments");
+    return slr_host::scene_prep(feat, z, zsub, tail, n_tail, scene, C, H, W, stream_);
+}
+
+// z == NULL: plain features (e^Z = 1)
+int slr_host::scene_prep(const float* feat, const float* z, const float* zsub, const float* tail, int n_tail, void* scene,
+                         int64_t C, int64_t H, int64_t W, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(feat && scene && C > 0 && H > 0 && W > 0 && H * W < (1ll << 27) &&
                    n_tail >= 0 && n_tail <= 2 && (n_tail == 0 || tail) && ((uintptr_t)scene & 31) == 0,
                    "slr_scene_prep: bad arguments");
     const int64_t P = H * W;
@@ -433,6 +464,24 @@ int fill_bins(const float* land, int64_t H, int64_t W, int n_frames, const Works
 }
 
 }  // namespace
+
+// One-frame table of a given flow (direct index only): landing coordinates, initial slot masks, moving blocks.
+int slr_host::flow_table(const float* flow, int64_t H, int64_t W, void* table, size_t table_bytes, slr_stream_t stream_)
+{
+    SLR_CHECK_ARGS(flow && table && H > 0 && W > 0 && H * W < (1ll << 27) && ((uintptr_t)table & 15) == 0 && slr_host::index_direct(),
+                   "flow_table: bad arguments");
+    const slr_host::ClipTable tab = slr_host::carve_table(table, H, W, 1);
+    SLR_CHECK_ARGS(tab.bytes <= table_bytes, "flow_table: table too small");
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int64_t P = H * W;
+    const int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
+    const int n_tiles = tiles_x * tiles_y;
+    SLR_CUDA(cudaMemsetAsync(tab.moving, 0, sizeof(unsigned), s));
+    flow_table_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(flow, (int)H, (int)W, tab.land, tab.moving);
+    const int64_t words = (int64_t)n_tiles * kPairsPerTile * 16;
+    static_lanes_kernel<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(flow, tab.mask0, (int)H, (int)W, tiles_x, n_tiles);
+    return SLR_LAUNCH_STATUS();
+}
 
 extern "C" size_t slr_clip_table_bytes(int64_t H, int64_t W, int n_frames)
 {

@@ -21,6 +21,11 @@ bool gather_staged();
 // "bins" and "staged" sort the sources into per-tile bins first and expand them tile by tile (bin_fill_kernel +
 // expand_kernel: the round-1 pipeline, which the staging plan of "staged" is built on).
 bool index_direct();
+// slr_scene_prep without requiring an importance plane (z == NULL: e^Z = 1), and the one-frame table of a given
+// flow: the pieces slr_softsplat_sum_fwd_gather puts in front of the clip pipeline (csrc/clip_plan.cu).
+int scene_prep(const float* feat, const float* z, const float* zsub, const float* tail, int n_tail, void* scene,
+               int64_t C, int64_t H, int64_t W, slr_stream_t stream);
+int flow_table(const float* flow, int64_t H, int64_t W, void* table, size_t table_bytes, slr_stream_t stream);
 }  // namespace slr_host
 
 #define SLR_CHECK_ARGS(cond, msg) \

@@ -15,6 +15,8 @@ softsplat.py:328-386).
 As in the reference, CPU tensors raise NotImplementedError (softsplat.py:418-419):
 there is no CPU path in this package.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -33,6 +35,22 @@ def _check_pair(input, flow):
     assert _lib.on_device(flow) and flow.device == input.device and flow.shape[0] == input.shape[0]
 
 
+#: elements per batch item (C * H * W) from which the summation splat goes through the gather pipeline instead of
+#: fp32 atomics.  Measured with the benchmark scene's mid-clip displacement, 65 channels (profiles/r02/forward_op.json):
+#: 768x1024 0.29 against 0.40 ms, 1536x2048 0.87 against 1.15 ms, but 512x512 0.25 against 0.15 ms and 2 x 256x256 0.33
+#: against 0.09 ms (the gather's dozen launches and the input interleave cost more than they save on small frames).
+#: SLR_SPLAT_GATHER_MIN overrides.
+GATHER_MIN_ELEMENTS = int(os.environ.get("SLR_SPLAT_GATHER_MIN", str(1 << 25)))
+
+
+def _gather_scratch_bytes(C, H, W):
+    """Scratch bytes of slr_softsplat_sum_fwd_gather, or 0 when the scatter kernel is the better choice (small
+    frames; a non-default SLR_GATHER_MODE; more than 2^27 pixels)."""
+    if C * H * W < GATHER_MIN_ELEMENTS or H * W >= (1 << 27):
+        return 0
+    return _lib.load().slr_softsplat_gather_scratch_bytes(C, H, W)
+
+
 class _FunctionSoftsplat(torch.autograd.Function):
     """Summation splat with the reference's autograd contract: saves (input, flow),
     returns (gradInput | None, gradFlow | None) by needs_input_grad
@@ -46,8 +64,16 @@ class _FunctionSoftsplat(torch.autograd.Function):
         # freshly allocated and caller-owned: callers take views of it and += into them
         output = input.new_empty([B, C, H, W])
         with torch.cuda.device(input.device):
-            _lib.call("slr_softsplat_sum_fwd", _lib.ptr(input), _lib.ptr(flow), _lib.ptr(output),
-                      B, C, H, W, 1, _lib.current_stream(input.device))
+            scratch_bytes = _gather_scratch_bytes(C, H, W)
+            if scratch_bytes:
+                # large frames: bin by destination + gather instead of 4 * C * H * W fp32 atomics (csrc/clip_gather.cu)
+                scratch = torch.empty(scratch_bytes // 4 + 64, dtype=torch.float32, device=input.device)
+                off = (-scratch.data_ptr() % 256) // 4
+                _lib.call("slr_softsplat_sum_fwd_gather", _lib.ptr(input), _lib.ptr(flow), _lib.ptr(output), B, C, H, W,
+                          _lib.ptr(scratch[off:]), scratch_bytes, _lib.current_stream(input.device))
+            else:
+                _lib.call("slr_softsplat_sum_fwd", _lib.ptr(input), _lib.ptr(flow), _lib.ptr(output),
+                          B, C, H, W, 1, _lib.current_stream(input.device))
         return output
 
     @staticmethod

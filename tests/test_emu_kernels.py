@@ -43,6 +43,43 @@ def test_emu_summation_splat_and_grads(shape):
     assert rel_err(gflow, oracle.softsplat_grad_flow(inp, flow, gout)) <= TOL
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 17, 23), (2, 9, 40, 70), (1, 65, 24, 40)])
+def test_emu_summation_splat_through_the_gather(shape):
+    """slr_softsplat_sum_fwd_gather: the operator-level splat as scene prep + one-frame flow table + insert + gather of
+    the un-normalised sums, against the oracle and against the atomic scatter; static rows, far flows, ragged tiles."""
+    B, C, H, W = shape
+    inp, flow = _case(4, B, C, H, W, amp=5.0)
+    flow[:, :, : H // 4] = 0.0                       # pixels that do not move receive themselves
+    flow[:, :, -2:, :5] = 1000.0                     # ... and some that leave the frame
+    nb = emu.lib().slr_softsplat_gather_scratch_bytes(C, H, W)
+    assert nb > 0
+    scratch = emu.aligned(nb)
+    scratch[:] = 0x5A
+    out = np.full_like(inp, np.nan)
+    emu.call("slr_softsplat_sum_fwd_gather", emu.p(inp), emu.p(flow), emu.p(out), B, C, H, W, emu.p(scratch), nb, None)
+    want = oracle.softsplat_sum(inp, flow)
+    assert rel_err(out, want) <= TOL
+    assert np.all(out[want == 0.0] == 0.0)
+    ref = np.full_like(inp, np.nan)
+    emu.call("slr_softsplat_sum_fwd", emu.p(inp), emu.p(flow), emu.p(ref), B, C, H, W, 1, None)
+    assert rel_err(out, ref) <= 1e-5
+
+
+def test_emu_summation_splat_through_the_gather_convergent_flow():
+    """Everything onto a few pixels: lists cut at the list depth, excess pairs by reductions, and (one frame, small
+    excess list) the whole-batch scatter fallback -- all without the normalisation."""
+    B, C, H, W = 1, 5, 40, 72
+    inp, _ = _case(6, B, C, H, W)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    for flow in (np.stack([(W / 2 + 0.3) - xs, (H / 3 + 0.6) - ys])[None].astype(np.float32),
+                 np.stack([-(xs - W / 2) * 0.45, -(ys - H / 2) * 0.2])[None].astype(np.float32)):
+        nb = emu.lib().slr_softsplat_gather_scratch_bytes(C, H, W)
+        scratch = emu.aligned(nb)
+        out = np.full_like(inp, np.nan)
+        emu.call("slr_softsplat_sum_fwd_gather", emu.p(inp), emu.p(flow), emu.p(out), B, C, H, W, emu.p(scratch), nb, None)
+        assert rel_err(out, oracle.softsplat_sum(inp, flow)) <= TOL
+
+
 def test_emu_golden_cases_from_the_reference_kernels(golden_softsplat):
     g = golden_softsplat
     for case in sorted({k.split("/")[0] for k in g.files if "/" in k}):

@@ -41,6 +41,37 @@ def test_summation_splat_vs_reference_golden(pkg, golden_softsplat, case):
 
 
 @pytest.mark.parametrize("case", SPLAT_CASES)
+def test_summation_splat_through_the_gather_vs_reference_golden(pkg, golden_softsplat, case, monkeypatch):
+    """The large-frame path of the operator (slr_softsplat_sum_fwd_gather), forced at the golden sizes."""
+    monkeypatch.setattr(pkg.softsplat, "GATHER_MIN_ELEMENTS", 0)
+    g = golden_softsplat
+    inp, flow = g[f"{case}/inp"], g[f"{case}/flow"]
+    out = pkg.FunctionSoftsplat(cu(inp), cu(flow), None, "summation").cpu().numpy()
+    assert rel_err(out, g[f"{case}/sum"]) <= TOL
+    assert np.all(out[g[f"{case}/sum"] == 0.0] == 0.0)
+
+
+def test_summation_splat_paths_agree_and_keep_autograd(pkg, monkeypatch):
+    """Gather path against atomic scatter at a shape with static rows, a batch of two and ragged tiles; the
+    backward (the reference's two gather kernels) is the same whichever forward ran."""
+    r = np.random.default_rng(5)
+    B, C, H, W = 2, 33, 150, 201
+    inp = r.standard_normal((B, C, H, W)).astype(np.float32)
+    flow = r.uniform(-6, 6, (B, 2, H, W)).astype(np.float32)
+    flow[:, :, :40] = 0.0
+    res = {}
+    for name, thresh in (("scatter", 1 << 62), ("gather", 0)):
+        monkeypatch.setattr(pkg.softsplat, "GATHER_MIN_ELEMENTS", thresh)
+        x, f = cu(inp).requires_grad_(True), cu(flow).requires_grad_(True)
+        y = pkg.FunctionSoftsplat(x, f, None, "summation")
+        y.backward(torch.ones_like(y))
+        res[name] = (y.detach().cpu().numpy(), x.grad.cpu().numpy(), f.grad.cpu().numpy())
+    assert rel_err(res["gather"][0], oracle.softsplat_sum(inp, flow)) <= TOL
+    assert rel_err(res["gather"][0], res["scatter"][0]) <= 1e-5
+    assert np.array_equal(res["gather"][1], res["scatter"][1]) and np.array_equal(res["gather"][2], res["scatter"][2])
+
+
+@pytest.mark.parametrize("case", SPLAT_CASES)
 def test_backward_vs_reference_golden(pkg, golden_softsplat, case):
     g = golden_softsplat
     x = cu(g[f"{case}/inp"]).requires_grad_(True)
