@@ -378,6 +378,7 @@ class JointSplat:
         mask = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_mask else None
         nnz = torch.empty(n, 1, H, W, dtype=torch.float32, device=self.device) if want_nnz else None
         batch = self._fitting_batch()
+        batch = -(-n // -(-n // batch))          # equal batches: 30 frames at batch 20 are 15 + 15, not 20 + 10
         batches = [(b0, min(batch, n - b0)) for b0 in range(0, n, batch)]
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
