@@ -94,6 +94,17 @@ class Scene:
         call("slr_scene_prep", p(self.feat), p(self.Z), p(self.zsub), p(self.tail), self.n_tail,
              p(self.scene), self.C, self.H, self.W, None)
 
+    @classmethod
+    def from_buffer(cls, scene, motion, C, H, W):
+        """Over an already prepared scene buffer (what sharding.SceneExchange delivers): no features, no Z."""
+        self = cls.__new__(cls)
+        self.feat = self.Z = self.tail = self.zsub = None
+        self.n_tail, self.C, self.H, self.W = 0, C, H, W
+        self.motion = f32(motion)
+        assert scene.ctypes.data % 32 == 0
+        self.scene = scene
+        return self
+
     def table(self, start, end, t0, n):
         """slr_clip_table for frames t0 .. t0+n-1; returns the handle frames(..., table=) takes."""
         nb = lib().slr_clip_table_bytes(self.H, self.W, n)
