@@ -544,7 +544,7 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float w)
 }
 
 #ifndef SLR_GATHER_LOADS
-#define SLR_GATHER_LOADS 8             // 256-bit loads a warp has in flight per batch (8 KB); measured 4 / 6 / 8 / 12: profiles/r02/tune_gather.jsonl
+#define SLR_GATHER_LOADS 12            // 256-bit loads a warp has in flight per batch (12 KB); measured 4 ... 16, with the bin pipeline (8 was best) and again with the direct index (6 / 8 / 10 / 12: 12 is best): profiles/r02/tune_gather.jsonl
 #endif
 constexpr int kGatherLoads = SLR_GATHER_LOADS;
 // largest divisor B of K with B * GI <= kGatherLoads
