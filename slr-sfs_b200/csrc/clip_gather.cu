@@ -11,14 +11,17 @@
 // writes the normalised result once.  No feature atomics, no accumulator round trip
 // through HBM, no separate normalise pass.
 //
-//   expand_kernel     one CTA per (destination tile 32x8, frame): turns the tile's bin into
-//                     per-lane (source, w_top, w_bottom) lists for its 4 row pairs.  Small
-//                     register footprint, 6 CTAs/SM: hides the latency of this pointer-chasing.
+//   insert_kernel     (default: the "direct index") one thread per (moving source pixel, direction, frame): the
+//                     source's 2-4 list cells (source, w_top, w_bottom) written straight into the lists of the
+//                     destination lanes; a slot is claimed by one atomicOr on the lane's 16-bit slot mask.
+//   expand_kernel     (SLR_GATHER_MODE=bins / staged) one CTA per (destination tile 32x8, frame): turns the tile's
+//                     bin (bin_fill_kernel, clip_plan.cu) into the same lists through a shared-memory table; staged:
+//                     also the staging plan of stagegather_kernel.
 //   rowgather_kernel  the hot kernel.  One warp per row pair (2 x 32 destination pixels), no
 //                     shared memory, no barriers.  A lane owns the pixels (x, y) and (x, y+1):
 //                     a source that feeds both (its north corners land on y, its south
 //                     corners on y+1) is loaded ONCE -- 12 loads instead of 16 per pixel pair
-//                     in regular flow.  Per channel group: <=12 independent LDG.128 in flight,
+//                     in regular flow.  Per group of 8 channels: up to 12 independent 256-bit loads in flight,
 //                     then the FMAs, then streaming stores.  A CTA is 4 such warps: 2 row pairs of
 //                     one tile in 2 consecutive frames (their sources differ by one frame's
 //                     displacement, so they share lines in L1).

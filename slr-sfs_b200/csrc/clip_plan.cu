@@ -3,13 +3,17 @@
 //   scene_prep      once per scene: G8[g][p] = feat[8g..8g+7][p] * e^(Z[p]-zsub), 32 bytes
 //                   (one 256-bit load later fetches 8 channels of a source pixel),
 //                   S[j][p] = scalar planes (2-layer tail channels, e^Z).
-//   euler_table     once per batch of frames: both Euler chains in registers, landing
-//                   coordinates of every (frame, direction, pixel), and per-(frame,
-//                   destination tile) entry counts.  Pixels with exactly zero motion never
-//                   move: they are not binned (clip_gather.cu adds their self-contribution).
-//   bin_scan        exclusive scan of the counts -> bin offsets.
-//   bin_fill        every moving (pixel, direction) is appended to the bins of the
+//   euler_table     once per run of frames: both Euler chains in registers, landing
+//                   coordinates of every (frame, direction, pixel); pixels with exactly zero motion never
+//                   move: they carry a marker (clip_gather.cu adds their self-contribution).  Direct index
+//                   (default): also the 256-pixel blocks in which something moves; bin pipeline: also the
+//                   per-(frame, destination tile) entry counts.
+//   static_lanes    direct index: the lanes' initial slot masks (static pixels reserve their own slot),
+//   slot_fill       copied into every frame of a batch; bind_batch: what a batch workspace refers to.
+//   bin_scan        bin pipeline: exclusive scan of the counts -> bin offsets.
+//   bin_fill        bin pipeline: every moving (pixel, direction) is appended to the bins of the
 //                   destination tiles its 2x2 footprint touches.
+//   flow_table      a one-frame table from a given flow (slr_softsplat_sum_fwd_gather).
 //
 // Reference: the Euler + splat-input part of forward_flow,
 // /root/reference/models/animating_softmax_splating.py:847-862,895 and
