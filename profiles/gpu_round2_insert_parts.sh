@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: measured an EXPERIMENT build that is not in the tree any more (knobs / variants removed after the
+# measurement; results in profiles/r02/direct_index_ab.jsonl or tune_gather.jsonl, discussion in DESIGN.md 4.3).
 # Component isolation of insert_kernel (timing only, results invalid): x1 = no stores, x2 = no atomics, x3 = loads + arithmetic only
 mkdir -p gpurun_out
 B="--no-cpu-baseline --no-e2e --steps 10"

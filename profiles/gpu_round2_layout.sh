@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: measured an EXPERIMENT build that is not in the tree any more (knobs / variants removed after the
+# measurement; results in profiles/r02/direct_index_ab.jsonl or tune_gather.jsonl, discussion in DESIGN.md 4.3).
 # Image-order layout of the shallow lists / slot words
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/layout_pytest.log 2>&1

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: measured an EXPERIMENT build that is not in the tree any more (knobs / variants removed after the
+# measurement; results in profiles/r02/direct_index_ab.jsonl or tune_gather.jsonl, discussion in DESIGN.md 4.3).
 # Persistent gather (fixed grid of k CTAs per SM): does leaving a quarter of the register file to the side stream pay?
 mkdir -p gpurun_out
 B="--no-cpu-baseline --no-e2e --steps 20"

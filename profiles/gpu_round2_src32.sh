@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: measured an EXPERIMENT build that is not in the tree any more (knobs / variants removed after the
+# measurement; results in profiles/r02/direct_index_ab.jsonl or tune_gather.jsonl, discussion in DESIGN.md 4.3).
 # Source-only list words (4 bytes) for the first 16 slots, weights derived by the gather
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/src32_pytest.log 2>&1

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: measured an EXPERIMENT build that is not in the tree any more (knobs / variants removed after the
+# measurement; results in profiles/r02/direct_index_ab.jsonl or tune_gather.jsonl, discussion in DESIGN.md 4.3).
 # Gather knobs again on the direct index: loads in flight, CTA shape
 mkdir -p gpurun_out
 B="--no-cpu-baseline --no-e2e --steps 20"
