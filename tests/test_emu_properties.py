@@ -169,3 +169,72 @@ def test_non_finite_motion_invalidates_the_chain_not_the_context():
     Z = rng.standard_normal((1, 1, H, W)).astype(np.float32)
     out = emu.Scene(feat, Z, dirty).frames(0, T, 0, T + 1)
     assert np.isfinite(out).all()
+
+
+@settings(**dict(COMMON, max_examples=40))
+@given(H=st.integers(1, 40), W=st.integers(1, 70), C=st.integers(1, 9), B=st.integers(1, 2),
+       kind=st.sampled_from(["random", "smooth", "constant", "integer", "half", "patchy"]),
+       amp=st.sampled_from([0.0, 0.75, 3.0, 9.0, 100.0]), seed=st.integers(0, 2 ** 16))
+def test_summation_splat_through_the_gather_matches_the_oracle(H, W, C, B, kind, amp, seed):
+    """slr_softsplat_sum_fwd_gather (scene prep + flow table + insert + un-normalised gather) on random shapes /
+    flows: 1-pixel images, all-static and all-leaving flows, integer and half-pixel landings."""
+    rng = np.random.default_rng(seed)
+    inp = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    flow = np.concatenate([_motion(kind, H, W, rng, amp) for _ in range(B)], 0)
+    nb = emu.lib().slr_softsplat_gather_scratch_bytes(C, H, W)
+    scratch = emu.aligned(nb)
+    scratch[:] = 0xA5
+    out = np.full_like(inp, np.nan)
+    emu.call("slr_softsplat_sum_fwd_gather", emu.p(inp), emu.p(flow), emu.p(out), B, C, H, W, emu.p(scratch), nb, None)
+    want = oracle.softsplat_sum(inp, flow)
+    assert rel_err(out, want) <= TOL
+    assert np.all(out[want == 0.0] == 0.0)
+
+
+@settings(**dict(COMMON, max_examples=40))
+@given(H=st.integers(1, 30), W=st.integers(1, 50), C=st.integers(1, 7), B=st.integers(1, 2),
+       kind=st.sampled_from(["random", "smooth", "constant", "integer", "half", "patchy"]),
+       amp=st.sampled_from([0.0, 0.75, 3.0, 9.0, 100.0]), seed=st.integers(0, 2 ** 16))
+def test_producer_splat_matches_the_oracle(H, W, C, B, kind, amp, seed):
+    """slr_producer_splat_fwd / _bwd (the fused training producer) on random shapes / flows."""
+    rng = np.random.default_rng(seed)
+    fs = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    zn = np.clip(rng.standard_normal((B, 1, H, W)) * 3 - 2, -20, 20).astype(np.float32)
+    flow = np.concatenate([_motion(kind, H, W, rng, amp) for _ in range(B)], 0)
+    alpha = rng.uniform(0.0, 1.0, B).astype(np.float32)
+    gacc = rng.standard_normal((B, C + 1, H, W)).astype(np.float32)
+    acc = np.full((B, C + 1, H, W), np.nan, np.float32)
+    emu.call("slr_producer_splat_fwd", emu.p(fs), emu.p(zn), emu.p(flow), emu.p(alpha), emu.p(acc), B, C, H, W, 0, None)
+    assert rel_err(acc, oracle.producer_splat(fs, zn, flow, alpha)[0]) <= TOL
+    d_fs, d_zn, d_flow = np.full_like(fs, np.nan), np.full_like(zn, np.nan), np.full_like(flow, np.nan)
+    emu.call("slr_producer_splat_bwd", emu.p(fs), emu.p(zn), emu.p(flow), emu.p(alpha), emu.p(gacc),
+             emu.p(d_fs), emu.p(d_zn), emu.p(d_flow), B, C, H, W, None)
+    w_fs, w_zn, w_flow = oracle.producer_splat_grads(fs, zn, flow, alpha, gacc)
+    assert rel_err(d_fs, w_fs) <= TOL and rel_err(d_zn, w_zn) <= TOL and rel_err(d_flow, w_flow) <= TOL
+
+
+def test_non_finite_flow_through_the_new_paths():
+    """NaN / inf flow: those sources miss the frame (as in the reference's range tests), nothing else is disturbed."""
+    rng = np.random.default_rng(3)
+    B, C, H, W = 1, 3, 12, 20
+    inp = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    flow = rng.uniform(-3, 3, (B, 2, H, W)).astype(np.float32)
+    flow[0, 0, 2, 3] = np.nan
+    flow[0, 1, 5, 7] = np.inf
+    flow[0, 0, 8, 1] = -np.inf
+    nb = emu.lib().slr_softsplat_gather_scratch_bytes(C, H, W)
+    out = np.full_like(inp, np.nan)
+    emu.call("slr_softsplat_sum_fwd_gather", emu.p(inp), emu.p(flow), emu.p(out), B, C, H, W, emu.p(emu.aligned(nb)), nb, None)
+    ref = np.full_like(inp, np.nan)
+    emu.call("slr_softsplat_sum_fwd", emu.p(inp), emu.p(flow), emu.p(ref), B, C, H, W, 1, None)
+    assert np.isfinite(out).all() and rel_err(out, ref) <= 1e-5
+    zn = rng.standard_normal((B, 1, H, W)).astype(np.float32)
+    alpha = np.array([0.4], np.float32)
+    acc = np.full((B, C + 1, H, W), np.nan, np.float32)
+    emu.call("slr_producer_splat_fwd", emu.p(inp), emu.p(zn), emu.p(flow), emu.p(alpha), emu.p(acc), B, C, H, W, 0, None)
+    assert np.isfinite(acc).all()
+    d_fs, d_zn = np.full_like(inp, np.nan), np.full_like(zn, np.nan)
+    emu.call("slr_producer_splat_bwd", emu.p(inp), emu.p(zn), emu.p(flow), emu.p(alpha), emu.p(np.ones_like(acc)),
+             emu.p(d_fs), emu.p(d_zn), None, B, C, H, W, None)
+    assert np.isfinite(d_fs).all() and np.isfinite(d_zn).all()
+    assert d_fs[0, :, 2, 3].tolist() == [0.0] * C and d_fs[0, :, 5, 7].tolist() == [0.0] * C
